@@ -1,0 +1,24 @@
+"""asg-b200: B200-native engine for AdaptiveSG.jl's hot path (batched hat-basis sparse-grid
+evaluation). The directory name carries a dot, so import it through the repo-root shim::
+
+    import asg_b200 as asg
+    G = asg.SparseGridInterpolant(3)
+    asg.train(G, f, 7, 5)
+    y = G.evaluate(X)
+
+Layout: ``csrc/`` CUDA kernels + C ABI (-> ``lib/libasg_cuda.so``), ``_capi.py`` ctypes binding,
+``interpolant.py`` host mirror of the reference interface, ``parallel.py`` point sharding over
+``torch.distributed``, ``julia/`` the ccall shim for the reference package.
+"""
+from . import _capi
+from ._capi import AsgError, InvalidNodeError, LIB_PATH, init, launch_count
+from .interpolant import (SparseGridInterpolant, adapt, allindices_of_level, basis, child, coefficients,
+                          dehierarchization_matrix, deserialize, hierarchization_matrix, isbig2add, isvalid,
+                          maxlevels, nodedepth, rsg, serialize, stack, train)
+
+__all__ = [
+    "SparseGridInterpolant", "rsg", "train", "adapt", "coefficients", "basis", "dehierarchization_matrix",
+    "hierarchization_matrix", "serialize", "deserialize", "maxlevels", "stack", "nodedepth", "isvalid",
+    "allindices_of_level", "child", "isbig2add", "AsgError", "InvalidNodeError", "init", "launch_count",
+    "LIB_PATH",
+]

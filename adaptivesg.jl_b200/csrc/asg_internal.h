@@ -1,0 +1,124 @@
+// asg_internal.h -- shared declarations of libasg_cuda.so (host packer, kernels, C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "asg_cuda.h"
+
+namespace asg {
+
+constexpr int kMaxDim = ASG_MAX_DIM;
+constexpr int kMaxDimFast = ASG_MAX_DIM_FAST;
+constexpr int kKeyBits = 30;        // per-dimension cell key q = floor(x01 * 2^30), clamped to 2^30-1
+constexpr int kMaxLevelFast = 32;   // cell bits of a level: b(l) = 0, 1, l-2  ->  l <= 32
+constexpr int kMaxPosBits = 32;     // position of a node inside its subspace must fit a uint32
+
+// ---- level-vector trie (device layout) -------------------------------------------------------
+// One record per trie node. Level k of the trie fixes the hierarchical level of dimension k.
+//   inner node (k < D-1): x = index of its first child in level k+1 (children are contiguous and
+//                         sorted by level; the end is the next record's x, a sentinel closes the array)
+//   leaf       (k = D-1): x = first coefficient slot of the subspace (dense) or first hash slot
+//   y: bits 0..7 level, bit 8 = hashed subspace, bits 16..23 = log2(hash table size)
+struct TrieRec {
+  uint32_t x;
+  uint32_t y;
+};
+constexpr uint32_t kRecHashed = 1u << 8;
+
+struct HashEnt {  // open addressing, linear probing; key = pos + 1 (0 = empty)
+  unsigned long long key;
+  double coef;
+};
+
+struct SweepDim {  // one (node, dimension) of the sweep engine: phi = hat(x*s - c)
+  double s;        // 2^(l-1), or 0 for l == 1
+  double c;        // (double) i, or 0 for l == 1
+};
+
+// Everything the kernels need, passed by value as a kernel parameter.
+struct DeviceGrid {
+  int D;
+  double lb[kMaxDim];
+  double width[kMaxDim];  // ub - lb, rounded once like (from_ub .- from_lb), src/math.jl:308
+  // subspace engine
+  const TrieRec *rec[kMaxDimFast];  // per trie level, each with a sentinel record
+  uint32_t n_root;                  // records in level 0
+  const double *coef;               // dense subspace blocks (zero padded)
+  const int32_t *orig;              // slot -> caller's node number, -1 = padding
+  const HashEnt *hent;              // hashed subspaces
+  const int32_t *horig;
+  // sweep engine (caller's node order)
+  int64_t N;
+  const SweepDim *sw;       // [N][D]
+  const uint64_t *sw_low;   // bit d set: l_nd <= 2 (phi is 0 outside [0,1] whatever the formula says)
+  const double *sw_coef;    // [N]
+  const int32_t *sw_depth;  // [N]
+};
+
+// ---- host-side packed grid -------------------------------------------------------------------
+struct PackResult {
+  bool canonical = false;
+  std::string why;  // why the grid is not canonical (empty when it is)
+  int max_level = 0;
+  int64_t max_depth = 0;
+  int64_t subspaces = 0, dense_subspaces = 0, trie_nodes = 0;
+  std::vector<std::vector<TrieRec>> rec;  // [D] levels, sentinel included
+  std::vector<double> coef;
+  std::vector<int32_t> orig;
+  std::vector<HashEnt> hent;
+  std::vector<int32_t> horig;
+  std::vector<int64_t> slot_of_node;  // >= 0: dense slot; < 0: -(hash slot) - 1
+  // sweep engine
+  std::vector<SweepDim> sw;
+  std::vector<uint64_t> sw_low;
+  std::vector<int32_t> depth;
+};
+
+// Validate + pack. levels/indices: row-major N x D copies owned by the caller. Returns ASG_OK,
+// ASG_EINVALID_NODE (and err) or ASG_EUNSUPPORTED.
+int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, const double *coefs,
+              PackResult &out, std::string &err);
+
+// ---- kernel launchers (asg_kernels_*.cu) -------------------------------------------------------
+struct EvalArgs {
+  const double *X;   // device
+  int64_t M, sp, sd;
+  int rem;             // depth budget: sum(l-1) <= rem  (INT_MAX/2: no mask)
+  const double *fvals; // optional: out = fvals - G
+  double *out;
+};
+struct BasisArgs {
+  const double *X;
+  int64_t M, sp, sd;
+  double atol;
+  int dropzeros;
+  int mode;                 // 0 count, 1 fill CSR, 2 dense
+  unsigned long long *row_nnz;     // mode 0 (device)
+  const long long *row_ptr;        // mode 1
+  long long *colidx;               // mode 1
+  double *vals;                    // mode 1
+  double *dense;                   // mode 2
+  int64_t ldm, ldn;
+};
+
+cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_basis_subspace(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_basis_sweep(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);
+// node coordinates: li = [n][D] pairs (level, index) as int64x2, Xout element (k,d) at k*sp + d*sd
+cudaError_t launch_nodes_x(int D, const double *lb_dev_or_null, const DeviceGrid &g, const long long *lev,
+                           const long long *idx, int64_t n, double *Xout, int64_t sp, int64_t sd, int *bad,
+                           cudaStream_t st, int64_t *launches);
+cudaError_t launch_scatter_f64(double *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,
+                               int64_t *launches);
+cudaError_t launch_scatter_hash(HashEnt *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,
+                                int64_t *launches);
+cudaError_t launch_fp64_peak(int iters, double *sink, cudaStream_t st, int64_t *launches, int *blocks, int *threads);
+cudaError_t launch_sort_rows(const long long *row_ptr, long long *colidx, double *vals, int64_t M, cudaStream_t st,
+                             int64_t *launches);
+
+}  // namespace asg

@@ -1,0 +1,193 @@
+// asg_pack.cpp -- host-side packing of the reference node store (src/class.jl:281-293: levels,
+// indices :: Matrix{Int} N x D, coefs :: Vector{Float64}) into the two device layouts:
+//
+//  (1) SWEEP layout, caller's node order: per (node, dim) the pair (s, c) with phi = hat(x*s - c),
+//      s = 2^(l-1) and c = i for l >= 2 (src/math.jl:347-351; the l == 2 forms are the same function
+//      on [0,1]), s = c = 0 for l == 1 (src/math.jl:352-353). Works for every node set phi accepts.
+//
+//  (2) SUBSPACE layout, for "canonical" grids (every node passes isvalid, src/math.jl:418-448, has
+//      an in-range index, appears once, and all coefficients are finite): nodes are grouped by level
+//      vector ("subspace"). In one subspace the supports of the nodes tile [0,1]^D, so a point has
+//      exactly one supporting node there and its position inside the subspace follows from the bits
+//      of the point's coordinates. Subspaces are sorted lexicographically and organised as a trie
+//      over dimensions so that prefix products are shared. A well filled subspace is stored as a
+//      full block of 2^bits coefficients (missing nodes are 0.0), a sparsely filled one (adapt!
+//      output) as a small open-addressing hash table keyed by the position.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "asg_internal.h"
+
+namespace asg {
+
+static inline int cell_bits(int l) { return l == 1 ? 0 : (l == 2 ? 1 : l - 2); }
+
+static inline uint32_t hash_slot(uint32_t pos, int lg) {
+  // multiplicative hash; must match hash_slot() in asg_kernels_subspace.cu
+  return lg == 0 ? 0u : (uint32_t)((pos * 0x9E3779B1u) >> (32 - lg));
+}
+
+int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, const double *coefs,
+              PackResult &out, std::string &err) {
+  out = PackResult();
+  out.sw.resize((size_t)N * D);
+  out.sw_low.assign((size_t)N, 0);
+  out.depth.resize((size_t)N);
+  out.slot_of_node.assign((size_t)N, 0);
+
+  bool canonical = (D <= kMaxDimFast);
+  std::string why = canonical ? "" : "D > ASG_MAX_DIM_FAST";
+  auto demote = [&](const char *w) {
+    if (canonical) { canonical = false; why = w; }
+  };
+
+  std::vector<uint8_t> lv;   // N x D level bytes (canonical path only)
+  std::vector<uint32_t> pos; // position inside the subspace
+  if (canonical) { lv.resize((size_t)N * D); pos.resize((size_t)N); }
+
+  int max_level = 0;
+  int64_t max_depth = 0;
+  for (int64_t n = 0; n < N; ++n) {
+    int64_t dsum = 0;
+    uint64_t p = 0;
+    int tb = 0;
+    for (int d = 0; d < D; ++d) {
+      const int64_t l = levels[n * D + d], i = indices[n * D + d];
+      // the rule of phi(x, l, i), src/math.jl:345-357: these are the pairs it throws on
+      if (l < 1 || (l == 2 && i != 0 && i != 2)) {
+        err = "invalid level-index pair (" + std::to_string(l) + ", " + std::to_string(i) + ") at node " +
+              std::to_string(n) + ", dim " + std::to_string(d);
+        return ASG_EINVALID_NODE;
+      }
+      if (l > 62) { err = "level > 62 is not supported"; return ASG_EUNSUPPORTED; }
+      dsum += l;
+      max_level = std::max<int>(max_level, (int)l);
+      SweepDim &s = out.sw[(size_t)n * D + d];
+      if (l == 1) {
+        s.s = 0.0; s.c = 0.0;
+        out.sw_low[n] |= (1ull << d);
+        if (i != 1) demote("level-1 index != 1");
+      } else {
+        s.s = std::ldexp(1.0, (int)(l - 1));  // power2(l-1), src/math.jl:59-61
+        s.c = (double)i;                       // Int -> Float64 promotion in x*2^(l-1) - i
+        if (l == 2) out.sw_low[n] |= (1ull << d);
+      }
+      if (canonical) {
+        if (l > kMaxLevelFast) { demote("level > 32"); continue; }
+        if (l > 2 && (i < 1 || !(i & 1) || i > ((int64_t)1 << (l - 1)) - 1)) { demote("index out of range"); continue; }
+        const int b = cell_bits((int)l);
+        const uint64_t cell = l == 1 ? 0 : (l == 2 ? (uint64_t)(i >> 1) : (uint64_t)((i - 1) >> 1));
+        tb += b;
+        if (tb > kMaxPosBits) { demote("subspace position needs more than 32 bits"); continue; }
+        p = (b ? (p << b) : p) | cell;
+        lv[(size_t)n * D + d] = (uint8_t)l;
+      }
+    }
+    const int64_t depth = dsum - D + 1;
+    if (depth > 0x3fffffff) { err = "depth overflow"; return ASG_EUNSUPPORTED; }
+    out.depth[n] = (int32_t)depth;
+    max_depth = std::max(max_depth, depth);
+    if (canonical) pos[n] = (uint32_t)p;
+  }
+  out.max_level = max_level;
+  out.max_depth = max_depth;
+  if (N >= 0x7fffffff) demote("N >= 2^31");
+
+  if (canonical && N > 0) {
+    std::vector<int64_t> perm((size_t)N);
+    std::iota(perm.begin(), perm.end(), (int64_t)0);
+    const uint8_t *L = lv.data();
+    std::sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
+      const int c = std::memcmp(L + (size_t)a * D, L + (size_t)b * D, (size_t)D);
+      if (c) return c < 0;
+      if (pos[a] != pos[b]) return pos[a] < pos[b];
+      return a < b;
+    });
+    out.rec.assign((size_t)D, {});
+    const uint8_t *prev = nullptr;
+    int64_t g0 = 0;
+    while (g0 < N && canonical) {
+      const uint8_t *cur = L + (size_t)perm[g0] * D;
+      int64_t g1 = g0 + 1;
+      while (g1 < N && std::memcmp(L + (size_t)perm[g1] * D, cur, (size_t)D) == 0) {
+        if (pos[perm[g1]] == pos[perm[g1 - 1]]) { demote("duplicate node"); break; }
+        ++g1;
+      }
+      if (!canonical) break;
+      const int64_t cnt = g1 - g0;
+      int tb = 0;
+      for (int d = 0; d < D; ++d) tb += cell_bits(cur[d]);
+      const uint64_t full = 1ull << tb;
+      uint32_t base, flags = 0;
+      if (full <= (uint64_t)std::max<int64_t>(4, 2 * cnt)) {
+        if (out.coef.size() + full >= 0xffffffffull) { demote("coefficient slots >= 2^32"); break; }
+        base = (uint32_t)out.coef.size();
+        out.coef.resize(out.coef.size() + full, 0.0);
+        out.orig.resize(out.orig.size() + full, -1);
+        for (int64_t k = g0; k < g1; ++k) {
+          const int64_t n = perm[k];
+          const size_t slot = (size_t)base + pos[n];
+          out.coef[slot] = coefs ? coefs[n] : 0.0;
+          out.orig[slot] = (int32_t)n;
+          out.slot_of_node[n] = (int64_t)slot;
+        }
+        ++out.dense_subspaces;
+      } else {
+        int lg = 1;
+        while ((1ll << lg) < 2 * cnt) ++lg;
+        const uint64_t size = 1ull << lg;
+        if (out.hent.size() + size >= 0xffffffffull) { demote("hash slots >= 2^32"); break; }
+        base = (uint32_t)out.hent.size();
+        out.hent.resize(out.hent.size() + size, HashEnt{0ull, 0.0});
+        out.horig.resize(out.horig.size() + size, -1);
+        for (int64_t k = g0; k < g1; ++k) {
+          const int64_t n = perm[k];
+          uint32_t s = hash_slot(pos[n], lg);
+          while (out.hent[(size_t)base + s].key != 0ull) s = (s + 1) & (uint32_t)(size - 1);
+          out.hent[(size_t)base + s] = HashEnt{(unsigned long long)pos[n] + 1ull, coefs ? coefs[n] : 0.0};
+          out.horig[(size_t)base + s] = (int32_t)n;
+          out.slot_of_node[n] = -(int64_t)((size_t)base + s) - 1;
+        }
+        flags = kRecHashed | ((uint32_t)lg << 16);
+      }
+      // trie: open new records from the first dimension whose level differs from the previous subspace
+      int k0 = 0;
+      if (prev) while (k0 < D - 1 && prev[k0] == cur[k0]) ++k0;
+      for (int k = k0; k < D; ++k) {
+        TrieRec r;
+        r.y = cur[k];
+        if (k < D - 1) {
+          r.x = (uint32_t)out.rec[(size_t)k + 1].size();
+        } else {
+          r.x = base;
+          r.y |= flags;
+        }
+        out.rec[(size_t)k].push_back(r);
+      }
+      prev = cur;
+      ++out.subspaces;
+      g0 = g1;
+    }
+    if (canonical) {
+      for (int k = 0; k < D; ++k) {
+        out.trie_nodes += (int64_t)out.rec[(size_t)k].size();
+        TrieRec s;
+        s.x = (k < D - 1) ? (uint32_t)out.rec[(size_t)k + 1].size() : 0u;
+        s.y = 0xffu;  // level 255: terminates every masked walk
+        // the sentinel of level k+1 is pushed after this one, so .size() above is the real count
+        out.rec[(size_t)k].push_back(s);
+      }
+    }
+  }
+  if (!canonical) {
+    out.rec.clear(); out.coef.clear(); out.orig.clear(); out.hent.clear(); out.horig.clear();
+    out.subspaces = out.dense_subspaces = out.trie_nodes = 0;
+  }
+  out.canonical = canonical && N > 0;
+  out.why = why;
+  return ASG_OK;
+}
+
+}  // namespace asg

@@ -1,0 +1,570 @@
+"""Host-side mirror of AdaptiveSG.jl's interface for the hot path, on top of libasg_cuda.so.
+
+The reference is Julia (absent from this image), so this mirror is Python: same names, argument
+meaning and error behaviour as the reference methods it stands for, numpy arrays where Julia has
+``Matrix{Int}`` / ``Vector{Float64}``.  Julia's ``train!`` / ``adapt!`` / ``rsg!`` are ``train`` /
+``adapt`` / ``rsg`` here (``!`` is not an identifier character in Python).  The Julia-side shim with
+the identical structure is ``julia/AdaptiveSGCUDA.jl``.
+
+Everything numerical happens on the GPU through the C ABI: evaluation (src/class.jl:629-680,
+747-761), node coordinates (src/math.jl:464-497), the residual step of train!/adapt!
+(src/train.jl:176-183, 362-363) and the basis rows (src/class.jl:434-567).  What stays on the host
+is what the north star keeps on the host: node enumeration (src/train.jl:40-78), child generation
+and the acceptance test (src/train.jl:337-398, src/math.jl:257-274, 418-448, 907-959) and the user
+callback ``f``.  There is no CPU evaluation fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import AsgError, InvalidNodeError, check, f64p, i64p
+
+__all__ = [
+    "SparseGridInterpolant", "rsg", "train", "adapt", "coefficients", "basis", "dehierarchization_matrix",
+    "hierarchization_matrix", "serialize", "deserialize", "maxlevels", "stack", "nodedepth", "isvalid",
+    "allindices_of_level", "child", "isbig2add", "AsgError", "InvalidNodeError",
+]
+
+_NODE_FIELDS = ("levels", "indices", "depths", "coefs", "lb", "ub")
+
+
+def _ptr(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class SparseGridInterpolant:
+    """Mirror of ``SparseGridInterpolant{D}`` (src/class.jl:281-319).
+
+    Public fields as in the reference: ``lb, ub`` (tuples), ``levels, indices`` (N x D int64),
+    ``depths`` (N int64), ``fvals, coefs`` (N float64).  The numpy arrays are the source of truth; the
+    device copy is a cache that is rebuilt when a field is re-assigned.  In-place edits of an array
+    (``G.coefs[3] = 1.0``) are invisible to Python -- call ``G.sync()`` afterwards.
+    """
+
+    def __init__(self, xdim: int, lb=None, ub=None):
+        # asserts of src/class.jl:301-306, same messages
+        assert xdim > 0, "Dimension must be positive."
+        lb = np.zeros(xdim) if lb is None else np.asarray(lb, dtype=np.float64).reshape(-1)
+        ub = np.ones(xdim) if ub is None else np.asarray(ub, dtype=np.float64).reshape(-1)
+        assert len(lb) == xdim, "Lower bound must match dimension."
+        assert len(ub) == xdim, "Upper bound must match dimension."
+        assert np.all(ub > lb), "Upper bound must be greater than lower bound."
+        assert np.all(np.isfinite(lb)), "Lower bound must be finite."
+        assert np.all(np.isfinite(ub)), "Upper bound must be finite."
+        object.__setattr__(self, "_handle", None)
+        object.__setattr__(self, "_dirty", True)
+        object.__setattr__(self, "_D", int(xdim))
+        self.lb = tuple(float(v) for v in lb)
+        self.ub = tuple(float(v) for v in ub)
+        self.levels = np.empty((0, xdim), dtype=np.int64)
+        self.indices = np.empty((0, xdim), dtype=np.int64)
+        self.depths = np.empty(0, dtype=np.int64)
+        self.fvals = np.empty(0, dtype=np.float64)
+        self.coefs = np.empty(0, dtype=np.float64)
+
+    # -- device mirror ---------------------------------------------------------------------------
+    def __setattr__(self, name, value):
+        if name in _NODE_FIELDS:
+            object.__setattr__(self, "_dirty", True)
+        object.__setattr__(self, name, value)
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None:
+            try:
+                _capi.load().asg_grid_destroy(h)
+            except Exception:
+                pass
+
+    def _grid(self):
+        """Create the device handle on first use (needs a B200: raises AsgError otherwise)."""
+        if self._handle is None or self._handle_bounds != (self.lb, self.ub):
+            _capi.init()
+            if self._handle is not None:
+                _capi.load().asg_grid_destroy(self._handle)
+            h = C.c_void_p()
+            lb = np.asarray(self.lb, dtype=np.float64)
+            ub = np.asarray(self.ub, dtype=np.float64)
+            check(_capi.load().asg_grid_create(self._D, _ptr(lb, f64p), _ptr(ub, f64p), C.byref(h)))
+            object.__setattr__(self, "_handle", h)
+            object.__setattr__(self, "_handle_bounds", (self.lb, self.ub))
+            object.__setattr__(self, "_dirty", True)
+        return self._handle
+
+    def sync(self):
+        """Push the host arrays to the device (full replace, like rsg!/deserialize do to the struct)."""
+        h = self._grid()
+        Lv = np.ascontiguousarray(self.levels, dtype=np.int64)
+        Ix = np.ascontiguousarray(self.indices, dtype=np.int64)
+        cf = np.ascontiguousarray(self.coefs, dtype=np.float64)
+        N = Lv.shape[0]
+        assert Lv.shape == (N, self._D) and Ix.shape == (N, self._D) and cf.shape == (N,), "inconsistent node arrays"
+        check(_capi.load().asg_grid_upload(h, N, _ptr(Lv, i64p), _ptr(Ix, i64p), self._D, 1, _ptr(cf, f64p)))
+        object.__setattr__(self, "_dirty", False)
+        return self
+
+    def _ensure(self):
+        h = self._grid()
+        if self._dirty:
+            self.sync()
+        return h
+
+    def info(self) -> dict:
+        gi = _capi.GridInfo()
+        check(_capi.load().asg_grid_info(self._ensure(), C.byref(gi)))
+        return gi.as_dict()
+
+    def set_path(self, path: str = "auto"):
+        code = {"auto": _capi.ASG_PATH_AUTO, "sweep": _capi.ASG_PATH_SWEEP, "subspace": _capi.ASG_PATH_SUBSPACE}[path]
+        check(_capi.load().asg_grid_set_path(self._ensure(), code))
+        return self
+
+    # -- Base overloads of src/class.jl:331-366 ---------------------------------------------------
+    def __len__(self):
+        return len(self.fvals)
+
+    @property
+    def ndims(self):
+        return self._D
+
+    @property
+    def size(self):
+        return (len(self.fvals), self._D)
+
+    def __contains__(self, x):
+        x = np.asarray(x, dtype=np.float64)
+        assert len(x) == self._D, "Input point must match the dimension of the grid."
+        return bool(np.all(x >= np.asarray(self.lb)) and np.all(x <= np.asarray(self.ub)))
+
+    def clamp(self, x):
+        return np.clip(np.asarray(x, dtype=np.float64), self.lb, self.ub)
+
+    def rand(self, n: int | None = None, rng=None):
+        """rand(G) / rand(G, n); note the reference returns a D x n matrix (src/class.jl:357-361)."""
+        rng = np.random.default_rng() if rng is None else rng
+        lb, ub = np.asarray(self.lb), np.asarray(self.ub)
+        if n is None:
+            return rng.random(self._D) * (ub - lb) + lb
+        return rng.random((self._D, n)) * (ub - lb)[:, None] + lb[:, None]
+
+    def linrange(self, d: int, n: int):
+        assert 1 <= d <= self._D, "Dimension index must be in [1, D]."
+        return np.linspace(self.lb[d - 1], self.ub[d - 1], n)
+
+    def __repr__(self):
+        s = f"SparseGridInterpolant f(x): R^{self._D} --> R\n#nodes: {len(self)}\nDomain:\n"
+        for d in range(self._D):
+            s += f"  x[{d + 1}] in [{self.lb[d]:.2f}, {self.ub[d]:.2f}]\n"
+        return s
+
+    # -- evaluation: src/class.jl:747-761 -> 629-643 ------------------------------------------------
+    def evaluate(self, X, max_depth: int | None = None, dims: int = 1, out=None) -> np.ndarray:
+        """Batched ``[G(x) for x in eachrow(X)]`` (``dims=1``, rows are points, the convention of
+        ``basis``) or ``eachcol`` (``dims=2``, what ``rand(G, n)`` returns).  No transpose is made:
+        the element strides go straight to the C ABI.  ``max_depth`` restricts the sum to nodes with
+        ``depth <= max_depth`` (``_interpolate_until_level``, src/class.jl:666-680)."""
+        X = np.asarray(X, dtype=np.float64)
+        assert X.ndim == 2, "X must be a matrix"
+        if dims == 2:
+            X = X.T
+        assert X.shape[1] == self._D, "Input point must match the dimension of the grid."
+        M = X.shape[0]
+        if out is None:
+            out = np.empty(M, dtype=np.float64)
+        assert out.shape == (M,) and out.dtype == np.float64 and out.flags.c_contiguous
+        h = self._ensure()
+        sp, sd = X.strides[0] // 8, X.strides[1] // 8
+        if M and (sp < 0 or sd < 0 or X.strides[0] % 8 or X.strides[1] % 8):
+            X = np.ascontiguousarray(X)
+            sp, sd = self._D, 1
+        check(_capi.load().asg_eval(h, _vp(X), M, sp, sd, -1 if max_depth is None else int(max_depth), _vp(out)))
+        return out
+
+    def __call__(self, x, safe: bool = True, extrapolate: bool = False):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 2:  # additive API: batched rows
+            return self.evaluate(x)
+        if safe:  # the reference accepts `safe` and checks nothing; the mirror does check
+            assert x.shape == (self._D,), "Input point must match the dimension of the grid."
+        if extrapolate and (x in self):
+            # src/class.jl:752-754 calls the undefined `__extrapolate` for in-domain x (UndefVarError)
+            raise NameError("__extrapolate not defined (reference defect, src/class.jl:754)")
+        return float(self.evaluate(x[None, :])[0])
+
+    def surplus(self, X, fvals, max_depth: int | None = None) -> np.ndarray:
+        """alpha = fvals - G_{depth<=max_depth}(X): the residual step of src/train.jl:176-183, 362-363."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        fvals = np.ascontiguousarray(fvals, dtype=np.float64)
+        M = X.shape[0]
+        assert X.shape == (M, self._D) and fvals.shape == (M,)
+        out = np.empty(M, dtype=np.float64)
+        check(_capi.load().asg_surplus(self._ensure(), _vp(X), M, self._D, 1, _vp(fvals),
+                                       -1 if max_depth is None else int(max_depth), _vp(out)))
+        return out
+
+    def nodes_x(self, levels=None, indices=None) -> np.ndarray:
+        """get_x rows (src/math.jl:490-497), computed on the device. Defaults to all grid nodes."""
+        if levels is None:
+            return stack(self)
+        Lv = np.ascontiguousarray(levels, dtype=np.int64)
+        Ix = np.ascontiguousarray(indices, dtype=np.int64)
+        n = Lv.shape[0]
+        out = np.empty((n, self._D), dtype=np.float64)
+        check(_capi.load().asg_nodes_x_li(self._grid(), n, _ptr(Lv, i64p), _ptr(Ix, i64p), self._D, 1,
+                                          _ptr(out, f64p), self._D, 1))
+        return out
+
+
+# -------------------------------------------------------------------------------------------------
+# node arithmetic kept on the host (integer-only; src/math.jl)
+# -------------------------------------------------------------------------------------------------
+def nodedepth(ls) -> int:
+    """src/math.jl:103-108"""
+    ls = np.asarray(ls)
+    return int(ls.sum() - len(ls) + 1)
+
+
+def isvalid(Ls, Is) -> bool:
+    """src/math.jl:418-448"""
+    Ls, Is = np.asarray(Ls), np.asarray(Is)
+    if Ls.ndim != 1 or len(Ls) < 1 or len(Is) != len(Ls):
+        return False
+    return bool(_valid_rows(Ls[None, :], Is[None, :])[0])
+
+
+def _valid_rows(L, I):
+    ok1 = (L == 1) & (I == 1)
+    ok2 = (L == 2) & ((I == 0) | (I == 2))
+    ok3 = (L > 2) & (I >= 1) & ((I & 1) == 1)
+    return np.all(ok1 | ok2 | ok3, axis=1) & ((L.sum(axis=1) - L.shape[1] + 1) >= 1)
+
+
+def allindices_of_level(l: int) -> np.ndarray:
+    """src/math.jl:651-661"""
+    if l > 2:
+        return np.arange(1, (1 << (l - 1)), 2, dtype=np.int64)
+    if l == 2:
+        return np.array([0, 2], dtype=np.int64)
+    if l == 1:
+        return np.array([1], dtype=np.int64)
+    raise ValueError(f"invalid level {l}")
+
+
+def child(Ls, Is, dims: int, side: str = "left"):
+    """src/math.jl:907-985 (``dims`` is 1-based like the reference)."""
+    if side not in ("left", "right"):
+        raise ValueError("side must be :left or :right")
+    L = np.array(Ls, dtype=np.int64)
+    I = np.array(Is, dtype=np.int64)
+    nl, ni = _children(L[None, dims - 1], I[None, dims - 1], side == "right")
+    L[dims - 1], I[dims - 1] = nl[0], ni[0]
+    return L, I
+
+
+def _children(l, i, right: bool):
+    """vectorised _child_left / _child_right (src/math.jl:907-959)."""
+    if np.any((l < 1) | ((l == 2) & (i != 0) & (i != 2))):
+        raise ValueError("invalid level-index pair")
+    if right:
+        inew = np.where(l > 2, 2 * i + 1, np.where(l == 1, 2, np.where(i == 0, 1, -1)))
+    else:
+        inew = np.where(l > 2, 2 * i - 1, np.where(l == 1, 0, np.where(i == 0, -1, 3)))
+    return l + 1, inew
+
+
+def isbig2add(alpha, fx, rtol, atol, use_rtol):
+    """src/math.jl:257-274, vectorised; isapprox(fx, 0, atol = rtol) is |fx| <= rtol."""
+    alpha, fx = np.asarray(alpha), np.asarray(fx)
+    if use_rtol:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return np.where(np.abs(fx) <= rtol, np.abs(alpha) > rtol, (np.abs(alpha) / np.abs(fx)) > rtol)
+    return np.abs(alpha) > atol
+
+
+# -------------------------------------------------------------------------------------------------
+# interface methods (src/class.jl:375-416)
+# -------------------------------------------------------------------------------------------------
+def stack(G: SparseGridInterpolant) -> np.ndarray:
+    """N x D node coordinates (src/class.jl:375-387), generated on the device."""
+    N = len(G.levels)
+    out = np.empty((N, G.ndims), dtype=np.float64)
+    if N:
+        check(_capi.load().asg_nodes_x(G._ensure(), 0, N, _ptr(out, f64p), G.ndims, 1))
+    return out
+
+
+def maxlevels(G: SparseGridInterpolant) -> np.ndarray:
+    """src/class.jl:401-407"""
+    if len(G.levels) == 0:
+        return np.zeros(G.ndims, dtype=np.int64)
+    return np.asarray(G.levels).max(axis=0)
+
+
+def coefficients(G: SparseGridInterpolant) -> np.ndarray:
+    """src/class.jl:414-416: the coefficient vector itself (an alias, not a copy)."""
+    return G.coefs
+
+
+# -------------------------------------------------------------------------------------------------
+# basis family (src/class.jl:434-567)
+# -------------------------------------------------------------------------------------------------
+def basis(*args, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16, dense: bool = False):
+    """``basis(x, G)`` / ``basis(Xs, G)`` / ``basis(G)`` (src/class.jl:434-454, 483-503, 521-538).
+
+    Documented intent (the reference body multiplies an all-zero sparse vector):
+    row m, column n is ``prod_d phi(x01_md; l_nd, i_nd)``; entries ``< atol`` are dropped when
+    ``dropzeros``; exact zeros are always dropped.  Returns a ``scipy.sparse.csc_matrix`` of shape
+    (M, N) (1 x N for a single point), or a dense ndarray with ``dense=True``.  ``safe`` is accepted
+    on all three methods (the reference forwards it to a method that lacks it)."""
+    import scipy.sparse as sps
+
+    if len(args) == 1:
+        G = args[0]
+        if len(G.levels) == 0:
+            return sps.csc_matrix((0, len(G)))
+        X = stack(G)
+    else:
+        X, G = args
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim == 1:
+            X = X[None, :]
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    M, D = X.shape
+    assert D == G.ndims, "Input point must match the dimension of the grid."
+    N = len(G)
+    h = G._ensure()
+    lib = _capi.load()
+    if dense:
+        out = np.empty((M, N), dtype=np.float64)
+        check(lib.asg_basis_dense(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _vp(out), N, 1))
+        return out
+    nnz = np.zeros(M, dtype=np.int64)
+    check(lib.asg_basis_count(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(nnz, i64p)))
+    ptr = np.zeros(M + 1, dtype=np.int64)
+    np.cumsum(nnz, out=ptr[1:])
+    col = np.empty(int(ptr[-1]), dtype=np.int64)
+    val = np.empty(int(ptr[-1]), dtype=np.float64)
+    check(lib.asg_basis_fill(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(col, i64p),
+                             _ptr(val, f64p)))
+    return sps.csr_matrix((val, col, ptr), shape=(M, N)).tocsc()
+
+
+def dehierarchization_matrix(G, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16):
+    """src/class.jl:555-567: identical to basis(G)."""
+    return basis(G, safe=safe, dropzeros=dropzeros, atol=atol)
+
+
+def hierarchization_matrix(G, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16):
+    """src/class.jl:591-604: sparse(E \\ I). A consumer of the hot path's output, solved on the host
+    with scipy (out of scope for the GPU path)."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+
+    E = dehierarchization_matrix(G, safe=safe, dropzeros=dropzeros, atol=atol).tocsc()
+    return sps.csc_matrix(spla.spsolve(E, sps.identity(E.shape[0], format="csc")))
+
+
+# -------------------------------------------------------------------------------------------------
+# I/O (src/io.jl:9-72): same keys, arrays aliased not copied
+# -------------------------------------------------------------------------------------------------
+def serialize(G: SparseGridInterpolant) -> dict:
+    return {"D": G.ndims, "lb": list(G.lb), "ub": list(G.ub), "levels": G.levels, "indices": G.indices,
+            "depths": G.depths, "fvals": G.fvals, "coefs": G.coefs}
+
+
+def deserialize(dat: dict) -> SparseGridInterpolant:
+    for k, msg in (("lb", "lower bound"), ("ub", "upper bound"), ("levels", "max_levels"), ("indices", "indices"),
+                   ("depths", "depths"), ("fvals", "fvals"), ("coefs", "coefs")):
+        assert k in dat, f"Serialized data must contain {msg}."
+    G = SparseGridInterpolant(dat["D"], lb=dat["lb"], ub=dat["ub"])
+    G.levels = dat["levels"]
+    G.indices = dat["indices"]
+    G.depths = dat["depths"]
+    G.fvals = dat["fvals"]
+    G.coefs = dat["coefs"]
+    return G
+
+
+# -------------------------------------------------------------------------------------------------
+# training (src/train.jl)
+# -------------------------------------------------------------------------------------------------
+def _level_vectors(D: int, budget: int, maxlevels) -> np.ndarray:
+    """Admissible level vectors of rsg! in Iterators.product order (dimension 1 fastest),
+    src/train.jl:56-57, enumerated with pruning instead of scanning the full product."""
+    out = []
+    ks = [1] * D
+
+    def rec(d: int, remaining: int):  # choose k_d for d = D-1 .. 0; `remaining` = budget left for dims <= d
+        if d < 0:
+            out.append(tuple(ks))
+            return
+        for k in range(1, min(int(maxlevels[d]), remaining - d) + 1):  # dims below d need >= 1 each
+            ks[d] = k
+            rec(d - 1, remaining - k)
+
+    rec(D - 1, budget)
+    return np.array(out, dtype=np.int64).reshape(-1, D)
+
+
+def rsg(G: SparseGridInterpolant, maxdepth: int, maxlevels) -> None:
+    """``rsg!`` (src/train.jl:40-78): fill G with the regular sparse grid node set, zero fvals/coefs."""
+    D = G.ndims
+    ml = np.full(D, int(maxlevels), dtype=np.int64) if np.isscalar(maxlevels) else np.asarray(maxlevels, dtype=np.int64)
+    if len(ml) != D:
+        raise ValueError("maxlevels must have D entries")
+    if np.any(ml < 1):
+        raise ValueError("maxlevels must be >= 1")
+    if maxdepth < 2:
+        raise ValueError("maxdepth must be >= 2")
+    lvs = _level_vectors(D, maxdepth + D - 1, ml)
+    Ls, Is = [], []
+    for ks in lvs:
+        per_dim = [allindices_of_level(int(k)) for k in ks]
+        # Iterators.product: first dimension fastest
+        mesh = np.meshgrid(*per_dim, indexing="ij")
+        idx = np.stack([m.reshape(-1, order="F") for m in mesh], axis=1)
+        Is.append(idx)
+        Ls.append(np.broadcast_to(ks, idx.shape))
+    G.levels = np.ascontiguousarray(np.concatenate(Ls, axis=0), dtype=np.int64)
+    G.indices = np.ascontiguousarray(np.concatenate(Is, axis=0), dtype=np.int64)
+    G.depths = G.levels.sum(axis=1) - D + 1
+    G.fvals = np.zeros(len(G.levels))
+    G.coefs = np.zeros(len(G.levels))
+
+
+def _apply_f(f, X: np.ndarray, vectorized: bool) -> np.ndarray:
+    if vectorized:
+        return np.ascontiguousarray(f(X), dtype=np.float64).reshape(len(X))
+    return np.array([float(f(x)) for x in X], dtype=np.float64)
+
+
+def train(G: SparseGridInterpolant, f, maxdepth: int, maxlevels, verbose: bool = False, vectorized: bool = False):
+    """``train!`` (src/train.jl:112-195). Per depth: node coordinates on the device, ``f`` on the
+    host, then ONE fused kernel call ``alpha = f - G_{depth<l}`` that also stores alpha as the
+    coefficients of that depth (src/train.jl:176-183).  ``vectorized=True`` calls ``f`` once per
+    depth with an (n, D) matrix instead of once per node."""
+    import time
+
+    rsg(G, maxdepth, maxlevels)
+    tic = time.time()
+    if verbose:
+        print(f"Regular sparse grid training starts\n# dimensions: {G.ndims}, # total nodes: {len(G)}")
+    h = G._ensure()
+    lib = _capi.load()
+    for lnow in range(1, maxdepth + 1):
+        idx = np.flatnonzero(G.depths == lnow).astype(np.int64)
+        if verbose:
+            print(f"Training level {lnow}/{maxdepth}... #nodes = {len(idx)}, ", end="")
+        if lnow == 1:
+            assert len(idx) == 1, "Only 1 root node (level = 1) allowed."
+            assert G.depths[0] == 1, "Root node depth must be in the 1st place."
+        if len(idx):
+            X = G.nodes_x(G.levels[idx], G.indices[idx])
+            fv = _apply_f(f, X, vectorized)
+            al = np.empty(len(idx), dtype=np.float64)
+            # depth 1: nothing is below the root, so alpha = f (src/train.jl:156-163)
+            check(lib.asg_surplus_nodes(h, len(idx), _ptr(idx, i64p), _ptr(fv, f64p), lnow - 1, 1, _ptr(al, f64p)))
+            G.fvals[idx] = fv
+            G.coefs[idx] = al  # host copy; the device copy was written by the kernel (store = 1)
+        if verbose:
+            print(f"Elapsed: {time.time() - tic:.2f} seconds.")
+    if verbose:
+        print(f"done in {time.time() - tic:.2f} seconds.")
+
+
+def adapt(G: SparseGridInterpolant, f2fit, maxdepth: int, verbose: bool = True, tol: float = 1e-3,
+          toltype: str = "absolute", parallel: bool = False, vectorized: bool = False, log: list | None = None):
+    """``adapt!`` (src/train.jl:235-463). Child generation, validity, acceptance and dedupe stay on
+    the host; all candidates of one level go through ONE surplus call against the whole current grid
+    (the grid is not mutated inside a level, src/train.jl:434-438).  ``parallel`` is accepted and
+    ignored: batching removes the threaded region.  New rows are appended in first-insertion order of
+    the reference's visiting order (for j, for parent, left then right); the reference's own row order
+    is Julia ``Dict`` iteration order, so compare node SETS."""
+    import time
+
+    assert len(G) > 0, "The grid structure in G is empty."
+    lnow = int(np.max(G.depths))
+    assert lnow <= maxdepth, "maxdepth must be >= current depth."
+    assert lnow > 0, "Ill-defined grid structure: maxdepth < 1 found."
+    toltype = toltype.lstrip(":")
+    if toltype == "absolute":
+        atol, rtol = tol, float("nan")
+    elif toltype == "relative":
+        atol, rtol = float("nan"), tol
+    else:
+        raise ValueError("toltype must be :absolute or :relative.")
+    D = G.ndims
+    lib = _capi.load()
+    if verbose:
+        print(f"Adaptive sparse grid adaption starts\n# dimensions: {D}, # current total nodes: {len(G)}, "
+              f"{toltype} tolerance: {tol}")
+    tic = time.time()
+    if lnow >= maxdepth:
+        if verbose:
+            print(f"Current depth {lnow} >= max depth {maxdepth}, stop adaption.")
+        return
+    while lnow < maxdepth:
+        parents = np.flatnonzero(G.depths == lnow)
+        if verbose:
+            print(f"level {lnow}/{maxdepth}, #parents: {len(parents)}, ", end="")
+        PL, PI = G.levels[parents], G.indices[parents]
+        cl, ci = [], []
+        for j in range(D):
+            ll, li = _children(PL[:, j], PI[:, j], False)
+            rl, ri = _children(PL[:, j], PI[:, j], True)
+            L2 = np.repeat(PL, 2, axis=0)
+            I2 = np.repeat(PI, 2, axis=0)
+            L2[0::2, j], I2[0::2, j] = ll, li
+            L2[1::2, j], I2[1::2, j] = rl, ri
+            ok = _valid_rows(L2, I2)
+            cl.append(L2[ok])
+            ci.append(I2[ok])
+        CL = np.concatenate(cl, axis=0) if cl else np.empty((0, D), np.int64)
+        CI = np.concatenate(ci, axis=0) if ci else np.empty((0, D), np.int64)
+        n_added = 0
+        if len(CL):
+            X = G.nodes_x(CL, CI)
+            fv = _apply_f(f2fit, X, vectorized)
+            al = G.surplus(X, fv)  # whole current grid
+            big = isbig2add(al, fv, rtol, atol, toltype == "relative")
+            if log is not None:
+                margin = float(np.min(np.abs(np.abs(al) - tol))) if toltype == "absolute" else float("nan")
+                log.append({"depth": lnow, "parents": len(parents), "candidates": len(CL), "min_margin": margin})
+            if np.any(big):
+                key = np.concatenate([CL[big], CI[big]], axis=1)
+                _, first = np.unique(key, axis=0, return_index=True)  # first insertion wins
+                first.sort()
+                sel = np.flatnonzero(big)[first]
+                n_added = len(sel)
+                newL, newI = CL[sel], CI[sel]
+                h = G._ensure()
+                check(lib.asg_grid_append(h, n_added, _ptr(np.ascontiguousarray(newL), i64p),
+                                          _ptr(np.ascontiguousarray(newI), i64p), D, 1,
+                                          _ptr(np.ascontiguousarray(al[sel]), f64p)))
+                # vcat onto the struct (src/train.jl:434-438) without invalidating the device copy
+                object.__setattr__(G, "levels", np.vstack([G.levels, newL]))
+                object.__setattr__(G, "indices", np.vstack([G.indices, newI]))
+                object.__setattr__(G, "depths", np.concatenate([G.depths, newL.sum(axis=1) - D + 1]))
+                G.fvals = np.concatenate([G.fvals, fv[sel]])
+                object.__setattr__(G, "coefs", np.concatenate([G.coefs, al[sel]]))
+        if log is not None and log and log[-1]["depth"] == lnow:
+            log[-1]["added"] = n_added
+        if n_added == 0:
+            if verbose:
+                print(f"\nConverged: no new nodes found. Elapsed: {time.time() - tic:.2f} seconds")
+            break
+        if verbose:
+            print(f"#added/#candidates/#total: {n_added}/{len(parents) * 2 * D}/{len(G)}, "
+                  f"Elapsed: {time.time() - tic:.2f} seconds.")
+        lnow += 1
+        if lnow == maxdepth:
+            if verbose:
+                print(f"Reached the maximum depth {maxdepth}. Elapsed: {time.time() - tic:.2f} seconds.")
+            break

@@ -1,0 +1,178 @@
+/*
+ * asg_cuda.h -- C ABI of libasg_cuda.so, the B200 (sm_100a) engine for AdaptiveSG.jl's hot path:
+ * batched evaluation of the hierarchical hat-basis interpolant
+ *
+ *      G(x) = sum_n c_n * prod_d phi(x01_d; l_nd, i_nd)
+ *
+ * The reference (pure Julia) has no FFI for this path; its boundary is the Julia method table.
+ * Each entry point below names the reference code (file:line in the AdaptiveSG.jl checkout) whose
+ * job it takes over.  A Julia package reaches these with plain `ccall` (see INTEGRATION.md and
+ * adaptivesg.jl_b200/julia/AdaptiveSGCUDA.jl); the Python mirror uses ctypes.
+ *
+ * Conventions
+ *  - every function returns an int32 status: 0 = ASG_OK, negative = ASG_E*; nothing throws across
+ *    the boundary; asg_last_error() returns a thread-local message for the last failure;
+ *  - no host pointer is retained after a call returns;
+ *  - matrices are addressed with explicit ELEMENT strides so that Julia's column-major
+ *    (row stride 1, column stride N) and C/numpy row-major layouts are both accepted without a copy;
+ *  - node arrays are Int64 like the reference's Matrix{Int} (src/class.jl:288-290);
+ *  - there is NO CPU fallback: without an sm_100 device every compute entry point fails with
+ *    ASG_ENODEVICE.
+ *  - calls on one handle are serialised by a per-handle mutex; different handles may be used
+ *    concurrently from different threads.
+ */
+#ifndef ASG_CUDA_H
+#define ASG_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASG_OK 0
+#define ASG_EINVAL (-1)        /* bad argument (null pointer, negative size, dimension mismatch)   */
+#define ASG_EINVALID_NODE (-2) /* (l,i) pair the reference rejects with ArgumentError, math.jl:355 */
+#define ASG_ENODEVICE (-3)     /* no usable sm_100 CUDA device; there is no CPU fallback           */
+#define ASG_ECUDA (-4)         /* CUDA runtime error, see asg_last_error()                         */
+#define ASG_ENOMEM (-5)        /* host or device allocation failed                                 */
+#define ASG_EUNSUPPORTED (-6)  /* valid request outside the engine's limits (e.g. D > 64)          */
+#define ASG_ESTATE (-7)        /* call order error (e.g. evaluate before upload)                   */
+
+#define ASG_MAX_DIM 64        /* hard limit of every path                                         */
+#define ASG_MAX_DIM_FAST 12   /* subspace-walk kernels are instantiated for D = 1..12              */
+
+/* evaluation engines; ASG_PATH_AUTO picks SUBSPACE when the grid is canonical, else SWEEP */
+#define ASG_PATH_AUTO 0
+#define ASG_PATH_SWEEP 1     /* tiled all-nodes sweep, exact reference semantics for ANY node set  */
+#define ASG_PATH_SUBSPACE 2  /* level-vector trie walk, one supporting node per subspace           */
+
+typedef struct asg_grid asg_grid;   /* opaque: device mirror of SparseGridInterpolant{D}, class.jl:281-319 */
+typedef struct asg_event asg_event; /* opaque: completion handle of an *_async call                        */
+
+typedef struct asg_grid_info_t {
+  int32_t D;
+  int32_t canonical;       /* 1: valid, in-range, duplicate-free nodes with finite coefs            */
+  int32_t path;            /* engine the next asg_eval will use (ASG_PATH_SWEEP / _SUBSPACE)        */
+  int32_t max_level;       /* max_n,d l_nd                                                          */
+  int64_t N;               /* nodes                                                                 */
+  int64_t max_depth;       /* max_n depth_n, depth = sum(l) - D + 1  (math.jl:103-108)              */
+  int64_t subspaces;       /* distinct level vectors (= non-zero terms per point on a regular grid) */
+  int64_t dense_subspaces; /* stored as full blocks                                                 */
+  int64_t trie_nodes;      /* nodes of the level-vector trie over all D levels                      */
+  int64_t coef_slots;      /* device coefficient slots incl. zero padding                           */
+  int64_t hash_slots;      /* open-addressing slots of sparsely filled subspaces                    */
+  int64_t device_bytes;    /* bytes resident in HBM for this grid                                   */
+  int64_t generation;      /* bumped by every upload / append / set_coefs                           */
+} asg_grid_info_t;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Select the CUDA device this process uses (one process per GPU). Fails with ASG_ENODEVICE when
+ * the device is absent or is not compute capability 10.x. Idempotent. */
+int32_t asg_init(int32_t device);
+int32_t asg_shutdown(void);
+int32_t asg_device_count(int32_t *count);
+const char *asg_last_error(void);
+const char *asg_version(void);
+/* number of CUDA kernels this library has launched since asg_init (bench.py: gpu_launches) */
+int32_t asg_launch_count(int64_t *count);
+/* pin / unpin a caller-owned host buffer so that H2D/D2H copies of asg_eval overlap with compute */
+int32_t asg_host_register(void *ptr, size_t bytes);
+int32_t asg_host_unregister(void *ptr);
+
+/* ---- node store: replaces the fields of SparseGridInterpolant{D} (src/class.jl:281-319) ----- */
+/* constructor asserts of src/class.jl:296-306: D > 0, finite bounds, ub > lb */
+int32_t asg_grid_create(int32_t D, const double *lb, const double *ub, asg_grid **out);
+int32_t asg_grid_destroy(asg_grid *g); /* safe from any thread (Julia finalizer) */
+
+/* Full replace of the node set (what rsg! / deserialize do, src/train.jl:68-75, src/io.jl:64-69).
+ * Element (n,d) of levels/indices is at [n*sn + d*sd]. coefs may be NULL (zeros, as rsg! leaves
+ * them, src/train.jl:74-75). Every (l,i) is checked with the rule of phi (src/math.jl:345-357):
+ * l < 1 or (l == 2 and i not in {0,2}) -> ASG_EINVALID_NODE. Depths are derived (math.jl:103-108). */
+int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int64_t *indices, int64_t sn,
+                        int64_t sd, const double *coefs);
+/* vcat of new rows (adapt!, src/train.jl:434-438) */
+int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
+                        int64_t sd, const double *coefs);
+/* G.coefs[first .. first+n-1] = coefs  (0-based node numbers; train!, src/train.jl:183) */
+int32_t asg_grid_set_coefs(asg_grid *g, int64_t first, int64_t n, const double *coefs);
+/* G.coefs[idx[k]] = coefs[k] */
+int32_t asg_grid_scatter_coefs(asg_grid *g, int64_t n, const int64_t *idx, const double *coefs);
+/* read back G.coefs (coefficients(G), src/class.jl:414-416) */
+int32_t asg_grid_get_coefs(asg_grid *g, int64_t first, int64_t n, double *coefs);
+int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info);
+int32_t asg_grid_set_path(asg_grid *g, int32_t path); /* force an engine (tests); AUTO restores */
+
+/* ---- evaluation: _interpolate / _interpolate_if / _interpolate_until_level / G(x)
+ *      (src/class.jl:629-643, 645-664, 666-680, 747-761) ----------------------------------- */
+/* out[m] = G(X[m,:]) for m < M, X in DOMAIN units (scale(), src/math.jl:301-309, is applied on the
+ * device); element (m,d) of X at [m*sp + d*sdim]. max_depth < 0: all nodes; otherwise only nodes
+ * with depth <= max_depth (the mask of _interpolate_until_level). Host buffers. */
+int32_t asg_eval(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
+                 double *out);
+/* alpha[m] = fvals[m] - G_{depth<=max_depth}(X[m,:]): the residual step of train! / adapt!
+ * (src/train.jl:176-183, 362-363, 381-382) fused into the evaluation kernel's epilogue */
+int32_t asg_surplus(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
+                    int64_t max_depth, double *alpha);
+/* Same, but the query points are the coordinates of the grid's own nodes idx[0..n-1], generated on
+ * the device exactly like get_x -> scale -> scale (src/train.jl:170-180). store != 0 additionally
+ * writes alpha into the coefficients of those nodes (G.coefs[i] = alpha, src/train.jl:183). */
+int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const double *fvals, int64_t max_depth,
+                          int32_t store, double *alpha);
+/* same two entry points with DEVICE pointers (points already resident in HBM), enqueued on
+ * `stream` (a cudaStream_t; NULL = the library's stream) without host synchronisation */
+int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
+                        double *dout, void *stream);
+int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim,
+                           const double *dfvals, int64_t max_depth, double *dalpha, void *stream);
+/* non-blocking host-buffer evaluation so a Julia thread is not pinned in a long ccall; the caller
+ * must keep X/out alive (GC.@preserve) until asg_wait returns; asg_wait frees the event */
+int32_t asg_eval_async(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
+                       double *out, asg_event **ev);
+int32_t asg_wait(asg_event *ev);
+
+/* ---- node coordinates: get_x / stack(G) (src/math.jl:464-497, src/class.jl:375-387) --------- */
+/* Xout[(k), d] = lb_d + (ub_d - lb_d) * x01(l,i), two roundings, no FMA; nodes first..first+n-1 */
+int32_t asg_nodes_x(asg_grid *g, int64_t first, int64_t n, double *Xout, int64_t sp, int64_t sdim);
+/* coordinates of arbitrary (l,i) rows in g's domain (adapt! children, src/train.jl:361, 380);
+ * rows get_x would reject (src/math.jl:474) -> ASG_EINVALID_NODE */
+int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
+                       int64_t sd, double *Xout, int64_t sp, int64_t sdim);
+
+/* ---- basis rows: basis(x,G) / basis(Xs,G) / basis(G) / dehierarchization_matrix
+ *      (src/class.jl:434-454, 483-503, 521-538, 555-567; documented intent) ----- */
+/* pass 1: row_nnz[m] = number of stored entries of row m. Entry (m,n) = prod_d phi(...) is stored
+ * when it is != 0 and (dropzeros == 0 or value >= atol)  (src/class.jl:450-453). */
+int32_t asg_basis_count(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                        int32_t dropzeros, int64_t *row_nnz);
+/* pass 2: CSR fill. row_ptr has M+1 entries (exclusive scan of row_nnz); colidx are 0-based node
+ * numbers in the caller's node order, ascending inside a row. */
+int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                       int32_t dropzeros, const int64_t *row_ptr, int64_t *colidx, double *vals);
+/* dense variant: out[m*ldm + n*ldn], every element written (zeros included) */
+int32_t asg_basis_dense(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                        int32_t dropzeros, double *out, int64_t ldm, int64_t ldn);
+/* dense variant into a DEVICE buffer (bench: HBM-write roofline without the D2H copy) */
+int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, double atol,
+                               int32_t dropzeros, double *dout, int64_t ldm, int64_t ldn, void *stream);
+
+/* ---- host-only diagnostics -------------------------------------------------------------------- */
+/* Run the packer (validation, subspace grouping, trie build) on a node set WITHOUT a device and
+ * report the sizes it would upload. No evaluation happens here. When the grid is not canonical,
+ * asg_last_error() says why. */
+int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t *indices, int64_t sn, int64_t sd,
+                      asg_grid_info_t *info);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------------- */
+/* dependent-free DFMA loop on every SM: returns the measured FP64 rate in FMA lane-ops per second
+ * (multiply by 2 for FLOP/s); the denominator of the FP64 roofline (MEASURED_PEAKS.json has none) */
+int32_t asg_measure_fp64_peak(double *fma_per_second);
+/* time (ms, CUDA events on the library stream) of the last asg_eval_device / asg_surplus_device /
+ * asg_basis_dense_device kernel sequence */
+int32_t asg_last_kernel_ms(double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASG_CUDA_H */

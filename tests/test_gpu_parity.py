@@ -1,0 +1,377 @@
+"""GPU parity: libasg_cuda.so (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): node sets / levels bit-exact; fp64 values within 1e-12 relative,
+1e-14 absolute near zero (conftest.assert_close). Sizes are chosen so the oracle finishes in seconds.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_close, parabola, sinsum, utility
+
+pytestmark = pytest.mark.gpu
+
+
+def _edge_points(D, lb, ub, rng, n=64):
+    """knots, corners, faces, out-of-domain, NaN, +-0.0"""
+    lb, ub = np.asarray(lb, float), np.asarray(ub, float)
+    pts = []
+    for k in range(0, 9):
+        pts.append(lb + (ub - lb) * (k / 8.0))                  # diagonal knots incl. both corners
+    dy = rng.integers(0, 65, size=(n, D)) / 64.0                  # dyadic points: exactly on knots
+    pts.extend(lb + (ub - lb) * dy)
+    c = rng.integers(0, 2, size=(16, D)).astype(float)            # corners
+    pts.extend(lb + (ub - lb) * c)
+    out = rng.random((8, D))
+    out[:, 0] = 1.5                                               # outside in one dim
+    pts.extend(lb + (ub - lb) * out)
+    out2 = rng.random((8, D))
+    out2[:, -1] = -0.25
+    pts.extend(lb + (ub - lb) * out2)
+    nanp = lb + (ub - lb) * rng.random((4, D))
+    nanp[:, D // 2] = np.nan
+    pts.extend(nanp)
+    infp = lb + (ub - lb) * rng.random((2, D))
+    infp[0, 0] = np.inf
+    infp[1, 0] = -np.inf
+    pts.extend(infp)
+    z = np.array(lb, copy=True)
+    if lb[0] == 0.0:
+        z[0] = -0.0
+    pts.append(z)
+    return np.array(pts, dtype=np.float64)
+
+
+def _mirror(asg, OG):
+    G = asg.SparseGridInterpolant(OG.D, lb=OG.lb, ub=OG.ub)
+    G.levels, G.indices, G.depths = OG.levels.copy(), OG.indices.copy(), OG.depths.copy()
+    G.fvals, G.coefs = OG.fvals.copy(), OG.coefs.copy()
+    return G
+
+
+@pytest.fixture(scope="module")
+def cfg1(oracle):
+    OG = oracle.OracleGrid(3)
+    OG.train(sinsum, 7, 5)
+    return OG
+
+
+@pytest.fixture(scope="module")
+def cfg2(oracle):
+    OG = oracle.OracleGrid(2)
+    OG.train(utility, 4, (3, 8))
+    OG.adapt(utility, 20, tol=1e-5)
+    return OG
+
+
+@pytest.fixture(scope="module")
+def cfg_d10(oracle):
+    OG = oracle.OracleGrid(10)
+    OG.rsg(5, 5)
+    rng = np.random.default_rng(1234)
+    OG.coefs = rng.standard_normal(len(OG)) * 2.0 ** (-OG.depths.astype(float))
+    return OG
+
+
+@pytest.fixture(scope="module")
+def cfg_nonunit(oracle):
+    D = 4
+    OG = oracle.OracleGrid(D, lb=np.arange(1, D + 1.0), ub=np.arange(2, D + 2.0) + 0.3)
+    OG.train(lambda x: float(np.sum(np.cos(x)) + x[0] * x[1]), 6, (4, 5, 6, 3))
+    return OG
+
+
+@pytest.mark.parametrize("path", ["subspace", "sweep"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg_d10", "cfg_nonunit"])
+def test_eval_parity(asg, request, name, path):
+    OG = request.getfixturevalue(name)
+    G = _mirror(asg, OG)
+    G.set_path(path)
+    rng = np.random.default_rng(42)
+    lb, ub = OG.lb, OG.ub
+    X = np.vstack([lb + (ub - lb) * rng.random((4000, OG.D)), _edge_points(OG.D, lb, ub, rng)])
+    want, scale = OG.evaluate(X, return_abssum=True)
+    got = G.evaluate(X)
+    assert_close(got, want, scale, f"{name}/{path}")
+    # out-of-domain and NaN points are exactly 0.0 (src/math.jl:349-353)
+    outside = ~np.all((X >= lb) & (X <= ub), axis=1)
+    assert outside.sum() >= 20
+    assert np.all(got[outside] == 0.0)
+    info = G.info()
+    assert info["path"] == (2 if path == "subspace" else 1)
+
+
+def test_eval_layouts_and_scalar_call(asg, cfg1):
+    G = _mirror(asg, cfg1)
+    rng = np.random.default_rng(7)
+    X = rng.random((1000, 3))
+    want = cfg1.evaluate(X)
+    a = G.evaluate(X)
+    b = G.evaluate(np.asfortranarray(X))              # Julia column-major M x D
+    c = G.evaluate(np.ascontiguousarray(X.T), dims=2)   # D x n as rand(G, n) returns
+    d = G.evaluate(np.repeat(X, 2, axis=1)[:, ::2])    # generic strides
+    assert_close(a, want, what="row-major")
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+    assert G(X[0]) == a[0]
+    assert np.array_equal(G(X[:5]), a[:5])
+    with pytest.raises(AssertionError):
+        G(np.zeros(4))
+    with pytest.raises(NameError):
+        G(X[0], extrapolate=True)                       # reference defect B3, mirrored
+
+
+def test_interpolation_property(asg, cfg1, cfg_nonunit):
+    """G(x_n) == fvals[n] at every node (residual fitting, src/train.jl:176-183)."""
+    for OG in (cfg1, cfg_nonunit):
+        G = _mirror(asg, OG)
+        X = asg.stack(G)
+        assert np.array_equal(X, OG.stack())            # device get_x is bit-exact (A2: no FMA)
+        got = G.evaluate(X)
+        assert np.max(np.abs(got - OG.fvals)) < 5e-14 * max(1.0, np.max(np.abs(OG.fvals)))
+
+
+@pytest.mark.parametrize("path", ["subspace", "sweep"])
+def test_masked_eval_and_surplus(asg, cfg1, cfg2, path):
+    rng = np.random.default_rng(3)
+    for OG in (cfg1, cfg2):
+        G = _mirror(asg, OG).set_path(path)
+        X = rng.random((500, OG.D))
+        for L in (1, 2, 3, 5, int(OG.depths.max())):
+            want, sc = OG.evaluate(X, max_depth=L, return_abssum=True)
+            assert_close(G.evaluate(X, max_depth=L), want, sc, f"mask {L}")
+        f = rng.standard_normal(500)
+        want = f - OG.evaluate(X, max_depth=4)
+        assert_close(G.surplus(X, f, max_depth=4), want, np.abs(f) + 1, "surplus")
+
+
+def test_train_parity(asg, oracle):
+    """train! on the GPU reproduces the oracle's grid: nodes bit-exact, coefficients in tolerance."""
+    for D, f, depth, ml, lb, ub in [(3, sinsum, 7, 5, None, None), (2, utility, 4, (3, 8), None, None),
+                                    (6, sinsum, 5, tuple(range(6, 12)), None, None),
+                                    (3, lambda x: float(np.sum(np.sin(x))), 6, 6, [1, 2, 3], [2, 3, 4])]:
+        OG = oracle.OracleGrid(D, lb=lb, ub=ub)
+        OG.train(f, depth, ml)
+        G = asg.SparseGridInterpolant(D, lb=lb, ub=ub)
+        asg.train(G, f, depth, ml)
+        assert np.array_equal(G.levels, OG.levels) and np.array_equal(G.indices, OG.indices)
+        assert np.array_equal(G.depths, OG.depths)
+        assert np.array_equal(G.fvals, OG.fvals)          # same f at bit-identical coordinates
+        assert_close(G.coefs, OG.coefs, np.abs(OG.fvals) + 1, "train coefs")
+        # device coefficients (written by the fused surplus kernel) equal the host copy
+        import ctypes as C
+        back = np.empty(len(G))
+        asg._capi.check(asg._capi.load().asg_grid_get_coefs(G._ensure(), 0, len(G), back.ctypes.data_as(asg._capi.f64p)))
+        assert np.array_equal(back, G.coefs)
+
+
+def test_train_analytic_exact(asg):
+    """f = prod 4x(1-x): every intermediate is dyadic, so surpluses are bit-exact."""
+    G = asg.SparseGridInterpolant(3)
+    asg.train(G, parabola, 6, 6)
+    s1 = lambda l: 1.0 if l == 1 else (-1.0 if l == 2 else 4.0 ** (2 - l))
+    exp = np.array([np.prod([s1(l) for l in L]) for L in G.levels])
+    assert len(G) == 441 and np.array_equal(G.coefs, exp)
+    # affine f: all surpluses at depth >= 3 are exactly 0, root = f(0.5,...)
+    G2 = asg.SparseGridInterpolant(2)
+    asg.train(G2, lambda x: 1.0 + 2.0 * x[0] - 0.5 * x[1], 5, 5)
+    assert G2.coefs[0] == 1.0 + 1.0 - 0.25
+    assert np.all(G2.coefs[G2.levels.max(axis=1) >= 3] == 0.0)
+
+
+def test_adapt_parity(asg, oracle, cfg2):
+    """adapt! node SET bit-exact against the oracle (row order is Dict order in Julia: compare sorted)."""
+    G = asg.SparseGridInterpolant(2)
+    asg.train(G, utility, 4, (3, 8))
+    log = []
+    asg.adapt(G, utility, 20, tol=1e-5, toltype="absolute", verbose=False, log=log)
+    OG = cfg2
+    assert len(G) == len(OG) == 12119
+
+    def keyed(Lv, Ix, vals):
+        key = np.concatenate([Lv, Ix], axis=1)
+        order = np.lexsort(key.T[::-1])
+        return key[order], vals[order]
+
+    kg, cg = keyed(G.levels, G.indices, G.coefs)
+    ko, co = keyed(OG.levels, OG.indices, OG.coefs)
+    _, fo = keyed(OG.levels, OG.indices, OG.fvals)
+    assert np.array_equal(kg, ko)
+    # alpha = f - G inherits the ABSOLUTE error of G, whose terms are as large as |f| (up to 10 here)
+    assert_close(cg, co, 4 * (np.abs(fo) + 1), "adapt coefs")
+    assert min(l["min_margin"] for l in log) > 1e-13      # no acceptance decision within rounding of tol (H6)
+    # and the adapted grid evaluates like the oracle's
+    rng = np.random.default_rng(5)
+    X = rng.random((2000, 2))
+    want, sc = OG.evaluate(X, return_abssum=True)
+    assert_close(G.evaluate(X), want, sc, "adapted eval")
+    assert G.info()["hash_slots"] > 0                      # sparsely filled subspaces were exercised
+
+
+def test_adapt_relative_d6(asg, oracle):
+    f = sinsum
+    OG = oracle.OracleGrid(4)
+    OG.train(f, 4, (3, 4, 5, 6))
+    OG.adapt(f, 7, tol=5e-2, toltype="relative")
+    G = asg.SparseGridInterpolant(4)
+    asg.train(G, f, 4, (3, 4, 5, 6))
+    asg.adapt(G, f, 7, tol=5e-2, toltype="relative", verbose=False)
+    a = {tuple(r) for r in np.concatenate([G.levels, G.indices], axis=1)}
+    b = {tuple(r) for r in np.concatenate([OG.levels, OG.indices], axis=1)}
+    assert a == b and len(G) > 100
+
+
+@pytest.mark.parametrize("path", ["subspace", "sweep"])
+def test_basis_parity(asg, cfg1, cfg2, cfg_nonunit, path):
+    rng = np.random.default_rng(11)
+    for OG in (cfg1, cfg2, cfg_nonunit):
+        G = _mirror(asg, OG).set_path(path)
+        lb, ub = OG.lb, OG.ub
+        X = np.vstack([lb + (ub - lb) * rng.random((200, OG.D)), _edge_points(OG.D, lb, ub, rng, 16)])
+        want = OG.basis(X)
+        B = asg.basis(X, G)
+        assert B.shape == (len(X), len(OG))
+        got = B.toarray()
+        assert np.array_equal(got != 0, want != 0)         # same sparsity pattern
+        assert_close(got, want, None, "basis values")
+        dense = asg.basis(X, G, dense=True)
+        assert np.array_equal(dense, got)
+        # README identity: sum(B .* C) == G(x)
+        assert_close(B @ OG.coefs, OG.evaluate(X), None, "B*C")
+        # dropzeros = false keeps tiny values, atol filter otherwise
+        w2 = OG.basis(X, dropzeros=False)
+        g2 = asg.basis(X, G, dropzeros=False).toarray()
+        assert np.array_equal(g2 != 0, w2 != 0)
+        w3 = OG.basis(X, atol=1e-3)
+        g3 = asg.basis(X, G, atol=1e-3).toarray()
+        assert np.array_equal(g3 != 0, w3 != 0)
+        # single point form
+        b1 = asg.basis(X[0], G)
+        assert b1.shape == (1, len(OG)) and np.array_equal(b1.toarray()[0], got[0])
+
+
+def test_dehierarchization(asg, cfg1):
+    G = _mirror(asg, cfg1)
+    E = asg.dehierarchization_matrix(G)
+    assert E.shape == (len(G), len(G))                    # README.md:162-163
+    assert np.array_equal(E.toarray(), cfg1.basis())
+    assert_close(E @ G.coefs, G.fvals, None, "E*coefs = fvals")
+    order = np.argsort(G.depths, kind="stable")
+    Es = E.toarray()[np.ix_(order, order)]
+    assert np.all(np.diag(Es) == 1.0) and np.all(np.triu(Es, 1) == 0.0)   # unit lower-triangular under depth sort
+    H = asg.hierarchization_matrix(G)
+    assert_close(H @ G.fvals, G.coefs, np.abs(G.fvals).max() * np.ones(len(G)) * 10, "H*fvals = coefs")
+
+
+def test_noncanonical_falls_back_to_sweep(asg, oracle):
+    """duplicates, out-of-range / even indices, non-finite coefficients: exact reference semantics."""
+    OG = oracle.OracleGrid(2)
+    OG.train(sinsum, 4, 4)
+    # duplicate node + a node whose support lies partly outside [0,1] + an even index at l > 2
+    OG.levels = np.vstack([OG.levels, OG.levels[5], [3, 3], [4, 3]])
+    OG.indices = np.vstack([OG.indices, OG.indices[5], [5, 1], [2, 3]])
+    OG.depths = OG.levels.sum(axis=1) - 1
+    OG.coefs = np.concatenate([OG.coefs, [0.25, -0.5, 0.125]])
+    OG.fvals = np.concatenate([OG.fvals, [0, 0, 0]])
+    G = _mirror(asg, OG)
+    rng = np.random.default_rng(0)
+    X = np.vstack([rng.random((500, 2)) * 1.6 - 0.3, _edge_points(2, OG.lb, OG.ub, rng)])
+    assert G.info()["canonical"] == 0 and G.info()["path"] == 1
+    want, sc = OG.evaluate(X, return_abssum=True)
+    assert_close(G.evaluate(X), want, sc, "non-canonical")
+    with pytest.raises(asg.AsgError):
+        G.set_path("subspace")
+    # non-finite coefficient: Inf * 0 = NaN propagates exactly as in the reference (A8)
+    OG2 = oracle.OracleGrid(2)
+    OG2.train(sinsum, 3, 3)
+    OG2.coefs[3] = np.inf
+    G2 = _mirror(asg, OG2)
+    X2 = rng.random((64, 2))
+    w = OG2.evaluate(X2)
+    g = G2.evaluate(X2)
+    assert np.array_equal(np.isnan(g), np.isnan(w)) and np.any(np.isnan(w))
+    assert G2.info()["path"] == 1
+
+
+def test_invalid_nodes_rejected(asg):
+    G = asg.SparseGridInterpolant(2)
+    G.levels = np.array([[1, 1], [2, 1]], dtype=np.int64)
+    G.indices = np.array([[1, 1], [1, 1]], dtype=np.int64)   # (2,1) is what phi throws on
+    G.depths = np.array([1, 2])
+    G.fvals = np.zeros(2)
+    G.coefs = np.zeros(2)
+    with pytest.raises(asg.InvalidNodeError):
+        G.evaluate(np.zeros((1, 2)))
+    G.levels = np.array([[1, 0]], dtype=np.int64)
+    G.indices = np.array([[1, 1]], dtype=np.int64)
+    G.depths, G.fvals, G.coefs = np.array([0]), np.zeros(1), np.zeros(1)
+    with pytest.raises(asg.InvalidNodeError):
+        G.sync()
+    with pytest.raises(asg.InvalidNodeError):                # get_x rejects even index at l > 2
+        asg.SparseGridInterpolant(1).nodes_x(np.array([[3]]), np.array([[2]]))
+
+
+def test_empty_and_tiny(asg):
+    G = asg.SparseGridInterpolant(3)
+    assert G.evaluate(np.zeros((0, 3))).shape == (0,)
+    X = np.random.default_rng(0).random((10, 3))
+    assert np.all(G.evaluate(X) == 0.0)                      # empty grid: sum over nothing
+    asg.rsg(G, 2, 2)
+    G.coefs = np.arange(1.0, len(G) + 1)
+    assert G.evaluate(np.full((1, 3), 0.5))[0] == 1.0        # only the root is non-zero at the centre
+    assert asg.basis(G).shape == (7, 7)
+    big = asg.SparseGridInterpolant(1)
+    asg.train(big, lambda x: float(np.sin(3 * x[0])), 20, 20)   # 1-D, levels up to 20
+    assert len(big) == 2 ** 19 + 1
+    xs = np.random.default_rng(1).random((1000, 1))
+    assert np.max(np.abs(big.evaluate(xs) - np.sin(3 * xs[:, 0]))) < 1e-10
+
+
+def test_async_and_set_coefs(asg, cfg1):
+    import ctypes as C
+    G = _mirror(asg, cfg1)
+    lib = asg._capi.load()
+    X = np.random.default_rng(9).random((3000, 3))
+    out = np.empty(3000)
+    ev = C.c_void_p()
+    asg._capi.check(lib.asg_eval_async(G._ensure(), C.c_void_p(X.ctypes.data), 3000, 3, 1, -1,
+                                       C.c_void_p(out.ctypes.data), C.byref(ev)))
+    asg._capi.check(lib.asg_wait(ev))
+    assert np.array_equal(out, G.evaluate(X))
+    new = np.linspace(-1, 1, len(G))
+    asg._capi.check(lib.asg_grid_set_coefs(G._ensure(), 0, len(G), new.ctypes.data_as(asg._capi.f64p)))
+    cfg = type(cfg1)(3)
+    cfg.levels, cfg.indices, cfg.depths, cfg.coefs, cfg.fvals = cfg1.levels, cfg1.indices, cfg1.depths, new, cfg1.fvals
+    want, sc = cfg.evaluate(X, return_abssum=True)
+    assert_close(G.evaluate(X), want, sc, "after set_coefs")
+    for p in ("sweep", "subspace"):
+        G.set_path(p)
+        assert_close(G.evaluate(X), want, sc, "after set_coefs " + p)
+
+
+def test_full_size_properties(asg):
+    """cfg3 at full grid size (D=10, 652 065 nodes): size-independent properties instead of the oracle.
+    Linearity in the coefficients, interpolation at nodes of a trained analytic function, engines agree."""
+    D = 10
+    G = asg.SparseGridInterpolant(D)
+    asg.rsg(G, 8, 8)
+    assert len(G) == 652065
+    info = G.info()
+    assert info["subspaces"] == 19448 and info["canonical"] == 1
+    rng = np.random.default_rng(2024)
+    c1 = rng.standard_normal(len(G)) * 2.0 ** (-G.depths.astype(float))
+    c2 = rng.standard_normal(len(G)) * 2.0 ** (-G.depths.astype(float))
+    X = rng.random((20000, D))
+    G.coefs = c1
+    y1 = G.evaluate(X)
+    G.coefs = c2
+    y2 = G.evaluate(X)
+    G.coefs = 2.0 * c1 - 0.5 * c2                            # exact scaling by powers of two
+    y3 = G.evaluate(X)
+    assert np.max(np.abs(y3 - (2.0 * y1 - 0.5 * y2))) < 1e-12
+    # sweep engine on a subsample agrees with the subspace engine
+    G.set_path("sweep")
+    ys = G.evaluate(X[:256])
+    assert np.max(np.abs(ys - y3[:256])) < 1e-12
+    G.set_path("auto")
+    # coefficient 1 on the root only -> G == 1 everywhere inside; basis row sums to the constant
+    G.coefs = np.where(G.depths == 1, 1.0, 0.0)
+    assert np.all(G.evaluate(X[:1000]) == 1.0)
