@@ -1,0 +1,77 @@
+"""Multi-GPU layer: the grid is REPLICATED, query points are SHARDED.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on the GPU box, gloo in CPU tests).
+The evaluation itself has no data-path collective: points are independent. Collectives appear only
+  C1  ``broadcast_grid``  -- node arrays root -> all, once per grid version,
+  C2  ``gather_results``  -- the M x 8 byte result shards back to every rank / the root.
+``train``/``adapt`` levels use the same pattern: shard the candidates, all-gather alpha, every rank
+appends the same rows.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(M: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous ceil(M / world) ranges: preserves the output order under concatenation."""
+    per = -(-M // world)
+    lo = min(M, rank * per)
+    return lo, min(M, lo + per)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def broadcast_grid(G, src: int = 0):
+    """C1: make every rank's SparseGridInterpolant identical to rank `src`'s (arrays + bounds)."""
+    dev = _dev()
+    D = G.ndims
+    meta = torch.tensor([len(G.levels) if dist.get_rank() == src else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src)
+    N = int(meta.item())
+    is_src = dist.get_rank() == src
+
+    def bc(arr, shape, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev) if is_src else \
+            torch.empty(shape, dtype=torch.from_numpy(np.empty(0, dtype=dtype)).dtype, device=dev)
+        dist.broadcast(t, src)
+        return t.cpu().numpy()
+
+    bounds = bc(np.concatenate([G.lb, G.ub]), (2 * D,), np.float64)
+    levels = bc(G.levels, (N, D), np.int64)
+    indices = bc(G.indices, (N, D), np.int64)
+    depths = bc(G.depths, (N,), np.int64)
+    fvals = bc(G.fvals, (N,), np.float64)
+    coefs = bc(G.coefs, (N,), np.float64)
+    if not is_src:
+        G.lb, G.ub = tuple(bounds[:D].tolist()), tuple(bounds[D:].tolist())
+        G.levels, G.indices, G.depths, G.fvals, G.coefs = levels, indices, depths, fvals, coefs
+    return G
+
+
+def gather_results(local: np.ndarray, M: int) -> np.ndarray:
+    """C2: concatenate the per-rank result shards (shard_range order) on every rank."""
+    world = dist.get_world_size()
+    dev = _dev()
+    per = -(-M // world) if M else 0
+    buf = torch.zeros(max(per, 1), dtype=torch.float64, device=dev)
+    if len(local):
+        buf[: len(local)] = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    sizes = [shard_range(M, r, world) for r in range(world)]
+    return np.concatenate([parts[r].cpu().numpy()[: hi - lo] for r, (lo, hi) in enumerate(sizes)])
+
+
+def evaluate_sharded(G, X: np.ndarray, max_depth: int | None = None, evaluator=None) -> np.ndarray:
+    """``[G(x) for x in eachrow(X)]`` with the rows split over the ranks. Every rank passes the same
+    X (or at least its own rows); every rank gets the full result. `evaluator` defaults to
+    ``G.evaluate`` (the CUDA path); CPU tests inject a stand-in to exercise the sharding logic."""
+    M = X.shape[0]
+    lo, hi = shard_range(M, dist.get_rank(), dist.get_world_size())
+    ev = evaluator if evaluator is not None else (lambda Z: G.evaluate(Z, max_depth=max_depth))
+    local = ev(X[lo:hi]) if hi > lo else np.empty(0)
+    return gather_results(local, M)
