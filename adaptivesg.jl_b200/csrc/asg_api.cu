@@ -89,7 +89,8 @@ struct asg_grid {
   std::vector<int64_t> levels, indices;
   std::vector<double> coefs;
   std::vector<int64_t> slot_of_node;
-  bool uploaded = false, canonical = false, finite = true;
+  bool uploaded = false, canonical = false, finite = true, regular = false;
+  RsgParams rp{};
   std::string why;
   int forced_path = ASG_PATH_AUTO;
   asg_grid_info_t info{};
@@ -110,6 +111,7 @@ struct asg_grid {
     if (forced_path == ASG_PATH_SWEEP) return ASG_PATH_SWEEP;
     return (canonical && finite) ? ASG_PATH_SUBSPACE : ASG_PATH_SWEEP;
   }
+  bool use_rsg() const { return regular && forced_path != ASG_PATH_TRIE; }
 };
 
 struct asg_event {
@@ -188,6 +190,8 @@ int repack(asg_grid *g) {
   int rc = pack_grid(g->D, g->N, g->levels.data(), g->indices.data(), g->coefs.data(), pk, err);
   if (rc != ASG_OK) return set_err(rc, err);
   g->canonical = pk.canonical;
+  g->regular = pk.regular;
+  g->rp = pk.rp;
   g->why = pk.why;
   g->finite = true;
   for (double c : g->coefs)
@@ -213,6 +217,7 @@ int repack(asg_grid *g) {
                              g->d_horig.bytes() + g->d_sw.bytes() + g->d_sw_low.bytes() + g->d_sw_coef.bytes() +
                              g->d_sw_depth.bytes());
   I.generation = gen;
+  I.regular = pk.regular ? 1 : 0;
   return ASG_OK;
 }
 
@@ -240,8 +245,10 @@ int rem_of(int64_t max_depth) {
 
 cudaError_t run_eval(asg_grid *g, const EvalArgs &a, cudaStream_t st) {
   int64_t l = 0;
-  cudaError_t e = (g->path() == ASG_PATH_SUBSPACE) ? launch_eval_subspace(g->dg, a, st, &l)
-                                                   : launch_eval_sweep(g->dg, a, st, &l);
+  cudaError_t e;
+  if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(g->dg, a, st, &l);
+  else if (g->use_rsg()) e = launch_eval_rsg(g->dg, g->rp, a, st, &l);
+  else e = launch_eval_subspace(g->dg, a, st, &l);
   bump(l);
   return e;
 }
@@ -558,8 +565,9 @@ int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info) {
 int32_t asg_grid_set_path(asg_grid *g, int32_t path) {
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  if (path != ASG_PATH_AUTO && path != ASG_PATH_SWEEP && path != ASG_PATH_SUBSPACE) return set_err(ASG_EINVAL, "bad path");
-  if (path == ASG_PATH_SUBSPACE && g->uploaded && !(g->canonical && g->finite))
+  if (path != ASG_PATH_AUTO && path != ASG_PATH_SWEEP && path != ASG_PATH_SUBSPACE && path != ASG_PATH_TRIE)
+    return set_err(ASG_EINVAL, "bad path");
+  if ((path == ASG_PATH_SUBSPACE || path == ASG_PATH_TRIE) && g->uploaded && !(g->canonical && g->finite))
     return set_err(ASG_EUNSUPPORTED, "grid is not canonical (" + g->why + "): only the sweep engine applies");
   g->forced_path = path;
   return ASG_OK;
@@ -586,7 +594,7 @@ int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, in
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx.stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), nullptr, dout};
   CK(cudaEventRecord(ctx.ev0, st));
   CK(run_eval(g, a, st));
@@ -601,7 +609,7 @@ int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp,
   if (M > 0 && !dfvals) return set_err(ASG_EINVAL, "null fvals");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx.stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), dfvals, dalpha};
   CK(cudaEventRecord(ctx.ev0, st));
   CK(run_eval(g, a, st));
@@ -826,7 +834,7 @@ int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   if (M == 0 || g->N == 0) return ASG_OK;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx.stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   BasisArgs a{};
   a.X = dX; a.M = M; a.sp = sp; a.sd = sdim; a.atol = atol; a.dropzeros = dropzeros; a.mode = 2;
   a.dense = dout; a.ldm = ldm; a.ldn = ldn;
@@ -905,6 +913,7 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->trie_nodes = pk.trie_nodes;
   info->coef_slots = (int64_t)pk.coef.size();
   info->hash_slots = (int64_t)pk.hent.size();
+  info->regular = pk.regular ? 1 : 0;
   if (!pk.canonical) t_err = pk.why;
   return ASG_OK;
 }

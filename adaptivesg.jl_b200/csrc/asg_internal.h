@@ -18,16 +18,28 @@ constexpr int kMaxLevelFast = 32;   // cell bits of a level: b(l) = 0, 1, l-2  -
 constexpr int kMaxPosBits = 32;     // position of a node inside its subspace must fit a uint32
 
 // ---- level-vector trie (device layout) -------------------------------------------------------
-// One record per trie node. Level k of the trie fixes the hierarchical level of dimension k.
+// One 16-byte record per trie node. Level k of the trie fixes the hierarchical level of dimension k.
 //   inner node (k < D-1): x = index of its first child in level k+1 (children are contiguous and
 //                         sorted by level; the end is the next record's x, a sentinel closes the array)
 //   leaf       (k = D-1): x = first coefficient slot of the subspace (dense) or first hash slot
-//   y: bits 0..7 level, bit 8 = hashed subspace, bits 16..23 = log2(hash table size)
-struct TrieRec {
+//   y: bits 0..7 level, bit 8 = hashed subspace, bits 16..23 = log2(hash table size),
+//      bits 24..29 = cell bits b(level), bit 30 = (level > 2)
+//   nodes of level D-2 ("prefix groups", the parents of the leaves) additionally carry
+//   w: bits 0..7 pb = position bits of dimensions 0..D-2, bits 8..15 lm, bit 16 FULL
+//   z: FULL only: coefficient slot of the first child. FULL means the children are the levels
+//      1..lm (lm <= kLeafTable), all dense and stored back to back, so the slot of the supporting
+//      node of level l is  z + ((off(l) + cell_l) << pb) + O  with off(l) = 0,1,3,5,9,17,...
+// Position of a node inside its subspace: the cells of dimensions 0..D-2 concatenated (dimension 0
+// most significant) form O (pb bits); the cell of the LAST dimension sits above them.
+struct __align__(16) TrieRec {
   uint32_t x;
   uint32_t y;
+  uint32_t z;
+  uint32_t w;
 };
 constexpr uint32_t kRecHashed = 1u << 8;
+constexpr uint32_t kRecFull = 1u << 16;
+constexpr int kLeafTable = 8;  // last-dimension levels 1..8 are served from per-thread register tables
 
 struct HashEnt {  // open addressing, linear probing; key = pos + 1 (0 = empty)
   unsigned long long key;
@@ -59,19 +71,32 @@ struct DeviceGrid {
   const int32_t *sw_depth;  // [N]
 };
 
+// ---- regular-sparse-grid fast path (asg_kernels_rsg.cu) ------------------------------------------
+constexpr int kRsgMaxBudget = 31;
+struct RsgParams {
+  int budget;                 // max over nodes of sum(l_d - 1)  (= max depth - 1)
+  int cut;                    // set per launch: budget - mask budget (0 = no depth mask)
+  int ml[kMaxDimFast];        // effective max level per dimension: min(max level, budget + 1)
+  // S[k][rem]: coefficient slots (per unit of prefix positions) of all level vectors over dimensions
+  // k..D-1 with sum(l-1) <= rem; S[D][*] = 1
+  uint32_t S[kMaxDimFast + 1][kRsgMaxBudget + 1];
+};
+
 // ---- host-side packed grid -------------------------------------------------------------------
 struct PackResult {
   bool canonical = false;
   std::string why;  // why the grid is not canonical (empty when it is)
   int max_level = 0;
   int64_t max_depth = 0;
-  int64_t subspaces = 0, dense_subspaces = 0, trie_nodes = 0;
+  int64_t subspaces = 0, dense_subspaces = 0, trie_nodes = 0, full_groups = 0;
   std::vector<std::vector<TrieRec>> rec;  // [D] levels, sentinel included
   std::vector<double> coef;
   std::vector<int32_t> orig;
   std::vector<HashEnt> hent;
   std::vector<int32_t> horig;
   std::vector<int64_t> slot_of_node;  // >= 0: dense slot; < 0: -(hash slot) - 1
+  bool regular = false;               // node set is exactly a regular sparse grid: RsgParams valid
+  RsgParams rp{};
   // sweep engine
   std::vector<SweepDim> sw;
   std::vector<uint64_t> sw_low;
@@ -106,6 +131,8 @@ struct BasisArgs {
 };
 
 cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
+                            int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_basis_subspace(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_basis_sweep(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);

@@ -3,14 +3,18 @@
 // and of the basis rows prod_d phi(...) (src/class.jl:434-454) by walking the level-vector trie
 // built in asg_pack.cpp.
 //
-// One thread owns one query point (registers: D unit-cube coordinates + D integer cell keys); a warp
-// owns 32 consecutive points, so all trie records it reads are warp-uniform broadcasts and the only
-// per-lane memory traffic is one 8-byte coefficient gather per subspace. Per trie node the thread
-// computes the 1-D hat of the single supporting node of that level,
+// One thread owns R query points (registers: D unit-cube coordinates + D integer cell keys each); a
+// warp owns 32*R points, so every trie record it reads is a warp-uniform broadcast, amortised over R
+// points, and the only per-lane memory traffic is one 8-byte coefficient gather per (point, subspace).
+// Per trie node the thread computes the 1-D hat of the single supporting node of that level,
 //      cell = floor(x01 * 2^b(l)),  i = 2*cell + [l > 2],  phi = 1 - |x01 * 2^(l-1) - i|,
 // which is the reference's phi (src/math.jl:345-357) evaluated only where it is non-zero:
 // x01*2^(l-1) is exact, the subtraction is the reference's single rounding (an FMA cannot change
 // it), and the l == 2 forms 1-2x / 2x-1 are bit-identical to 1-|2x-i| on [0,1].
+// For the LAST dimension the hats and cells of levels 1..8 are tabulated once per point in registers,
+// and a FULL prefix group (children = levels 1..lm, dense, back to back) is evaluated as
+//      acc += P * sum_l coef[z + ((off(l)+cell_l) << pb) + O] * phi_l
+// i.e. three instructions (IMAD.WIDE, LDG, DFMA) per (point, subspace).
 // Points outside [0,1]^D (or NaN) evaluate to exactly 0.0 as in the reference (src/math.jl:349-353).
 #include <climits>
 
@@ -23,143 +27,287 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t pos, int lg) {
 }
 
 __device__ __forceinline__ TrieRec ld_rec(const TrieRec *p) {
-  const uint2 v = __ldg(reinterpret_cast<const uint2 *>(p));
+  const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
   TrieRec r;
   r.x = v.x;
   r.y = v.y;
+  r.z = v.z;
+  r.w = v.w;
   return r;
 }
 
-// 1-D hat of the supporting node of level l >= 2 at unit-cube coordinate x (q = its 30-bit cell key).
-__device__ __forceinline__ void hat_li(double x, uint32_t q, int l, double &ph, uint32_t &cell, int &b) {
-  b = l > 3 ? l - 2 : 1;
-  cell = q >> (kKeyBits - b);
-  const uint32_t i = 2u * cell + (l > 2 ? 1u : 0u);
+__device__ __forceinline__ double u32_to_f64(uint32_t i) {
   // (double) i without the slow I2F.F64: 2^52 + i has i in its low mantissa bits
-  const double di = __hiloint2double(0x43300000, (int)i) - 4503599627370496.0;
-  const double s = __hiloint2double((1023 + l - 1) << 20, 0);  // 2^(l-1) = power2(l-1), src/math.jl:59-61
-  const double t = fma(x, s, -di);                             // x*2^(l-1) - i, one rounding as in the reference
-  ph = 1.0 - fabs(t);                                          // |t| <= 1 by construction of the cell
+  return __hiloint2double(0x43300000, (int)i) - 4503599627370496.0;
 }
 
+// 1-D hat of the supporting node of level l >= 2 at unit-cube coordinate x (q = its 30-bit cell key).
+// b = cell bits of the level (uniform), s = 2^(l-1) (uniform).
+__device__ __forceinline__ void hat_cell(double x, uint32_t q, int b, uint32_t odd, double s, double &ph,
+                                         uint32_t &cell) {
+  cell = q >> (kKeyBits - b);
+  const uint32_t i = (cell << 1) + odd;
+  const double t = fma(x, s, -u32_to_f64(i));  // x*2^(l-1) - i, one rounding as in the reference
+  ph = 1.0 - fabs(t);                          // |t| <= 1 by construction of the cell
+}
+
+__device__ __forceinline__ int bits_of(int l) { return l > 3 ? l - 2 : 1; }                     // l >= 2
+__device__ __forceinline__ double pow2_lm1(int l) { return __hiloint2double((1023 + l - 1) << 20, 0); }  // 2^(l-1)
+
 // ---- sinks: what happens at a leaf (= one subspace) --------------------------------------------
+template <int R>
 struct EvalSink {
-  double acc;
-  __device__ __forceinline__ void dense(const DeviceGrid &g, uint32_t slot, double P) {
-    acc = fma(__ldg(g.coef + slot), P, acc);
+  double acc[R];
+  __device__ __forceinline__ void dense(const DeviceGrid &g, int r, uint32_t slot, double P) {
+    acc[r] = fma(__ldg(g.coef + slot), P, acc[r]);
   }
-  __device__ __forceinline__ void hashed(const DeviceGrid &, const HashEnt &e, uint32_t, double P) {
-    acc = fma(e.coef, P, acc);
+  __device__ __forceinline__ void hashed(const DeviceGrid &, int r, const HashEnt &e, uint32_t, double P) {
+    acc[r] = fma(e.coef, P, acc[r]);
   }
+  static constexpr bool kFast = true;  // may use the FULL-group fast path (plain sum of products)
 };
 
+template <int R>
 struct BasisSink {
   int mode;  // 0 count, 1 fill, 2 dense
   double atol;
   int dropzeros;
-  long long cnt;      // entries emitted so far in this row
-  long long *colidx;  // row start (mode 1)
-  double *vals;
-  double *row;  // dense row base (mode 2)
+  long long cnt[R];      // entries emitted so far in this row
+  long long *colidx[R];  // row start (mode 1)
+  double *vals[R];
+  double *row[R];  // dense row base (mode 2)
   int64_t ldn;
-  __device__ __forceinline__ void emit(int32_t col, double v) {
+  __device__ __forceinline__ void emit(int r, int32_t col, double v) {
     if (col < 0 || v == 0.0 || (dropzeros && v < atol)) return;  // src/class.jl:450-453
     if (mode == 1) {
-      colidx[cnt] = col;
-      vals[cnt] = v;
+      colidx[r][cnt[r]] = col;
+      vals[r][cnt[r]] = v;
     } else if (mode == 2) {
-      row[(int64_t)col * ldn] = v;
+      row[r][(int64_t)col * ldn] = v;
     }
-    ++cnt;
+    ++cnt[r];
   }
-  __device__ __forceinline__ void dense(const DeviceGrid &g, uint32_t slot, double P) { emit(__ldg(g.orig + slot), P); }
-  __device__ __forceinline__ void hashed(const DeviceGrid &g, const HashEnt &, uint32_t hslot, double P) {
-    emit(__ldg(g.horig + hslot), P);
+  __device__ __forceinline__ void dense(const DeviceGrid &g, int r, uint32_t slot, double P) {
+    emit(r, __ldg(g.orig + slot), P);
   }
+  __device__ __forceinline__ void hashed(const DeviceGrid &g, int r, const HashEnt &, uint32_t hslot, double P) {
+    emit(r, __ldg(g.horig + hslot), P);
+  }
+  static constexpr bool kFast = false;
 };
 
-template <class Sink>
-__device__ __forceinline__ void leaf(const DeviceGrid &g, const TrieRec &r, double P, uint32_t O, Sink &sink) {
-  if (!(r.y & kRecHashed)) {
-    sink.dense(g, r.x + O, P);
-  } else {
-    const int lg = (int)((r.y >> 16) & 0xffu);
-    const uint32_t mask = (1u << lg) - 1u;
-    const unsigned long long key = (unsigned long long)O + 1ull;
-    uint32_t s = hash_slot(O, lg);
-    for (;;) {  // table is at most half full: an empty slot always ends the probe
-      const uint32_t hs = r.x + s;
-      const double2 raw = __ldg(reinterpret_cast<const double2 *>(g.hent + hs));
-      HashEnt e;
-      e.key = (unsigned long long)__double_as_longlong(raw.x);
-      e.coef = raw.y;
-      if (e.key == key) { sink.hashed(g, e, hs, P); break; }
-      if (e.key == 0ull) break;
-      s = (s + 1u) & mask;
+// per-thread state of R points
+template <int D, int R>
+struct Points {
+  double x[R][D];
+  uint32_t q[R][D];
+  // last-dimension tables, levels 2..kLeafTable (level 1: phi = 1, w = 0)
+  double ph[R][kLeafTable + 1];
+  uint32_t w[R][kLeafTable + 1];  // off(l) + cell_l
+};
+
+template <int R>
+struct Prefix {  // running product / position over the dimensions fixed so far
+  double P[R];
+  uint32_t O[R];
+};
+
+template <int R, class Sink>
+__device__ __forceinline__ void leaf_generic(const DeviceGrid &g, const TrieRec &r, const Prefix<R> &pf,
+                                             const uint32_t (&cell)[R], const double (&ph)[R], int pb, Sink &sink) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t pos = (cell[k] << pb) | pf.O[k];
+    const double P = pf.P[k] * ph[k];
+    if (!(r.y & kRecHashed)) {
+      sink.dense(g, k, r.x + pos, P);
+    } else {
+      const int lg = (int)((r.y >> 16) & 0xffu);
+      const uint32_t mask = (1u << lg) - 1u;
+      const unsigned long long key = (unsigned long long)pos + 1ull;
+      uint32_t s = hash_slot(pos, lg);
+      for (;;) {  // table is at most half full: an empty slot always ends the probe
+        const uint32_t hs = r.x + s;
+        const double2 raw = __ldg(reinterpret_cast<const double2 *>(g.hent + hs));
+        HashEnt e;
+        e.key = (unsigned long long)__double_as_longlong(raw.x);
+        e.coef = raw.y;
+        if (e.key == key) { sink.hashed(g, k, e, hs, P); break; }
+        if (e.key == 0ull) break;
+        s = (s + 1u) & mask;
+      }
     }
   }
 }
 
+// leaves of one prefix group [jb, je) of trie level D-1, generic form (any levels, dense or hashed)
+template <int D, int R, class Sink>
+__device__ __forceinline__ void leaves_generic(const DeviceGrid &g, const Points<D, R> &pt, const Prefix<R> &pf,
+                                               uint32_t jb, uint32_t je, int rem, int pb, Sink &sink) {
+  const TrieRec *rec = g.rec[D - 1];
+  for (uint32_t j = jb; j < je; ++j) {
+    const TrieRec r = ld_rec(rec + j);
+    const int l = (int)(r.y & 0xffu);
+    if (l - 1 > rem) break;
+    uint32_t cell[R];
+    double ph[R];
+    if (l > 1) {
+      const int b = bits_of(l);
+      const double s = pow2_lm1(l);
+      const uint32_t odd = l > 2 ? 1u : 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k) hat_cell(pt.x[k][D - 1], pt.q[k][D - 1], b, odd, s, ph[k], cell[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { cell[k] = 0u; ph[k] = 1.0; }
+    }
+    leaf_generic<R>(g, r, pf, cell, ph, pb, sink);
+  }
+}
+
+// FULL prefix group: levels 1..lm of the last dimension, dense, back to back (see asg_internal.h)
+template <int D, int R>
+__device__ __forceinline__ void leaves_full(const DeviceGrid &g, const Points<D, R> &pt, const Prefix<R> &pf,
+                                            uint32_t base1, int pb, int lm, EvalSink<R> &sink) {
+  const double *A0[R];
+  double inner[R];
+  const uint32_t npre8 = 8u << pb;  // byte stride between consecutive last-dimension cells
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    A0[k] = g.coef + (base1 + pf.O[k]);
+    inner[k] = __ldg(A0[k]);  // level 1: phi = 1, cell = 0
+  }
+#pragma unroll
+  for (int l = 2; l <= kLeafTable; ++l) {
+    if (l > lm) break;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const double *p;  // A0 + w * npre8 bytes in ONE instruction (IMAD.WIDE.U32)
+      asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(pt.w[k][l]), "r"(npre8), "l"(A0[k]));
+      inner[k] = fma(__ldg(p), pt.ph[k][l], inner[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) sink.acc[k] = fma(pf.P[k], inner[k], sink.acc[k]);
+}
+
 // ---- the walk: compile-time recursion over dimensions, so x[K], q[K], P, O all live in registers -
-template <int D, int K>
+template <int D, int R, int K>
 struct Walk {
   template <class Sink>
-  static __device__ __forceinline__ void run(const DeviceGrid &g, const double (&x)[D], const uint32_t (&q)[D],
-                                             double P, uint32_t O, uint32_t jb, uint32_t je, int rem, Sink &sink) {
-    const TrieRec *rec = g.rec[K];
-    TrieRec r = ld_rec(rec + jb);
-    for (uint32_t j = jb; j < je; ++j) {
-      const TrieRec rn = ld_rec(rec + j + 1);  // next sibling (or the sentinel): gives this node's child end
-      const int l = (int)(r.y & 0xffu);
-      if (l - 1 > rem) break;  // depth mask of _interpolate_until_level; siblings are sorted by level
-      double Pn = P;
-      uint32_t On = O;
-      if (l > 1) {
-        double ph;
-        uint32_t cell;
-        int b;
-        hat_li(x[K], q[K], l, ph, cell, b);
-        Pn = P * ph;
-        On = (O << b) | cell;
+  static __device__ __forceinline__ void run(const DeviceGrid &g, const Points<D, R> &pt, const Prefix<R> &pf,
+                                             uint32_t jb, uint32_t je, int rem, Sink &sink) {
+    if constexpr (K == D - 1) {
+      leaves_generic<D, R>(g, pt, pf, jb, je, rem, 0, sink);  // D == 1: the root's children are the leaves
+    } else {
+      const TrieRec *rec = g.rec[K];
+      TrieRec r = ld_rec(rec + jb);
+      for (uint32_t j = jb; j < je; ++j) {
+        const TrieRec rn = ld_rec(rec + j + 1);  // next sibling (or the sentinel): gives this node's child end
+        const int l = (int)(r.y & 0xffu);
+        if (l - 1 > rem) break;  // depth mask of _interpolate_until_level; siblings are sorted by level
+        Prefix<R> nx;
+        if (l > 1) {
+          const int b = (int)((r.y >> 24) & 0x3fu);  // packer: cell bits of the level
+          const uint32_t odd = (r.y >> 30) & 1u;     // packer: l > 2
+          const uint32_t twob = 1u << b;
+          const double s = pow2_lm1(l);
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            double ph;
+            uint32_t cell;
+            hat_cell(pt.x[k][K], pt.q[k][K], b, odd, s, ph, cell);
+            nx.P[k] = pf.P[k] * ph;
+            nx.O[k] = pf.O[k] * twob + cell;  // (O << b) | cell as one IMAD
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < R; ++k) { nx.P[k] = pf.P[k]; nx.O[k] = pf.O[k]; }
+        }
+        const int rem2 = rem - (l - 1);
+        if constexpr (K < D - 2) {
+          Walk<D, R, K + 1>::run(g, pt, nx, r.x, rn.x, rem2, sink);
+        } else {  // K == D-2: this node is a prefix group, its children are leaves
+          const int pb = (int)(r.w & 0xffu);
+          bool fast = false;
+          if constexpr (Sink::kFast) {
+            if (r.w & kRecFull) {
+              const int lm = min((int)((r.w >> 8) & 0xffu), rem2 + 1);
+              leaves_full<D, R>(g, pt, nx, r.z, pb, lm, sink);
+              fast = true;
+            }
+          }
+          if (!fast) leaves_generic<D, R>(g, pt, nx, r.x, rn.x, rem2, pb, sink);
+        }
+        r = rn;
       }
-      if constexpr (K < D - 1) {
-        Walk<D, K + 1>::run(g, x, q, Pn, On, r.x, rn.x, rem - (l - 1), sink);
-      } else {
-        leaf(g, r, Pn, On, sink);
-      }
-      r = rn;
     }
   }
 };
 
 // scale() of src/math.jl:301-309 with to = [0,1]:  0.0 + (1.0 * (x - lb)) / (ub - lb)
-template <int D>
+// Returns false for a point outside the domain / NaN; such a point is walked at the centre of the
+// cube (valid addresses) and its result is replaced by the reference's exact 0.0 afterwards.
+template <int D, int R>
 __device__ __forceinline__ bool load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp, int64_t sd,
-                                           double (&x)[D], uint32_t (&q)[D]) {
+                                           Points<D, R> &pt, int k) {
   bool inside = true;
+  double u[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     const double xd = X[m * sp + d * sd];
-    const double u = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));
-    x[d] = u;
-    inside = inside && (u >= 0.0) && (u <= 1.0);  // NaN fails both
-    const double k = u * 1073741824.0;              // exact
-    q[d] = (u >= 0.0 && u < 1.0) ? (uint32_t)k : ((1u << kKeyBits) - 1u);
+    u[d] = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));
+    inside = inside && (u[d] >= 0.0) && (u[d] <= 1.0);  // NaN fails both
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double v = inside ? u[d] : 0.5;
+    pt.x[k][d] = v;
+    pt.q[k][d] = v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);  // floor(v * 2^30), exact
+  }
+  // last-dimension tables
+  const double xl = pt.x[k][D - 1];
+  const uint32_t ql = pt.q[k][D - 1];
+  pt.ph[k][0] = pt.ph[k][1] = 1.0;
+  pt.w[k][0] = pt.w[k][1] = 0u;
+#pragma unroll
+  for (int l = 2; l <= kLeafTable; ++l) {
+    const int b = l > 3 ? l - 2 : 1;
+    uint32_t cell;
+    hat_cell(xl, ql, b, l > 2 ? 1u : 0u, pow2_lm1(l), pt.ph[k][l], cell);
+    // off(l) = number of cells of levels 1..l-1 = 0,1,3,5,9,17,33,65 = 2^(l-2) + 1 for l >= 3
+    const uint32_t off = l == 2 ? 1u : ((1u << (l - 2)) + 1u);
+    pt.w[k][l] = off + cell;
   }
   return inside;
 }
 
-template <int D>
-__global__ void __launch_bounds__(256) k_eval_subspace(const DeviceGrid g, const EvalArgs a) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += stride) {
-    double x[D];
-    uint32_t q[D];
-    const bool inside = load_point<D>(g, a.X, m, a.sp, a.sd, x, q);
-    EvalSink sink;
-    sink.acc = 0.0;
-    if (inside) Walk<D, 0>::run(g, x, q, 1.0, 0u, 0u, g.n_root, a.rem, sink);
-    a.out[m] = a.fvals ? (a.fvals[m] - sink.acc) : sink.acc;
+template <int D, int R>
+__global__ void __launch_bounds__(256, (R == 1 ? 2 : 1)) k_eval_subspace(const DeviceGrid g, const EvalArgs a) {
+  const int64_t tile = (int64_t)blockDim.x * R;
+  const int64_t stride = (int64_t)gridDim.x * tile;
+  for (int64_t base = (int64_t)blockIdx.x * tile; base < a.M; base += stride) {
+    Points<D, R> pt;
+    bool inside[R];
+    int64_t m[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      m[k] = base + (int64_t)k * blockDim.x + threadIdx.x;
+      const int64_t mm = m[k] < a.M ? m[k] : a.M - 1;  // tail lanes redo the last point, never store
+      inside[k] = load_point<D, R>(g, a.X, mm, a.sp, a.sd, pt, k);
+    }
+    EvalSink<R> sink;
+    Prefix<R> pf;
+#pragma unroll
+    for (int k = 0; k < R; ++k) { sink.acc[k] = 0.0; pf.P[k] = 1.0; pf.O[k] = 0u; }
+    Walk<D, R, 0>::run(g, pt, pf, 0u, g.n_root, a.rem, sink);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (m[k] < a.M) {
+        const double v = inside[k] ? sink.acc[k] : 0.0;
+        a.out[m[k]] = a.fvals ? (a.fvals[m[k]] - v) : v;
+      }
+    }
   }
 }
 
@@ -167,34 +315,32 @@ template <int D>
 __global__ void __launch_bounds__(256) k_basis_subspace(const DeviceGrid g, const BasisArgs a) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += stride) {
-    double x[D];
-    uint32_t q[D];
-    const bool inside = load_point<D>(g, a.X, m, a.sp, a.sd, x, q);
-    BasisSink sink;
+    Points<D, 1> pt;
+    const bool inside = load_point<D, 1>(g, a.X, m, a.sp, a.sd, pt, 0);
+    BasisSink<1> sink;
     sink.mode = a.mode;
     sink.atol = a.atol;
     sink.dropzeros = a.dropzeros;
-    sink.cnt = 0;
-    sink.colidx = nullptr;
-    sink.vals = nullptr;
-    sink.row = nullptr;
+    sink.cnt[0] = 0;
+    sink.colidx[0] = nullptr;
+    sink.vals[0] = nullptr;
+    sink.row[0] = nullptr;
     sink.ldn = a.ldn;
     if (a.mode == 1) {
       const long long p0 = a.row_ptr[m];
-      sink.colidx = a.colidx + p0;
-      sink.vals = a.vals + p0;
+      sink.colidx[0] = a.colidx + p0;
+      sink.vals[0] = a.vals + p0;
     } else if (a.mode == 2) {
-      sink.row = a.dense + m * a.ldm;
+      sink.row[0] = a.dense + m * a.ldm;
     }
-    if (inside) Walk<D, 0>::run(g, x, q, 1.0, 0u, 0u, g.n_root, INT_MAX / 2, sink);
-    if (a.mode == 0) a.row_nnz[m] = (unsigned long long)sink.cnt;
+    if (inside) {  // outside the domain every basis value is 0: the row is empty
+      Prefix<1> pf;
+      pf.P[0] = 1.0;
+      pf.O[0] = 0u;
+      Walk<D, 1, 0>::run(g, pt, pf, 0u, g.n_root, INT_MAX / 2, sink);
+    }
+    if (a.mode == 0) a.row_nnz[m] = (unsigned long long)sink.cnt[0];
   }
-}
-
-static int grid_for(int64_t M, int threads, int sms) {
-  const int64_t need = (M + threads - 1) / threads;
-  const int64_t cap = (int64_t)sms * 16;  // a few waves of resident CTAs, grid-stride beyond that
-  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
 static int sm_count() {
@@ -206,6 +352,12 @@ static int sm_count() {
     if (sms <= 0) sms = 148;
   }
   return sms;
+}
+
+static int grid_for(int64_t M, int per_block, int sms, int waves) {
+  const int64_t need = (M + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)sms * waves;  // resident CTAs x a few waves, grid-stride beyond that
+  return (int)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
 #define ASG_DISPATCH_D(D_, CALL)                                                          \
@@ -220,10 +372,20 @@ static int sm_count() {
 cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
   if (a.M <= 0) return cudaSuccess;
   const int threads = 256;
-  const int blocks = grid_for(a.M, threads, sm_count());
-#define CALL(DD) k_eval_subspace<DD><<<blocks, threads, 0, st>>>(g, a)
-  ASG_DISPATCH_D(g.D, CALL)
+  const int sms = sm_count();
+  // two points per thread once there is enough work to fill the machine with half the threads
+  const bool two = a.M >= (int64_t)sms * threads * 4;
+  if (two) {
+    const int blocks = grid_for(a.M, threads * 2, sms, 16);
+#define CALL(DD) k_eval_subspace<DD, 2><<<blocks, threads, 0, st>>>(g, a)
+    ASG_DISPATCH_D(g.D, CALL)
 #undef CALL
+  } else {
+    const int blocks = grid_for(a.M, threads, sms, 16);
+#define CALL(DD) k_eval_subspace<DD, 1><<<blocks, threads, 0, st>>>(g, a)
+    ASG_DISPATCH_D(g.D, CALL)
+#undef CALL
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -231,7 +393,7 @@ cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStr
 cudaError_t launch_basis_subspace(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches) {
   if (a.M <= 0) return cudaSuccess;
   const int threads = 256;
-  const int blocks = grid_for(a.M, threads, sm_count());
+  const int blocks = grid_for(a.M, threads, sm_count(), 16);
 #define CALL(DD) k_basis_subspace<DD><<<blocks, threads, 0, st>>>(g, a)
   ASG_DISPATCH_D(g.D, CALL)
 #undef CALL

@@ -79,9 +79,11 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
         if (l > 2 && (i < 1 || !(i & 1) || i > ((int64_t)1 << (l - 1)) - 1)) { demote("index out of range"); continue; }
         const int b = cell_bits((int)l);
         const uint64_t cell = l == 1 ? 0 : (l == 2 ? (uint64_t)(i >> 1) : (uint64_t)((i - 1) >> 1));
+        if (tb + b > kMaxPosBits) { demote("subspace position needs more than 32 bits"); continue; }
+        // dims 0..D-2: concatenate (dim 0 most significant); the last dim goes on top of them
+        if (d < D - 1 || D == 1) p = (b ? (p << b) : p) | cell;
+        else p |= cell << tb;
         tb += b;
-        if (tb > kMaxPosBits) { demote("subspace position needs more than 32 bits"); continue; }
-        p = (b ? (p << b) : p) | cell;
         lv[(size_t)n * D + d] = (uint8_t)l;
       }
     }
@@ -157,12 +159,19 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
       if (prev) while (k0 < D - 1 && prev[k0] == cur[k0]) ++k0;
       for (int k = k0; k < D; ++k) {
         TrieRec r;
-        r.y = cur[k];
+        r.y = cur[k] | ((uint32_t)cell_bits(cur[k]) << 24) | (cur[k] > 2 ? (1u << 30) : 0u);
+        r.z = 0;
+        r.w = 0;
         if (k < D - 1) {
           r.x = (uint32_t)out.rec[(size_t)k + 1].size();
         } else {
           r.x = base;
           r.y |= flags;
+        }
+        if (k == D - 2) {
+          int pb = 0;
+          for (int d = 0; d < D - 1; ++d) pb += cell_bits(cur[d]);
+          r.w = (uint32_t)pb;
         }
         out.rec[(size_t)k].push_back(r);
       }
@@ -170,12 +179,70 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
       ++out.subspaces;
       g0 = g1;
     }
+    if (canonical && D >= 2) {
+      // mark FULL prefix groups: children = levels 1..lm, all dense, back to back
+      auto &par = out.rec[(size_t)D - 2];
+      const auto &lf = out.rec[(size_t)D - 1];
+      for (size_t j = 0; j < par.size(); ++j) {
+        const uint32_t cb = par[j].x, ce = (j + 1 < par.size()) ? par[j + 1].x : (uint32_t)lf.size();
+        const int pb = (int)(par[j].w & 0xffu);
+        const int lm = (int)(ce - cb);
+        bool full = lm >= 1 && lm <= kLeafTable;
+        uint64_t expect = lf[cb].x;
+        for (int c = 0; full && c < lm; ++c) {
+          const TrieRec &r = lf[cb + c];
+          if ((int)(r.y & 0xffu) != c + 1 || (r.y & kRecHashed) || r.x != expect) full = false;
+          expect += 1ull << (pb + cell_bits(c + 1));
+        }
+        if (full) {
+          par[j].z = lf[cb].x;
+          par[j].w |= ((uint32_t)lm << 8) | kRecFull;
+          ++out.full_groups;
+        }
+      }
+    }
+    if (canonical && D >= 2 && out.hent.empty() && (int64_t)out.coef.size() == N && max_depth - 1 <= kRsgMaxBudget) {
+      // Is the node set exactly a regular sparse grid (src/train.jl:56-63)? Every subspace is complete
+      // (coef slots == N, no padding, no hash) -- it remains to check that the set of level vectors is
+      // {l : l_d <= ml_d, sum(l_d - 1) <= budget}: all present vectors satisfy that by construction of
+      // ml and budget, so it suffices to compare counts.
+      RsgParams &rp = out.rp;
+      rp.budget = (int)(max_depth - 1);
+      rp.cut = 0;
+      std::vector<int> mlv((size_t)D, 1);
+      for (int64_t n = 0; n < N; ++n)
+        for (int d = 0; d < D; ++d) mlv[(size_t)d] = std::max<int>(mlv[(size_t)d], lv[(size_t)n * D + d]);
+      for (int d = 0; d < D; ++d) rp.ml[d] = std::min(mlv[(size_t)d], rp.budget + 1);
+      // C[k][rem]: number of level vectors over dims k..D-1; S[k][rem]: coefficient slots
+      std::vector<std::vector<uint64_t>> Cn((size_t)D + 1, std::vector<uint64_t>((size_t)rp.budget + 1, 1));
+      std::vector<std::vector<uint64_t>> Sn = Cn;
+      bool fits = true;
+      for (int k = D - 1; k >= 0; --k)
+        for (int rem = 0; rem <= rp.budget; ++rem) {
+          uint64_t c = 0, sz = 0;
+          for (int l = 1; l <= std::min(rp.ml[k], rem + 1); ++l) {
+            c += Cn[(size_t)k + 1][(size_t)(rem - (l - 1))];
+            sz += Sn[(size_t)k + 1][(size_t)(rem - (l - 1))] << cell_bits(l);
+          }
+          Cn[(size_t)k][(size_t)rem] = c;
+          Sn[(size_t)k][(size_t)rem] = sz;
+          if (sz > 0xffffffffull) fits = false;
+        }
+      if (fits && Cn[0][(size_t)rp.budget] == (uint64_t)out.subspaces && Sn[0][(size_t)rp.budget] == (uint64_t)N &&
+          rp.ml[D - 1] <= kLeafTable && rp.ml[D - 2] <= kLeafTable) {
+        for (int k = 0; k <= D; ++k)
+          for (int rem = 0; rem <= rp.budget; ++rem) rp.S[k][rem] = (uint32_t)Sn[(size_t)k][(size_t)rem];
+        out.regular = true;
+      }
+    }
     if (canonical) {
       for (int k = 0; k < D; ++k) {
         out.trie_nodes += (int64_t)out.rec[(size_t)k].size();
         TrieRec s;
         s.x = (k < D - 1) ? (uint32_t)out.rec[(size_t)k + 1].size() : 0u;
         s.y = 0xffu;  // level 255: terminates every masked walk
+        s.z = 0;
+        s.w = 0;
         // the sentinel of level k+1 is pushed after this one, so .size() above is the real count
         out.rec[(size_t)k].push_back(s);
       }

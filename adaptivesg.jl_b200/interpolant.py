@@ -122,7 +122,8 @@ class SparseGridInterpolant:
         return gi.as_dict()
 
     def set_path(self, path: str = "auto"):
-        code = {"auto": _capi.ASG_PATH_AUTO, "sweep": _capi.ASG_PATH_SWEEP, "subspace": _capi.ASG_PATH_SUBSPACE}[path]
+        code = {"auto": _capi.ASG_PATH_AUTO, "sweep": _capi.ASG_PATH_SWEEP, "subspace": _capi.ASG_PATH_SUBSPACE,
+                "trie": _capi.ASG_PATH_TRIE}[path]
         check(_capi.load().asg_grid_set_path(self._ensure(), code))
         return self
 

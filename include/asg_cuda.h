@@ -46,7 +46,9 @@ extern "C" {
 /* evaluation engines; ASG_PATH_AUTO picks SUBSPACE when the grid is canonical, else SWEEP */
 #define ASG_PATH_AUTO 0
 #define ASG_PATH_SWEEP 1     /* tiled all-nodes sweep, exact reference semantics for ANY node set  */
-#define ASG_PATH_SUBSPACE 2  /* level-vector trie walk, one supporting node per subspace           */
+#define ASG_PATH_SUBSPACE 2  /* subspace walk, one supporting node per subspace (record-free on     */
+                             /* regular sparse grids, level-vector trie otherwise)                 */
+#define ASG_PATH_TRIE 3      /* subspace walk forced through the generic trie (tests: cross-check) */
 
 typedef struct asg_grid asg_grid;   /* opaque: device mirror of SparseGridInterpolant{D}, class.jl:281-319 */
 typedef struct asg_event asg_event; /* opaque: completion handle of an *_async call                        */
@@ -65,6 +67,7 @@ typedef struct asg_grid_info_t {
   int64_t hash_slots;      /* open-addressing slots of sparsely filled subspaces                    */
   int64_t device_bytes;    /* bytes resident in HBM for this grid                                   */
   int64_t generation;      /* bumped by every upload / append / set_coefs                           */
+  int64_t regular;         /* 1: node set is exactly a regular sparse grid (record-free fast walk)  */
 } asg_grid_info_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -121,7 +124,7 @@ int32_t asg_surplus(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t
 int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const double *fvals, int64_t max_depth,
                           int32_t store, double *alpha);
 /* same two entry points with DEVICE pointers (points already resident in HBM), enqueued on
- * `stream` (a cudaStream_t; NULL = the library's stream) without host synchronisation */
+ * `stream` (a cudaStream_t; NULL = the CUDA default stream) without host synchronisation */
 int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
                         double *dout, void *stream);
 int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim,

@@ -80,7 +80,7 @@ def cfg_nonunit(oracle):
     return OG
 
 
-@pytest.mark.parametrize("path", ["subspace", "sweep"])
+@pytest.mark.parametrize("path", ["subspace", "trie", "sweep"])
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg_d10", "cfg_nonunit"])
 def test_eval_parity(asg, request, name, path):
     OG = request.getfixturevalue(name)
@@ -97,7 +97,8 @@ def test_eval_parity(asg, request, name, path):
     assert outside.sum() >= 20
     assert np.all(got[outside] == 0.0)
     info = G.info()
-    assert info["path"] == (2 if path == "subspace" else 1)
+    assert info["path"] == (1 if path == "sweep" else 2)
+    assert info["regular"] == (0 if name == "cfg2" else 1)    # regular grids take the record-free walk
 
 
 def test_eval_layouts_and_scalar_call(asg, cfg1):
@@ -129,13 +130,13 @@ def test_interpolation_property(asg, cfg1, cfg_nonunit):
         assert np.max(np.abs(got - OG.fvals)) < 5e-14 * max(1.0, np.max(np.abs(OG.fvals)))
 
 
-@pytest.mark.parametrize("path", ["subspace", "sweep"])
+@pytest.mark.parametrize("path", ["subspace", "trie", "sweep"])
 def test_masked_eval_and_surplus(asg, cfg1, cfg2, path):
     rng = np.random.default_rng(3)
     for OG in (cfg1, cfg2):
         G = _mirror(asg, OG).set_path(path)
         X = rng.random((500, OG.D))
-        for L in (1, 2, 3, 5, int(OG.depths.max())):
+        for L in (0, 1, 2, 3, 5, int(OG.depths.max()), int(OG.depths.max()) + 3):
             want, sc = OG.evaluate(X, max_depth=L, return_abssum=True)
             assert_close(G.evaluate(X, max_depth=L), want, sc, f"mask {L}")
         f = rng.standard_normal(500)
@@ -342,7 +343,7 @@ def test_async_and_set_coefs(asg, cfg1):
     cfg.levels, cfg.indices, cfg.depths, cfg.coefs, cfg.fvals = cfg1.levels, cfg1.indices, cfg1.depths, new, cfg1.fvals
     want, sc = cfg.evaluate(X, return_abssum=True)
     assert_close(G.evaluate(X), want, sc, "after set_coefs")
-    for p in ("sweep", "subspace"):
+    for p in ("sweep", "trie", "subspace"):
         G.set_path(p)
         assert_close(G.evaluate(X), want, sc, "after set_coefs " + p)
 
@@ -367,11 +368,20 @@ def test_full_size_properties(asg):
     G.coefs = 2.0 * c1 - 0.5 * c2                            # exact scaling by powers of two
     y3 = G.evaluate(X)
     assert np.max(np.abs(y3 - (2.0 * y1 - 0.5 * y2))) < 1e-12
-    # sweep engine on a subsample agrees with the subspace engine
+    # sweep engine and generic trie walk on a subsample agree with the record-free regular walk
+    assert info["regular"] == 1
     G.set_path("sweep")
     ys = G.evaluate(X[:256])
     assert np.max(np.abs(ys - y3[:256])) < 1e-12
+    G.set_path("trie")
+    yt = G.evaluate(X[:4096])
+    assert np.max(np.abs(yt - y3[:4096])) < 1e-12
     G.set_path("auto")
+    # large batch (two points per thread) equals small batches (one point per thread)
+    Xb = rng.random((400000, D))
+    yb = G.evaluate(Xb)
+    ysmall = np.concatenate([G.evaluate(Xb[k:k + 50000]) for k in range(0, 100000, 50000)])
+    assert np.array_equal(yb[:100000], ysmall)
     # coefficient 1 on the root only -> G == 1 everywhere inside; basis row sums to the constant
     G.coefs = np.where(G.depths == 1, 1.0, 0.0)
     assert np.all(G.evaluate(X[:1000]) == 1.0)

@@ -152,7 +152,20 @@ def test_packer_trie_sizes(asg):
     asg.rsg(G, 7, 5)
     rc, info, _ = _pack_info(asg, G.levels, G.indices)
     assert rc == 0 and info["canonical"] == 1 and info["subspaces"] == 72 and info["coef_slots"] == 737
-    assert info["max_level"] == 5 and info["max_depth"] == 7 and info["hash_slots"] == 0
+    assert info["max_level"] == 5 and info["max_depth"] == 7 and info["hash_slots"] == 0 and info["regular"] == 1
+    # drop one node / one whole subspace: still canonical, no longer a regular sparse grid
+    keep = np.ones(len(G.levels), bool)
+    keep[100] = False
+    rc, info2, _ = _pack_info(asg, G.levels[keep], G.indices[keep])
+    assert rc == 0 and info2["canonical"] == 1 and info2["regular"] == 0
+    keep = ~np.all(G.levels == G.levels[-1], axis=1)
+    rc, info3, _ = _pack_info(asg, G.levels[keep], G.indices[keep])
+    assert rc == 0 and info3["canonical"] == 1 and info3["regular"] == 0 and info3["subspaces"] == 71
+    # anisotropic caps are regular too
+    A = asg.SparseGridInterpolant(4)
+    asg.rsg(A, 6, (4, 5, 6, 3))
+    rc, info4, _ = _pack_info(asg, A.levels, A.indices)
+    assert rc == 0 and info4["regular"] == 1
     G = asg.SparseGridInterpolant(10)
     asg.rsg(G, 8, 8)
     rc, info, _ = _pack_info(asg, G.levels, G.indices)
@@ -163,6 +176,7 @@ def test_packer_trie_sizes(asg):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg2_nodes.npz"))
     rc, info, _ = _pack_info(asg, g["key"][:, :2], g["key"][:, 2:])
     assert rc == 0 and info["canonical"] == 1 and info["subspaces"] == 148 and info["hash_slots"] > 0
+    assert info["regular"] == 0
 
 
 def test_packer_rejects_and_demotes(asg):
