@@ -15,6 +15,7 @@
 //        IMAD.WIDE (address), LDG (coefficient gather), DFMA.
 // Arithmetic per 1-D hat is the reference's phi on its support (see asg_kernels_subspace.cu).
 #include <climits>
+#include <cstdlib>
 
 #include "asg_internal.h"
 
@@ -232,7 +233,8 @@ cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp_in, const E
   if (a.rem < 0) rp.cut = rp.budget + 1;  // nothing qualifies: every loop bound becomes 0
   const int threads = 128;
   const int sms = sm_count();
-  const bool two = a.M >= (int64_t)sms * threads * 8;
+  bool two = a.M >= (int64_t)sms * threads * 8;
+  if (const char *e = getenv("ASG_RSG_R")) two = (e[0] == '2');  // experiment knob
   const int per_block = threads * (two ? 2 : 1);
   int64_t need = (a.M + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sms * 32;
