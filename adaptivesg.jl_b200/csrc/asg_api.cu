@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
@@ -97,6 +98,8 @@ struct asg_grid {
   DeviceGrid dg{};
   // device storage
   DevBuf<TrieRec> d_rec;
+  DevBuf<GroupRec> d_grp;
+  DevBuf<StreamTile> d_tiles;
   DevBuf<double> d_coef, d_sw_coef;
   DevBuf<int32_t> d_orig, d_horig, d_sw_depth;
   DevBuf<HashEnt> d_hent;
@@ -111,7 +114,15 @@ struct asg_grid {
     if (forced_path == ASG_PATH_SWEEP) return ASG_PATH_SWEEP;
     return (canonical && finite) ? ASG_PATH_SUBSPACE : ASG_PATH_SWEEP;
   }
-  bool use_rsg() const { return regular && forced_path != ASG_PATH_TRIE; }
+  // which walk of the subspace engine: 0 = flat group stream (default), 1 = record-free regular walk,
+  // 2 = recursive trie walk (ASG_PATH_TRIE, D == 1, or ASG_EVAL_KERNEL=trie)
+  int walk() const {
+    static const char *env = getenv("ASG_EVAL_KERNEL");
+    if (forced_path == ASG_PATH_TRIE || D < 2 || dg.n_tiles == 0) return 2;
+    if (env && env[0] == 't') return 2;
+    if (env && env[0] == 'r' && regular) return 1;
+    return 0;
+  }
 };
 
 struct asg_event {
@@ -175,6 +186,16 @@ int device_upload(asg_grid *g, const PackResult &pk) {
       CK(cudaMemcpyAsync(g->d_hent.p, pk.hent.data(), pk.hent.size() * sizeof(HashEnt), cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(g->d_horig.p, pk.horig.data(), pk.horig.size() * 4, cudaMemcpyHostToDevice, st));
     }
+    if (int rc = g->d_grp.reserve(pk.grp.size())) return rc;
+    if (int rc = g->d_tiles.reserve(pk.tiles.size())) return rc;
+    if (!pk.grp.empty()) {
+      CK(cudaMemcpyAsync(g->d_grp.p, pk.grp.data(), pk.grp.size() * sizeof(GroupRec), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(g->d_tiles.p, pk.tiles.data(), pk.tiles.size() * sizeof(StreamTile), cudaMemcpyHostToDevice, st));
+    }
+    dg.grp = g->d_grp.p;
+    dg.tiles = g->d_tiles.p;
+    dg.n_grp = (uint32_t)pk.grp.size();
+    dg.n_tiles = (uint32_t)pk.tiles.size();
     dg.coef = g->d_coef.p;
     dg.orig = g->d_orig.p;
     dg.hent = g->d_hent.p;
@@ -211,9 +232,9 @@ int repack(asg_grid *g) {
   I.subspaces = pk.subspaces;
   I.dense_subspaces = pk.dense_subspaces;
   I.trie_nodes = pk.trie_nodes;
-  I.coef_slots = (int64_t)pk.coef.size();
+  I.coef_slots = (int64_t)pk.coef.size() - pk.coef_pad;
   I.hash_slots = (int64_t)pk.hent.size();
-  I.device_bytes = (int64_t)(g->d_rec.bytes() + g->d_coef.bytes() + g->d_orig.bytes() + g->d_hent.bytes() +
+  I.device_bytes = (int64_t)(g->d_rec.bytes() + g->d_grp.bytes() + g->d_tiles.bytes() + g->d_coef.bytes() + g->d_orig.bytes() + g->d_hent.bytes() +
                              g->d_horig.bytes() + g->d_sw.bytes() + g->d_sw_low.bytes() + g->d_sw_coef.bytes() +
                              g->d_sw_depth.bytes());
   I.generation = gen;
@@ -247,7 +268,8 @@ cudaError_t run_eval(asg_grid *g, const EvalArgs &a, cudaStream_t st) {
   int64_t l = 0;
   cudaError_t e;
   if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(g->dg, a, st, &l);
-  else if (g->use_rsg()) e = launch_eval_rsg(g->dg, g->rp, a, st, &l);
+  else if (g->walk() == 0) e = launch_eval_stream(g->dg, a, st, &l);
+  else if (g->walk() == 1) e = launch_eval_rsg(g->dg, g->rp, a, st, &l);
   else e = launch_eval_subspace(g->dg, a, st, &l);
   bump(l);
   return e;
@@ -431,7 +453,7 @@ int32_t asg_grid_destroy(asg_grid *g) {
     std::lock_guard<std::recursive_mutex> lk(g->mu);
     if (ctx.ready) {
       cudaSetDevice(ctx.device);
-      g->d_rec.release(); g->d_coef.release(); g->d_sw_coef.release(); g->d_orig.release(); g->d_horig.release();
+      g->d_rec.release(); g->d_grp.release(); g->d_tiles.release(); g->d_coef.release(); g->d_sw_coef.release(); g->d_orig.release(); g->d_horig.release();
       g->d_sw_depth.release(); g->d_hent.release(); g->d_sw.release(); g->d_sw_low.release();
       for (int s = 0; s < 2; ++s) { g->s_X[s].release(); g->s_out[s].release(); g->s_f[s].release(); }
       g->s_i64a.release(); g->s_i64b.release(); g->s_tmp.release(); g->s_tmp2.release(); g->s_flag.release();
@@ -911,7 +933,7 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->subspaces = pk.subspaces;
   info->dense_subspaces = pk.dense_subspaces;
   info->trie_nodes = pk.trie_nodes;
-  info->coef_slots = (int64_t)pk.coef.size();
+  info->coef_slots = (int64_t)pk.coef.size() - pk.coef_pad;
   info->hash_slots = (int64_t)pk.hent.size();
   info->regular = pk.regular ? 1 : 0;
   if (!pk.canonical) t_err = pk.why;

@@ -51,6 +51,30 @@ struct SweepDim {  // one (node, dimension) of the sweep engine: phi = hat(x*s -
   double c;        // (double) i, or 0 for l == 1
 };
 
+// ---- flat group stream (asg_kernels_stream.cu) -----------------------------------------------------
+// One 32-byte record per prefix group (= trie node of level D-2) in depth-first order, carrying the
+// whole path so that no tree bookkeeping is left on the device: the kernel runs ONE flat loop over
+// the records, re-derives the prefix products only from dimension k0 on, and evaluates the group's
+// leaves. Records and the coefficient slices they reference are streamed through shared memory in
+// tiles (cp.async.bulk + mbarrier, double buffered).
+struct __align__(16) GroupRec {
+  uint32_t base1;   // FULL: coefficient slot of the level-1 leaf; GENERIC: first leaf record (rec[D-1])
+  uint32_t npre8;   // 8 << pb: byte stride between consecutive last-dimension cells
+  uint32_t meta;    // bits 0..7 lm | 8..15 k0 | 16..23 used = sum(l-1) of the prefix | 24 FULL | 25 GLOBAL
+  uint32_t nchild;  // GENERIC: number of leaf records
+  uint32_t lev_lo;  // levels of dimensions 0..D-2, 5 bits each (dims 0..5 here,
+  uint32_t lev_hi;  //  dims 6..11 here)
+  uint32_t s_hi;    // dimension D-2: high word of the double 2^(l-1) (unused when l == 1)
+  uint32_t bod;     // dimension D-2: bits 0..7 cell bits b | bit 8 (l > 2) | bits 16..23 pb
+};
+constexpr uint32_t kGrpFull = 1u << 24;
+constexpr uint32_t kGrpGlobal = 1u << 25;  // coefficients are read from global memory, not from the tile
+struct StreamTile {  // records [r0, r1) reference FULL-group coefficient slots inside [c0, c1)
+  uint32_t r0, r1, c0, c1;
+};
+constexpr int kTileCoefs = 4096;  // doubles per shared-memory coefficient tile (32 KB)
+constexpr int kTileRecs = 128;    // records per tile (4 KB)
+
 // Everything the kernels need, passed by value as a kernel parameter.
 struct DeviceGrid {
   int D;
@@ -63,6 +87,9 @@ struct DeviceGrid {
   const int32_t *orig;              // slot -> caller's node number, -1 = padding
   const HashEnt *hent;              // hashed subspaces
   const int32_t *horig;
+  const GroupRec *grp;              // flat group stream
+  const StreamTile *tiles;
+  uint32_t n_grp, n_tiles;
   // sweep engine (caller's node order)
   int64_t N;
   const SweepDim *sw;       // [N][D]
@@ -90,11 +117,14 @@ struct PackResult {
   int64_t max_depth = 0;
   int64_t subspaces = 0, dense_subspaces = 0, trie_nodes = 0, full_groups = 0;
   std::vector<std::vector<TrieRec>> rec;  // [D] levels, sentinel included
-  std::vector<double> coef;
+  std::vector<double> coef;           // + coef_pad zero slots at the end (tile copies are 16-byte granular)
+  int64_t coef_pad = 0;
   std::vector<int32_t> orig;
   std::vector<HashEnt> hent;
   std::vector<int32_t> horig;
   std::vector<int64_t> slot_of_node;  // >= 0: dense slot; < 0: -(hash slot) - 1
+  std::vector<GroupRec> grp;          // flat group stream (D >= 2)
+  std::vector<StreamTile> tiles;
   bool regular = false;               // node set is exactly a regular sparse grid: RsgParams valid
   RsgParams rp{};
   // sweep engine
@@ -131,6 +161,7 @@ struct BasisArgs {
 };
 
 cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);

@@ -1,0 +1,396 @@
+// asg_kernels_stream.cu -- STREAM walk of the subspace engine (sm_100a): the main evaluation kernel.
+//
+//   G(x) = sum_n c_n prod_d phi(x01_d; l_nd, i_nd)                       (src/class.jl:629-643)
+//
+// The level-vector trie of asg_pack.cpp is flattened on the host into one 32-byte record per prefix
+// group (all subspaces that share the levels of dimensions 0..D-2), in depth-first order, so the
+// device runs ONE flat loop with no tree bookkeeping:
+//   * the CTA streams tiles of {records, the coefficient slices they reference} from L2 into shared
+//     memory with 1-D TMA bulk copies (cp.async.bulk) completed on mbarriers, double buffered;
+//   * a thread owns R query points; a record is a warp-uniform broadcast read from shared memory;
+//   * per record the prefix products P[k] / prefix positions O[k] are re-derived only from the first
+//     dimension k0 whose level changed (a fall-through switch, so P[k], O[k] stay in registers);
+//   * the leaves of the group are the levels 1..lm of the last dimension, evaluated against
+//     per-point register tables (hat value, cell) as  IMAD (address), LDS.64 (gather), DFMA.
+// The 1-D hat is the reference's phi (src/math.jl:345-357) evaluated on its support only, with the
+// reference's single rounding (see asg_device.cuh). Out-of-domain / NaN points give exactly 0.0.
+// Groups that are not FULL (adapt! output: missing levels, hashed subspaces) or whose slice exceeds
+// a tile take the same loop but read leaf records / coefficients from global memory.
+#include <cstdlib>
+
+#include "asg_device.cuh"
+
+namespace asg {
+
+constexpr int kStreamThreads = 256;
+
+struct __align__(16) StreamSmem {
+  double coef[2][kTileCoefs];
+  GroupRec rec[2][kTileRecs];
+  unsigned long long bar[2];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// producer side (one thread): start the copies of tile t into buffer `buf`
+__device__ __forceinline__ void issue_tile(const DeviceGrid &g, StreamSmem &sm, uint32_t t, int buf) {
+  const StreamTile tl = g.tiles[t];
+  const uint32_t rbytes = (tl.r1 - tl.r0) * (uint32_t)sizeof(GroupRec);
+  const uint32_t cbytes = (tl.c1 - tl.c0) * 8u;
+  // the buffer was last read through the generic proxy: order those reads before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(&sm.bar[buf], rbytes + cbytes);
+  tma_load_1d(sm.rec[buf], g.grp + tl.r0, rbytes, &sm.bar[buf]);
+  if (cbytes) tma_load_1d(sm.coef[buf], g.coef + tl.c0, cbytes, &sm.bar[buf]);
+}
+
+template <int D, int R>
+struct StreamPoints {
+  static constexpr int DP = D - 1;  // prefix dimensions 0..D-2
+  double x[R][DP];
+  uint32_t q[R][DP];
+  double ph[R][kLeafTable + 1];   // last dimension: hat of level l (levels 2..8)
+  uint32_t w[R][kLeafTable + 1];  // last dimension: off(l) + cell_l
+  double xl[R];                   // last dimension coordinate / key (generic groups)
+  uint32_t ql[R];
+};
+
+template <int D, int R>
+__device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp,
+                                                  int64_t sd, StreamPoints<D, R> &pt, int k) {
+  bool inside = true;
+  double u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double xd = X[m * sp + d * sd];
+    u[d] = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));  // scale(), src/math.jl:308
+    inside = inside && (u[d] >= 0.0) && (u[d] <= 1.0);                      // NaN fails both
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double v = inside ? u[d] : 0.5;  // walked at the centre; the result is replaced by the exact 0.0
+    const uint32_t q = v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);  // floor(v*2^30), exact
+    if (d < D - 1) {
+      pt.x[k][d] = v;
+      pt.q[k][d] = q;
+    } else {
+      pt.xl[k] = v;
+      pt.ql[k] = q;
+      pt.ph[k][0] = pt.ph[k][1] = 1.0;
+      pt.w[k][0] = pt.w[k][1] = 0u;
+#pragma unroll
+      for (int l = 2; l <= kLeafTable; ++l) {
+        uint32_t cell;
+        hat_cell(v, q, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.ph[k][l], cell);
+        pt.w[k][l] = (l == 2 ? 1u : ((1u << (l - 2)) + 1u)) + cell;  // off(l) = 0,1,3,5,9,17,33,65
+      }
+    }
+  }
+  return inside;
+}
+
+// prefix products P[k][K], positions O[k][K] of R points over the D-1 prefix dimensions
+template <int D, int R>
+struct PrefixRegs {
+  double P[R][D - 1];
+  uint32_t O[R][D - 1];
+};
+
+// stage K: derive P[K], O[K] from P[K-1], O[K-1] for the level l of dimension K
+template <int D, int R, int K>
+__device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, int l, int b, uint32_t odd,
+                                      double s) {
+  if (l > 1) {
+    const uint32_t twob = 1u << b;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      double ph;
+      uint32_t cell;
+      hat_cell(pt.x[k][K], pt.q[k][K], b, odd, s, ph, cell);
+      if constexpr (K == 0) {
+        pr.P[k][0] = ph;
+        pr.O[k][0] = cell;
+      } else {
+        pr.P[k][K] = pr.P[k][K - 1] * ph;
+        pr.O[k][K] = pr.O[k][K - 1] * twob + cell;  // (O << b) | cell as one IMAD
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if constexpr (K == 0) {
+        pr.P[k][0] = 1.0;
+        pr.O[k][0] = 0u;
+      } else {
+        pr.P[k][K] = pr.P[k][K - 1];
+        pr.O[k][K] = pr.O[k][K - 1];
+      }
+    }
+  }
+}
+
+template <int D, int R, int K>
+__device__ __forceinline__ void stage_from_levels(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, uint32_t lev_lo,
+                                                  uint32_t lev_hi) {
+  const int l = (int)(((K < 6 ? lev_lo : lev_hi) >> (5 * (K % 6))) & 31u);
+  stage<D, R, K>(pt, pr, l, bits_of(l), l > 2 ? 1u : 0u, pow2_lm1(l));
+}
+
+// FULL group from the shared-memory tile: 32-bit shared addresses, LDS gathers
+template <int D, int R>
+__device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, const PrefixRegs<D, R> &pr,
+                                                uint32_t tile_addr, uint32_t slot0, uint32_t npre8, int lm,
+                                                double (&acc)[R]) {
+  uint32_t a0[R];
+  double inner[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    a0[k] = tile_addr + (slot0 + pr.O[k][D - 2]) * 8u;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner[k]) : "r"(a0[k]));  // level 1: phi = 1, cell = 0
+  }
+#pragma unroll
+  for (int l = 2; l <= kLeafTable; ++l) {
+    if (l > lm) break;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      double c;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(a0[k] + pt.w[k][l] * npre8));
+      inner[k] = fma(c, pt.ph[k][l], inner[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = fma(pr.P[k][D - 2], inner[k], acc[k]);
+}
+
+// FULL group whose slice is too large for a tile: same arithmetic, coefficients from global memory
+template <int D, int R>
+__device__ __forceinline__ void group_full_global(const DeviceGrid &g, const StreamPoints<D, R> &pt,
+                                                  const PrefixRegs<D, R> &pr, uint32_t base1, uint32_t npre8, int lm,
+                                                  double (&acc)[R]) {
+  const double *A0[R];
+  double inner[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    A0[k] = g.coef + (base1 + pr.O[k][D - 2]);
+    inner[k] = __ldg(A0[k]);
+  }
+#pragma unroll
+  for (int l = 2; l <= kLeafTable; ++l) {
+    if (l > lm) break;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const double *p = reinterpret_cast<const double *>(reinterpret_cast<const char *>(A0[k]) +
+                                                         (uint64_t)pt.w[k][l] * npre8);
+      inner[k] = fma(__ldg(p), pt.ph[k][l], inner[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = fma(pr.P[k][D - 2], inner[k], acc[k]);
+}
+
+// GENERIC group: explicit leaf records (any levels, dense or hashed), global memory
+template <int D, int R>
+__device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R> &pt,
+                                              const PrefixRegs<D, R> &pr, uint32_t jb, uint32_t n, int rem, int pb,
+                                              double (&acc)[R]) {
+  EvalSink<R> sink;
+  Prefix<R> pf;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    sink.acc[k] = acc[k];
+    pf.P[k] = pr.P[k][D - 2];
+    pf.O[k] = pr.O[k][D - 2];
+  }
+  const TrieRec *rec = g.rec[D - 1];
+  for (uint32_t j = jb; j < jb + n; ++j) {
+    const TrieRec r = ld_rec(rec + j);
+    const int l = (int)(r.y & 0xffu);
+    if (l - 1 > rem) break;
+    uint32_t cell[R];
+    double ph[R];
+    if (l > 1) {
+      const int b = bits_of(l);
+      const double s = pow2_lm1(l);
+      const uint32_t odd = l > 2 ? 1u : 0u;
+#pragma unroll
+      for (int k = 0; k < R; ++k) hat_cell(pt.xl[k], pt.ql[k], b, odd, s, ph[k], cell[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { cell[k] = 0u; ph[k] = 1.0; }
+    }
+    leaf_generic<R>(g, r, pf, cell, ph, pb, sink);
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = sink.acc[k];
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_stream(const DeviceGrid g, const EvalArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+  const int64_t tile_pts = (int64_t)blockDim.x * R;
+  const int64_t stride = (int64_t)gridDim.x * tile_pts;
+  const uint32_t ntiles = g.n_tiles;
+  if (threadIdx.x == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
+
+  for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
+    StreamPoints<D, R> pt;
+    bool inside[R];
+    int64_t m[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      m[k] = base + (int64_t)k * blockDim.x + threadIdx.x;
+      const int64_t mm = m[k] < a.M ? m[k] : a.M - 1;  // tail lanes redo the last point, never store
+      inside[k] = stream_load_point<D, R>(g, a.X, mm, a.sp, a.sd, pt, k);
+    }
+    if (threadIdx.x == 0) {
+      issue_tile(g, sm, 0, 0);
+      if (ntiles > 1) issue_tile(g, sm, 1, 1);
+    }
+    PrefixRegs<D, R> pr;
+    double acc[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) acc[k] = 0.0;
+    int kmin = 0;  // prefix registers are valid from dimension 0 .. kmin-1 (nothing at the start)
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      const int buf = (int)(t & 1u);
+      const StreamTile tl = g.tiles[t];
+      mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+      const uint32_t tile_addr = smem_u32(sm.coef[buf]);
+      const uint32_t nrec = tl.r1 - tl.r0;
+      for (uint32_t j = 0; j < nrec; ++j) {
+        const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.rec[buf][j]);        // base1, npre8, meta, nchild
+        const uint4 rb = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 1);  // lev_lo, lev_hi, s_hi, bod
+        const int used = (int)((ra.z >> 16) & 0xffu);
+        const int k0 = (int)((ra.z >> 8) & 0xffu);
+        if (used > a.rem) {  // depth mask of _interpolate_until_level: the whole group lies deeper
+          kmin = min(kmin, k0);
+          continue;
+        }
+        const int kfrom = min(k0, kmin);
+        kmin = D;  // after this record every prefix register is valid
+        // stages kfrom .. D-3 (rare) from the packed levels, stage D-2 (every record) from precomputed fields
+        switch (kfrom) {
+          case 0: if constexpr (D - 2 > 0) stage_from_levels<D, R, 0>(pt, pr, rb.x, rb.y);
+          case 1: if constexpr (D - 2 > 1) stage_from_levels<D, R, (D - 2 > 1 ? 1 : 0)>(pt, pr, rb.x, rb.y);
+          case 2: if constexpr (D - 2 > 2) stage_from_levels<D, R, (D - 2 > 2 ? 2 : 0)>(pt, pr, rb.x, rb.y);
+          case 3: if constexpr (D - 2 > 3) stage_from_levels<D, R, (D - 2 > 3 ? 3 : 0)>(pt, pr, rb.x, rb.y);
+          case 4: if constexpr (D - 2 > 4) stage_from_levels<D, R, (D - 2 > 4 ? 4 : 0)>(pt, pr, rb.x, rb.y);
+          case 5: if constexpr (D - 2 > 5) stage_from_levels<D, R, (D - 2 > 5 ? 5 : 0)>(pt, pr, rb.x, rb.y);
+          case 6: if constexpr (D - 2 > 6) stage_from_levels<D, R, (D - 2 > 6 ? 6 : 0)>(pt, pr, rb.x, rb.y);
+          case 7: if constexpr (D - 2 > 7) stage_from_levels<D, R, (D - 2 > 7 ? 7 : 0)>(pt, pr, rb.x, rb.y);
+          case 8: if constexpr (D - 2 > 8) stage_from_levels<D, R, (D - 2 > 8 ? 8 : 0)>(pt, pr, rb.x, rb.y);
+          case 9: if constexpr (D - 2 > 9) stage_from_levels<D, R, (D - 2 > 9 ? 9 : 0)>(pt, pr, rb.x, rb.y);
+          default: break;
+        }
+        {
+          const int lA = (int)(((D - 2 < 6 ? rb.x : rb.y) >> (5 * ((D - 2) % 6))) & 31u);
+          stage<D, R, D - 2>(pt, pr, lA, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
+        }
+        const int rem = a.rem - used;  // budget left for the last dimension
+        if (ra.z & kGrpFull) {
+          const int lm = min((int)(ra.z & 0xffu), rem + 1);
+          if (!(ra.z & kGrpGlobal)) group_full_smem<D, R>(pt, pr, tile_addr, ra.x - tl.c0, ra.y, lm, acc);
+          else group_full_global<D, R>(g, pt, pr, ra.x, ra.y, lm, acc);
+        } else {
+          group_generic<D, R>(g, pt, pr, ra.x, ra.w, rem, (int)((rb.w >> 16) & 0xffu), acc);
+        }
+      }
+      __syncthreads();  // every warp is done with buffer `buf`
+      if (threadIdx.x == 0 && t + 2 < ntiles) issue_tile(g, sm, t + 2, buf);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if (m[k] < a.M) {
+        const double v = inside[k] ? acc[k] : 0.0;
+        a.out[m[k]] = a.fvals ? (a.fvals[m[k]] - v) : v;
+      }
+    }
+  }
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+#define ASG_DISPATCH_D2(D_, CALL)                                                         \
+  switch (D_) {                                                                           \
+    case 2: CALL(2); break;   case 3: CALL(3); break;                                     \
+    case 4: CALL(4); break;   case 5: CALL(5); break;   case 6: CALL(6); break;           \
+    case 7: CALL(7); break;   case 8: CALL(8); break;   case 9: CALL(9); break;           \
+    case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break;         \
+    default: return cudaErrorInvalidValue;                                                \
+  }
+
+cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
+  if (a.M <= 0) return cudaSuccess;
+  const int threads = kStreamThreads;
+  const int sms = sm_count();
+  const size_t smem = sizeof(StreamSmem);
+  bool two = a.M >= (int64_t)sms * threads * 4;
+  if (const char *e = getenv("ASG_STREAM_R")) two = (e[0] == '2');  // experiment knob
+  const int per_block = threads * (two ? 2 : 1);
+  // persistent-style grid: every CTA re-streams the whole grid per batch of points, so use as few
+  // batches as possible: one CTA per resident slot, grid-stride over the points
+  const int resident = two ? 1 : 2;
+  int64_t need = (a.M + per_block - 1) / per_block;
+  const int64_t cap = (int64_t)sms * resident;
+  const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+#define CALL(DD)                                                                                          \
+  do {                                                                                                    \
+    if (two) {                                                                                            \
+      cudaFuncSetAttribute(k_eval_stream<DD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_eval_stream<DD, 2><<<blocks, threads, smem, st>>>(g, a);                                          \
+    } else {                                                                                              \
+      cudaFuncSetAttribute(k_eval_stream<DD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      k_eval_stream<DD, 1><<<blocks, threads, smem, st>>>(g, a);                                          \
+    }                                                                                                     \
+  } while (0)
+  ASG_DISPATCH_D2(g.D, CALL)
+#undef CALL
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+}  // namespace asg

@@ -108,6 +108,8 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
       return a < b;
     });
     out.rec.assign((size_t)D, {});
+    std::vector<uint64_t> grp_levels;  // per prefix group: levels of dims 0..D-2, 5 bits each
+    std::vector<uint8_t> grp_k0, grp_used;
     const uint8_t *prev = nullptr;
     int64_t g0 = 0;
     while (g0 < N && canonical) {
@@ -169,9 +171,17 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
           r.y |= flags;
         }
         if (k == D - 2) {
-          int pb = 0;
-          for (int d = 0; d < D - 1; ++d) pb += cell_bits(cur[d]);
+          int pb = 0, used = 0;
+          uint64_t lvp = 0;
+          for (int d = 0; d < D - 1; ++d) {
+            pb += cell_bits(cur[d]);
+            used += cur[d] - 1;
+            lvp |= (uint64_t)(cur[d] & 31) << (5 * d);
+          }
           r.w = (uint32_t)pb;
+          grp_levels.push_back(lvp);
+          grp_k0.push_back((uint8_t)k0);  // first dimension whose level differs from the previous subspace
+          grp_used.push_back((uint8_t)std::min(used, 255));
         }
         out.rec[(size_t)k].push_back(r);
       }
@@ -234,6 +244,67 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
           for (int rem = 0; rem <= rp.budget; ++rem) rp.S[k][rem] = (uint32_t)Sn[(size_t)k][(size_t)rem];
         out.regular = true;
       }
+    }
+    if (canonical && D >= 2) {
+      // flat group stream + shared-memory tiles
+      const auto &par = out.rec[(size_t)D - 2];
+      const auto &lf = out.rec[(size_t)D - 1];
+      out.grp.resize(par.size());
+      std::vector<uint32_t> span_lo(par.size(), 0), span_hi(par.size(), 0);
+      for (size_t j = 0; j < par.size(); ++j) {
+        const TrieRec &r = par[j];
+        const uint32_t cb = r.x, ce = (j + 1 < par.size()) ? par[j + 1].x : (uint32_t)lf.size();
+        const int pb = (int)(r.w & 0xffu);
+        const int lA = (int)(r.y & 0xffu);
+        GroupRec &q = out.grp[j];
+        q.npre8 = 8u << pb;
+        q.lev_lo = (uint32_t)(grp_levels[j] & 0x3fffffffull);
+        q.lev_hi = (uint32_t)(grp_levels[j] >> 30);
+        q.s_hi = (uint32_t)(1023 + lA - 1) << 20;
+        q.bod = (uint32_t)cell_bits(lA) | (lA > 2 ? 0x100u : 0u) | ((uint32_t)pb << 16);
+        q.meta = ((uint32_t)grp_k0[j] << 8) | ((uint32_t)grp_used[j] << 16);
+        if (r.w & kRecFull) {
+          const int lm = (int)((r.w >> 8) & 0xffu);
+          q.base1 = r.z;
+          q.nchild = (uint32_t)lm;
+          q.meta |= (uint32_t)lm | kGrpFull;
+          span_lo[j] = r.z;
+          uint64_t cells = 0;
+          for (int l = 1; l <= lm; ++l) cells += 1ull << cell_bits(l);
+          span_hi[j] = (uint32_t)(r.z + (cells << pb));
+        } else {
+          q.base1 = cb;
+          q.nchild = ce - cb;
+          q.meta |= kGrpGlobal;
+        }
+      }
+      // greedy tiling: a tile covers consecutive records whose FULL slices fit kTileCoefs doubles
+      size_t j = 0;
+      while (j < par.size()) {
+        StreamTile t{(uint32_t)j, (uint32_t)j, 0u, 0u};
+        bool have = false;
+        while (j < par.size() && (int)(j - t.r0) < kTileRecs) {
+          GroupRec &q = out.grp[j];
+          if (q.meta & kGrpFull) {
+            const uint32_t lo = span_lo[j] & ~1u, hi = (span_hi[j] + 1u) & ~1u;  // 16-byte aligned bulk copies
+            if (hi - lo > (uint32_t)kTileCoefs) {
+              q.meta |= kGrpGlobal;  // a single slice larger than a tile: read it from global memory
+            } else if (!have) {
+              t.c0 = lo; t.c1 = hi; have = true;
+            } else {
+              const uint32_t nlo = std::min(t.c0, lo), nhi = std::max(t.c1, hi);
+              if (nhi - nlo > (uint32_t)kTileCoefs) break;  // does not fit any more: close the tile
+              t.c0 = nlo; t.c1 = nhi;
+            }
+          }
+          ++j;
+        }
+        t.r1 = (uint32_t)j;
+        out.tiles.push_back(t);
+      }
+      out.coef_pad = 2;
+      out.coef.resize(out.coef.size() + 2, 0.0);  // tiles round their end up to an even slot
+      out.orig.resize(out.orig.size() + 2, -1);
     }
     if (canonical) {
       for (int k = 0; k < D; ++k) {
