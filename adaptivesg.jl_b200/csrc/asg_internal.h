@@ -61,13 +61,17 @@ struct __align__(16) GroupRec {
   uint32_t base1;   // FULL: coefficient slot of the level-1 leaf; GENERIC: first leaf record (rec[D-1])
   uint32_t npre8;   // 8 << pb: byte stride between consecutive last-dimension cells
   uint32_t meta;    // bits 0..7 lm | 8..15 k0 | 16..23 used = sum(l-1) of the prefix | 24 FULL | 25 GLOBAL
-  uint32_t nchild;  // GENERIC: number of leaf records
+  uint32_t nchild;  // GENERIC: number of leaf records; SUPER: lmB of lA = 1..8, 4 bits each
   uint32_t lev_lo;  // levels of dimensions 0..D-2, 5 bits each (dims 0..5 here,
   uint32_t lev_hi;  //  dims 6..11 here)
   uint32_t s_hi;    // dimension D-2: high word of the double 2^(l-1) (unused when l == 1)
   uint32_t bod;     // dimension D-2: bits 0..7 cell bits b | bit 8 (l > 2) | bits 16..23 pb
 };
 constexpr uint32_t kGrpFull = 1u << 24;
+// SUPER record: all groups of one level-(D-3) node merged. They are the levels 1..lmA (meta bits 0..7)
+// of dimension D-2, each FULL with lmB(lA) levels of the last dimension (nchild: 4 bits per lA), stored
+// back to back starting at base1; npre8 = 8 << (position bits of dimensions 0..D-3).
+constexpr uint32_t kGrpSuper = 1u << 26;
 constexpr uint32_t kGrpGlobal = 1u << 25;  // coefficients are read from global memory, not from the tile
 struct StreamTile {  // records [r0, r1) reference FULL-group coefficient slots inside [c0, c1)
   uint32_t r0, r1, c0, c1;

@@ -75,8 +75,10 @@ struct StreamPoints {
   static constexpr int DP = D - 1;  // prefix dimensions 0..D-2
   double x[R][DP];
   uint32_t q[R][DP];
-  double ph[R][kLeafTable + 1];   // last dimension: hat of level l (levels 2..8)
-  uint32_t w[R][kLeafTable + 1];  // last dimension: off(l) + cell_l
+  double ph[R][kLeafTable + 1];    // last dimension: hat of level l (levels 2..8)
+  uint32_t w[R][kLeafTable + 1];   // last dimension: off(l) + cell_l
+  double phA[R][kLeafTable + 1];   // dimension D-2: hat of level l   (SUPER records)
+  uint32_t ceA[R][kLeafTable + 1]; // dimension D-2: cell of level l
   double xl[R];                   // last dimension coordinate / key (generic groups)
   uint32_t ql[R];
 };
@@ -99,6 +101,11 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
     if (d < D - 1) {
       pt.x[k][d] = v;
       pt.q[k][d] = q;
+      if (d == D - 2) {
+#pragma unroll
+        for (int l = 2; l <= kLeafTable; ++l)
+          hat_cell(v, q, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phA[k][l], pt.ceA[k][l]);
+      }
     } else {
       pt.xl[k] = v;
       pt.ql[k] = q;
@@ -214,6 +221,65 @@ __device__ __forceinline__ void group_full_global(const DeviceGrid &g, const Str
   for (int k = 0; k < R; ++k) acc[k] = fma(pr.P[k][D - 2], inner[k], acc[k]);
 }
 
+// SUPER record: levels 1..lmA of dimension D-2 x levels 1..lmB(lA) of dimension D-1, both unrolled
+// against the register tables. P, O are the prefix product / position over dimensions 0..D-3.
+// mask_rem < 0: no depth mask; otherwise budget left for the last two dimensions.
+template <int D, int R, bool SMEM>
+__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
+                                            const uint32_t (&O)[R], uint32_t tile_addr, uint32_t slot0, uint32_t base1,
+                                            uint32_t npre8, int lmA, uint32_t lmBs, int mask_rem, double (&acc)[R]) {
+  double inner2[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) inner2[k] = 0.0;
+  uint32_t sbase = tile_addr + slot0 * 8u;      // SMEM: byte address of the current group's slice
+  const char *gbase = reinterpret_cast<const char *>(g.coef + base1);  // !SMEM
+  if (mask_rem >= 0) lmA = min(lmA, mask_rem + 1);
+#pragma unroll
+  for (int lA = 1; lA <= kLeafTable; ++lA) {
+    if (lA > lmA) break;
+    constexpr int kDummy = 0;
+    (void)kDummy;
+    const int bA = lA == 1 ? 0 : (lA > 3 ? lA - 2 : 1);
+    const uint32_t np = npre8 << bA;  // byte stride between consecutive last-dimension cells
+    const int lmB_all = (int)((lmBs >> (4 * (lA - 1))) & 15u);
+    const int lmB = mask_rem >= 0 ? min(lmB_all, mask_rem - (lA - 1) + 1) : lmB_all;
+    uint32_t off[R];
+    double inner1[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const uint32_t OA = lA == 1 ? O[k] : ((O[k] << bA) | pt.ceA[k][lA]);
+      off[k] = OA * 8u;
+      if constexpr (SMEM) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner1[k]) : "r"(sbase + off[k]));
+      } else {
+        inner1[k] = __ldg(reinterpret_cast<const double *>(gbase + off[k]));
+      }
+    }
+#pragma unroll
+    for (int lB = 2; lB <= kLeafTable; ++lB) {
+      if (lB > lmB) break;
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        double c;
+        if constexpr (SMEM) {
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(sbase + off[k] + pt.w[k][lB] * np));
+        } else {
+          c = __ldg(reinterpret_cast<const double *>(gbase + off[k] + (uint64_t)pt.w[k][lB] * np));
+        }
+        inner1[k] = fma(c, pt.ph[k][lB], inner1[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) inner2[k] = lA == 1 ? inner1[k] : fma(pt.phA[k][lA], inner1[k], inner2[k]);
+    // next group starts after this one's cells: 1, 3, 5, 9, ... = off(lmB + 1) cells of np bytes each
+    const uint32_t cells = lmB_all < 2 ? 1u : ((1u << (lmB_all - 1)) + 1u);
+    if constexpr (SMEM) sbase += cells * np;
+    else gbase += (uint64_t)cells * np;
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = fma(P[k], inner2[k], acc[k]);
+}
+
 // GENERIC group: explicit leaf records (any levels, dense or hashed), global memory
 template <int D, int R>
 __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R> &pt,
@@ -250,7 +316,7 @@ __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamP
   for (int k = 0; k < R; ++k) acc[k] = sink.acc[k];
 }
 
-template <int D, int R>
+template <int D, int R, bool MASKED>
 __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_stream(const DeviceGrid g, const EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
@@ -297,12 +363,15 @@ __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_strea
         const uint4 rb = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 1);  // lev_lo, lev_hi, s_hi, bod
         const int used = (int)((ra.z >> 16) & 0xffu);
         const int k0 = (int)((ra.z >> 8) & 0xffu);
-        if (used > a.rem) {  // depth mask of _interpolate_until_level: the whole group lies deeper
-          kmin = min(kmin, k0);
-          continue;
+        int kfrom = k0;
+        if constexpr (MASKED) {
+          if (used > a.rem) {  // depth mask of _interpolate_until_level: the whole group lies deeper
+            kmin = min(kmin, k0);
+            continue;
+          }
+          kfrom = min(k0, kmin);
+          kmin = D;  // after this record every prefix register is valid
         }
-        const int kfrom = min(k0, kmin);
-        kmin = D;  // after this record every prefix register is valid
         // stages kfrom .. D-3 (rare) from the packed levels, stage D-2 (every record) from precomputed fields
         switch (kfrom) {
           case 0: if constexpr (D - 2 > 0) stage_from_levels<D, R, 0>(pt, pr, rb.x, rb.y);
@@ -317,11 +386,26 @@ __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_strea
           case 9: if constexpr (D - 2 > 9) stage_from_levels<D, R, (D - 2 > 9 ? 9 : 0)>(pt, pr, rb.x, rb.y);
           default: break;
         }
+        const int rem = MASKED ? a.rem - used : INT_MAX / 2;  // budget left below the prefix
+        if (ra.z & kGrpSuper) {
+          double P7[R];
+          uint32_t O7[R];
+#pragma unroll
+          for (int k = 0; k < R; ++k) {
+            if constexpr (D >= 3) { P7[k] = pr.P[k][D - 3]; O7[k] = pr.O[k][D - 3]; }
+            else { P7[k] = 1.0; O7[k] = 0u; }
+          }
+          const int lmA = (int)(ra.z & 0xffu);
+          if (!(ra.z & kGrpGlobal))
+            group_super<D, R, true>(g, pt, P7, O7, tile_addr, ra.x - tl.c0, ra.x, ra.y, lmA, ra.w, MASKED ? rem : -1, acc);
+          else
+            group_super<D, R, false>(g, pt, P7, O7, tile_addr, 0u, ra.x, ra.y, lmA, ra.w, MASKED ? rem : -1, acc);
+          continue;
+        }
         {
           const int lA = (int)(((D - 2 < 6 ? rb.x : rb.y) >> (5 * ((D - 2) % 6))) & 31u);
           stage<D, R, D - 2>(pt, pr, lA, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
         }
-        const int rem = a.rem - used;  // budget left for the last dimension
         if (ra.z & kGrpFull) {
           const int lm = min((int)(ra.z & 0xffu), rem + 1);
           if (!(ra.z & kGrpGlobal)) group_full_smem<D, R>(pt, pr, tile_addr, ra.x - tl.c0, ra.y, lm, acc);
@@ -377,18 +461,20 @@ cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStrea
   int64_t need = (a.M + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sms * resident;
   const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
+  const bool masked = a.rem < INT_MAX / 4;
+#define LAUNCH(DD, RR, MM)                                                                                      \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(k_eval_stream<DD, RR, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    k_eval_stream<DD, RR, MM><<<blocks, threads, smem, st>>>(g, a);                                             \
+  } while (0)
 #define CALL(DD)                                                                                          \
   do {                                                                                                    \
-    if (two) {                                                                                            \
-      cudaFuncSetAttribute(k_eval_stream<DD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      k_eval_stream<DD, 2><<<blocks, threads, smem, st>>>(g, a);                                          \
-    } else {                                                                                              \
-      cudaFuncSetAttribute(k_eval_stream<DD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      k_eval_stream<DD, 1><<<blocks, threads, smem, st>>>(g, a);                                          \
-    }                                                                                                     \
+    if (two) { if (masked) LAUNCH(DD, 2, true); else LAUNCH(DD, 2, false); }                              \
+    else     { if (masked) LAUNCH(DD, 1, true); else LAUNCH(DD, 1, false); }                              \
   } while (0)
   ASG_DISPATCH_D2(g.D, CALL)
 #undef CALL
+#undef LAUNCH
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -278,14 +278,58 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
           q.meta |= kGrpGlobal;
         }
       }
-      // greedy tiling: a tile covers consecutive records whose FULL slices fit kTileCoefs doubles
+      // merge the groups of one level-(D-3) node into a single SUPER record when they are the levels
+      // 1..lmA of dimension D-2, all FULL and stored back to back (always true on regular grids)
+      {
+        std::vector<GroupRec> merged;
+        std::vector<uint32_t> mlo, mhi;
+        const size_t ngrp = par.size();
+        std::vector<uint32_t> pbeg;  // child ranges of the level-(D-3) nodes inside rec[D-2]
+        if (D >= 3) {
+          for (const TrieRec &r : out.rec[(size_t)D - 3]) pbeg.push_back(r.x);
+        } else {
+          pbeg.push_back(0u);
+        }
+        pbeg.push_back((uint32_t)ngrp);
+        for (size_t pi = 0; pi + 1 < pbeg.size(); ++pi) {
+          const uint32_t cb = pbeg[pi], ce = pbeg[pi + 1];
+          const int lmA = (int)(ce - cb);
+          bool super = lmA >= 1 && lmA <= kLeafTable;
+          uint32_t lmBs = 0;
+          for (uint32_t j = cb; super && j < ce; ++j) {
+            const GroupRec &q = out.grp[j];
+            if (!(q.meta & kGrpFull) || (int)(par[j].y & 0xffu) != (int)(j - cb) + 1) super = false;
+            else if (j > cb && span_lo[j] != span_hi[j - 1]) super = false;
+            else lmBs |= (q.meta & 0xfu) << (4 * (j - cb));
+          }
+          if (super) {
+            GroupRec q = out.grp[cb];
+            q.meta = (uint32_t)lmA | (q.meta & 0x00ffff00u) | kGrpSuper;  // k0 and used of the first child (lA = 1)
+            q.nchild = lmBs;
+            merged.push_back(q);
+            mlo.push_back(span_lo[cb]);
+            mhi.push_back(span_hi[ce - 1]);
+          } else {
+            for (uint32_t j = cb; j < ce; ++j) {
+              merged.push_back(out.grp[j]);
+              mlo.push_back(span_lo[j]);
+              mhi.push_back(span_hi[j]);
+            }
+          }
+        }
+        out.grp.swap(merged);
+        span_lo.swap(mlo);
+        span_hi.swap(mhi);
+      }
+      // greedy tiling: a tile covers consecutive records whose dense slices fit kTileCoefs doubles
       size_t j = 0;
-      while (j < par.size()) {
+      const size_t nrec = out.grp.size();
+      while (j < nrec) {
         StreamTile t{(uint32_t)j, (uint32_t)j, 0u, 0u};
         bool have = false;
-        while (j < par.size() && (int)(j - t.r0) < kTileRecs) {
+        while (j < nrec && (int)(j - t.r0) < kTileRecs) {
           GroupRec &q = out.grp[j];
-          if (q.meta & kGrpFull) {
+          if (q.meta & (kGrpFull | kGrpSuper)) {
             const uint32_t lo = span_lo[j] & ~1u, hi = (span_hi[j] + 1u) & ~1u;  // 16-byte aligned bulk copies
             if (hi - lo > (uint32_t)kTileCoefs) {
               q.meta |= kGrpGlobal;  // a single slice larger than a tile: read it from global memory
