@@ -279,7 +279,11 @@ cudaError_t run_eval(asg_grid *g, const EvalArgs &a, cudaStream_t st) {
 // strides. Fast paths: row-major rows (sdim == 1) and column-major columns (sp == 1).
 int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, int64_t sdim, double *dX,
                  int64_t &dsp, int64_t &dsd, cudaStream_t st, std::vector<double> &repack_buf) {
-  if (sdim == 1 || D == 1) {
+  if ((sdim == 1 || D == 1) && sp == D) {  // dense row-major block: one flat copy
+    dsp = D;
+    dsd = 1;
+    CK(cudaMemcpyAsync(dX, X + m0 * sp, (size_t)cnt * D * 8, cudaMemcpyHostToDevice, st));
+  } else if (sdim == 1 || D == 1) {
     dsp = D;
     dsd = 1;
     CK(cudaMemcpy2DAsync(dX, (size_t)D * 8, X + m0 * sp, (size_t)sp * 8, (size_t)D * 8, (size_t)cnt,
@@ -306,7 +310,7 @@ int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, in
 int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
               int64_t max_depth, double *out) {
   const int D = g->D;
-  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 20);
+  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 22);  // 4 Mi points per pipeline slot
   std::vector<double> repack_buf;
   const int nslot = M > chunk ? 2 : 1;
   for (int s = 0; s < nslot; ++s) {

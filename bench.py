@@ -45,17 +45,26 @@ def build_grid_arrays():
 
 
 def fp64_op_counts(levels):
-    """FP64 work of the subspace walk for ONE point, counted from the trie of `levels` (N x D):
-    every trie node with level > 1 costs DADD (int->double) + DFMA + DADD (1-|t|) + DMUL (prefix product),
-    every subspace (leaf) one more DFMA for c * P. Returns (fp64 instructions, flops)."""
+    """FP64 work the stream kernel (asg_kernels_stream.cu, SUPER records) must do for ONE point, counted
+    from the level vectors of `levels` (N x D). Dimensions 0..D-3 are walked: every trie node there with
+    level > 1 costs DADD (int->double) + DFMA + DADD (1-|t|) + DMUL (prefix product) = 4 instr / 5 flop.
+    Dimensions D-2, D-1 come from per-point tables: 1 DFMA per subspace with l_{D-1} > 1, 1 DFMA per prefix
+    group with l_{D-2} > 1, 1 DFMA per level-(D-3) node (acc += P * inner); the tables themselves cost
+    2 * 7 * 3 instr once per point. Returns (fp64 instructions, flops, subspaces)."""
     lv = np.unique(levels, axis=0)
+    D = lv.shape[1]
     nontrivial = 0
-    for k in range(1, lv.shape[1] + 1):
+    for k in range(1, max(D - 2, 0) + 1):
         pre = np.unique(lv[:, :k], axis=0)
         nontrivial += int(np.count_nonzero(pre[:, k - 1] > 1))
     leaves = len(lv)
-    instr = 4 * nontrivial + leaves
-    flops = 5 * nontrivial + 2 * leaves
+    leaf_fma = int(np.count_nonzero(lv[:, -1] > 1))
+    groups = np.unique(lv[:, :-1], axis=0) if D >= 2 else np.zeros((1, 0))
+    group_fma = int(np.count_nonzero(groups[:, -1] > 1)) if D >= 2 else 0
+    supers = len(np.unique(lv[:, :-2], axis=0)) if D >= 3 else 1
+    fma = leaf_fma + group_fma + supers
+    instr = 4 * nontrivial + fma + 42
+    flops = 5 * nontrivial + 2 * fma + 2 * 7 * 4
     return instr, flops, leaves
 
 
@@ -300,7 +309,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_eval_subspace<10>) -----------------------------------
+    # ---- roofline of the dominant kernel (k_eval_stream<10,...>) -----------------------------------
     fma_rate = C.c_double()
     asg._capi.check(lib.asg_measure_fp64_peak(C.byref(fma_rate)))
     instr, flops, leaves = fp64_op_counts(G.levels)
@@ -315,7 +324,7 @@ def main():
     alg_bytes = pts_per_launch * (8 * D + 8)
     roofline = {
         "bound": "fp64",  # FP64 CUDA-core pipe: the path is a sparse gather-product, not HBM- or tensor-bound
-        "kernel": f"k_eval_subspace<{D}>",
+        "kernel": f"k_eval_stream<{D},R,false>",
         "achieved": flops * pts_per_launch / (k_ms * 1e-3) / 1e12,
         "peak": 2.0 * fma_rate.value / 1e12,
         "unit": "TFLOP/s",
@@ -334,10 +343,13 @@ def main():
                              "note": "N*M/t with every (node, point) pair counted, SURVEY.md 8d; > 1 because "
                                      "only the one supporting node per subspace is visited"},
     }
-    prof = os.path.join(ROOT, "profiles", "r01_eval_subspace_d10_summary.json")
+    prof = os.path.join(ROOT, "profiles", "r01_final_eval_stream_d10_summary.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            # ncu capture is of a shorter launch: scale its measured DRAM bytes to this launch's point count
+            roofline["traffic"] = pj["dram_bytes_per_launch"] * pts_per_launch / pj["points_per_launch"]
+            roofline["traffic_source"] = os.path.basename(prof)
         except Exception:
             pass
 

@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Secondary measurements: the other BASELINE.json configs (parity-test cases, not the headline line).
+One JSON line per config; run on a B200:  python benchmarks/bench_configs.py > gpurun_out/configs.jsonl
+
+cfg1  README D=3 RSG train!(7,5), evaluate 1e5 points            (+ oracle check on 2000 points)
+cfg2  D=2 train!(4,(3,8)) + adapt!(20, 1e-5), evaluate 1e7 points (hashed subspaces, generic groups)
+cfg4  D=6 train!(7,(6..11)) + adapt!(13, 3e-3): whole loop with the GPU surplus step per level
+cfg5  D=4 RSG(10,10): basis(X,G) sparse (count/fill/sort) and dense (HBM-write bound) for 5e4 points
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import asg_b200 as asg  # noqa: E402
+
+sinsum = lambda x: float(np.sum(np.sin(2 * np.pi * x)))
+sinsum_v = lambda X: np.sum(np.sin(2 * np.pi * X), axis=1)
+utility = lambda x: -1.0 / (0.1 + float(np.sum(x)))
+utility_v = lambda X: -1.0 / (0.1 + np.sum(X, axis=1))
+
+
+def timed(fn, reps=3):
+    fn()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        t.append(time.perf_counter() - t0)
+    return min(t)
+
+
+def main():
+    import torch
+    asg.init(0)
+    lib = asg._capi.load()
+    rng = np.random.default_rng(42)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    # ---- cfg1 -------------------------------------------------------------------------------------
+    G = asg.SparseGridInterpolant(3)
+    t0 = time.perf_counter()
+    asg.train(G, sinsum_v, 7, 5, vectorized=True)
+    t_train = time.perf_counter() - t0
+    X = rng.random((100000, 3))
+    dt = timed(lambda: G.evaluate(X))
+    from oracle import oracle as o
+    OG = o.OracleGrid(3)
+    OG.levels, OG.indices, OG.depths, OG.coefs, OG.fvals = G.levels, G.indices, G.depths, G.coefs, G.fvals
+    err = float(np.max(np.abs(G.evaluate(X[:2000]) - OG.evaluate(X[:2000]))))
+    print(json.dumps({"config": "cfg1", "nodes": len(G), "train_s": t_train, "points": len(X), "eval_ms": dt * 1e3,
+                      "points_per_s": len(X) / dt, "max_abs_err_vs_oracle": err, "info": G.info()}), flush=True)
+
+    # ---- cfg2 -------------------------------------------------------------------------------------
+    G = asg.SparseGridInterpolant(2)
+    t0 = time.perf_counter()
+    asg.train(G, utility_v, 4, (3, 8), vectorized=True)
+    asg.adapt(G, utility_v, 20, tol=1e-5, verbose=False, vectorized=True)
+    t_build = time.perf_counter() - t0
+    X = rng.random((10_000_000, 2))
+    dt = timed(lambda: G.evaluate(X), reps=2)
+    print(json.dumps({"config": "cfg2", "nodes": len(G), "train_adapt_s": t_build, "points": len(X),
+                      "eval_ms_host_buffers": dt * 1e3, "points_per_s": len(X) / dt, "info": G.info()}), flush=True)
+
+    # ---- cfg4 -------------------------------------------------------------------------------------
+    G = asg.SparseGridInterpolant(6)
+    l0 = asg.launch_count()
+    t0 = time.perf_counter()
+    asg.train(G, sinsum_v, 7, tuple(range(6, 12)), vectorized=True)
+    t_train = time.perf_counter() - t0
+    n_rsg = len(G)
+    log = []
+    t0 = time.perf_counter()
+    asg.adapt(G, sinsum_v, 13, tol=3e-3, verbose=False, vectorized=True, log=log)
+    t_adapt = time.perf_counter() - t0
+    print(json.dumps({"config": "cfg4", "rsg_nodes": n_rsg, "nodes": len(G), "train_s": t_train, "adapt_s": t_adapt,
+                      "levels": log, "kernel_launches": asg.launch_count() - l0, "info": G.info()}), flush=True)
+
+    # ---- cfg5 -------------------------------------------------------------------------------------
+    G = asg.SparseGridInterpolant(4)
+    asg.rsg(G, 10, 10)
+    G.coefs = rng.standard_normal(len(G))
+    N = len(G)
+    M = 50000
+    X = rng.random((M, 4))
+    t_sparse = timed(lambda: asg.basis(X, G), reps=2)
+    B = asg.basis(X, G)
+    y = G.evaluate(X)
+    err = float(np.max(np.abs(B @ G.coefs - y)))
+    # dense variant into a device buffer: HBM-write bound, 8*N bytes per point
+    dX = torch.from_numpy(X).cuda()
+    out = torch.empty((M, N), dtype=torch.float64, device="cuda")
+    h = G._ensure()
+    st = torch.cuda.current_stream().cuda_stream
+
+    def dense():
+        asg._capi.check(lib.asg_basis_dense_device(h, C.c_void_p(dX.data_ptr()), M, 4, 1, 1e-16, 1,
+                                                   C.c_void_p(out.data_ptr()), N, 1, C.c_void_p(st)))
+        torch.cuda.synchronize()
+    for _ in range(3):
+        dense()
+    ms = C.c_double()
+    ts = []
+    for _ in range(5):
+        dense()
+        asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))
+        ts.append(ms.value)
+    k_ms = float(np.median(ts))
+    gbs = M * N * 8 / (k_ms * 1e-3) / 1e9
+    nnz_dense = int(torch.count_nonzero(out).item())
+    print(json.dumps({"config": "cfg5", "nodes": N, "points": M, "sparse_basis_s": t_sparse, "nnz": int(B.nnz),
+                      "nnz_per_row": B.nnz / M, "B_times_C_vs_eval_max_abs": err, "dense_ms": k_ms,
+                      "dense_bytes": M * N * 8, "dense_write_GBps": gbs, "hbm_peak_GBps": peaks.get("hbm_gbs"),
+                      "dense_frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None,
+                      "dense_nnz_matches_sparse": nnz_dense == int(B.nnz)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
