@@ -122,7 +122,7 @@ def cpu_reference_rate(Gh, seconds_target, threads=0, steps=1, warmup=0):
     from oracle import oracle as o
     OG = o.OracleGrid(D)
     OG.levels, OG.indices, OG.depths, OG.coefs, OG.fvals = Gh.levels, Gh.indices, Gh.depths, Gh.coefs, Gh.fvals
-    cores = threads or o.num_threads()
+    cores = threads or os.cpu_count() or o.num_threads()   # torchrun exports OMP_NUM_THREADS=1: ask explicitly
     rng = np.random.default_rng(42)
     probe = rng.random((cores * 2, D))
     t0 = time.perf_counter()
