@@ -52,7 +52,7 @@ struct SweepDim {  // one (node, dimension) of the sweep engine: phi = hat(x*s -
 };
 
 // ---- flat group stream (asg_kernels_stream.cu) -----------------------------------------------------
-// One 32-byte record per prefix group (= trie node of level D-2) in depth-first order, carrying the
+// One 48-byte record per prefix group (= trie node of level D-2) in depth-first order, carrying the
 // whole path so that no tree bookkeeping is left on the device: the kernel runs ONE flat loop over
 // the records, re-derives the prefix products only from dimension k0 on, and evaluates the group's
 // leaves. Records and the coefficient slices they reference are streamed through shared memory in
@@ -66,7 +66,9 @@ struct __align__(16) GroupRec {
   uint32_t lev_hi;  //  dims 6..11 here)
   uint32_t s_hi;    // dimension D-2: high word of the double 2^(l-1) (unused when l == 1)
   uint32_t bod;     // dimension D-2: bits 0..7 cell bits b | bit 8 (l > 2) | bits 16..23 pb
+  uint16_t offs[8]; // SUPER: start of the slice of group lA = 1..8, in cells of npre8 bytes, relative to base1
 };
+static_assert(sizeof(GroupRec) == 48, "GroupRec is streamed as three 16-byte words");
 constexpr uint32_t kGrpFull = 1u << 24;
 // SUPER record: all groups of one level-(D-3) node merged. They are the levels 1..lmA (meta bits 0..7)
 // of dimension D-2, each FULL with lmB(lA) levels of the last dimension (nchild: 4 bits per lA), stored
@@ -77,7 +79,7 @@ struct StreamTile {  // records [r0, r1) reference FULL-group coefficient slots 
   uint32_t r0, r1, c0, c1;
 };
 constexpr int kTileCoefs = 4096;  // doubles per shared-memory coefficient tile (32 KB)
-constexpr int kTileRecs = 128;    // records per tile (4 KB)
+constexpr int kTileRecs = 128;    // records per tile (6 KB)
 
 // Everything the kernels need, passed by value as a kernel parameter.
 struct DeviceGrid {

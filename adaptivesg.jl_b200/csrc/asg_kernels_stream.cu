@@ -22,12 +22,19 @@
 
 namespace asg {
 
-constexpr int kStreamThreads = 256;
+// threads per CTA: one point per thread -> 2 CTAs of 256 per SM; two points per thread -> 1 CTA of 384
+template <int R>
+struct StreamCfg {
+  static constexpr int kThreads = R == 1 ? 256 : 384;
+  static constexpr int kCtasPerSm = R == 1 ? 2 : 1;
+};
 
 struct __align__(16) StreamSmem {
   double coef[2][kTileCoefs];
   GroupRec rec[2][kTileRecs];
   unsigned long long bar[2];
+  // followed by the unit-cube coordinates / cell keys of the prefix dimensions of every point of the
+  // CTA: double xs[D-1][R][threads]; uint32_t qs[D-1][R][threads]  (read only at non-trivial stages)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,9 +79,9 @@ __device__ __forceinline__ void issue_tile(const DeviceGrid &g, StreamSmem &sm, 
 
 template <int D, int R>
 struct StreamPoints {
-  static constexpr int DP = D - 1;  // prefix dimensions 0..D-2
-  double x[R][DP];
-  uint32_t q[R][DP];
+  static constexpr int DP = D - 1;  // prefix dimensions 0..D-2: coordinates live in shared memory
+  const double *xs;                 // xs[(K*R + k)*threads + tid]
+  const uint32_t *qs;
   double ph[R][kLeafTable + 1];    // last dimension: hat of level l (levels 2..8)
   uint32_t w[R][kLeafTable + 1];   // last dimension: off(l) + cell_l
   double phA[R][kLeafTable + 1];   // dimension D-2: hat of level l   (SUPER records)
@@ -85,7 +92,8 @@ struct StreamPoints {
 
 template <int D, int R>
 __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp,
-                                                  int64_t sd, StreamPoints<D, R> &pt, int k) {
+                                                  int64_t sd, StreamPoints<D, R> &pt, int k, double *xs, uint32_t *qs) {
+  constexpr int NT = StreamCfg<R>::kThreads;
   bool inside = true;
   double u[D];
 #pragma unroll
@@ -99,8 +107,8 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
     const double v = inside ? u[d] : 0.5;  // walked at the centre; the result is replaced by the exact 0.0
     const uint32_t q = v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);  // floor(v*2^30), exact
     if (d < D - 1) {
-      pt.x[k][d] = v;
-      pt.q[k][d] = q;
+      xs[(d * R + k) * NT + threadIdx.x] = v;
+      qs[(d * R + k) * NT + threadIdx.x] = q;
       if (d == D - 2) {
 #pragma unroll
         for (int l = 2; l <= kLeafTable; ++l)
@@ -134,12 +142,13 @@ template <int D, int R, int K>
 __device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, int l, int b, uint32_t odd,
                                       double s) {
   if (l > 1) {
+    constexpr int NT = StreamCfg<R>::kThreads;
     const uint32_t twob = 1u << b;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       double ph;
       uint32_t cell;
-      hat_cell(pt.x[k][K], pt.q[k][K], b, odd, s, ph, cell);
+      hat_cell(pt.xs[(K * R + k) * NT + threadIdx.x], pt.qs[(K * R + k) * NT + threadIdx.x], b, odd, s, ph, cell);
       if constexpr (K == 0) {
         pr.P[k][0] = ph;
         pr.O[k][0] = cell;
@@ -225,14 +234,15 @@ __device__ __forceinline__ void group_full_global(const DeviceGrid &g, const Str
 // against the register tables. P, O are the prefix product / position over dimensions 0..D-3.
 // mask_rem < 0: no depth mask; otherwise budget left for the last two dimensions.
 template <int D, int R, bool SMEM>
-__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
-                                            const uint32_t (&O)[R], uint32_t tile_addr, uint32_t slot0, uint32_t base1,
-                                            uint32_t npre8, int lmA, uint32_t lmBs, int mask_rem, double (&acc)[R]) {
+__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt,
+                                            const PrefixRegs<D, R> &pr, uint32_t tile_addr, uint32_t slot0,
+                                            uint32_t base1, uint32_t npre8, int lmA, uint32_t lmBs, const uint4 &offs,
+                                            int mask_rem, double (&acc)[R]) {
   double inner2[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) inner2[k] = 0.0;
-  uint32_t sbase = tile_addr + slot0 * 8u;      // SMEM: byte address of the current group's slice
-  const char *gbase = reinterpret_cast<const char *>(g.coef + base1);  // !SMEM
+  const uint32_t sbase0 = tile_addr + slot0 * 8u;                        // SMEM: byte address of the first slice
+  const char *gbase0 = reinterpret_cast<const char *>(g.coef + base1);  // !SMEM
   if (mask_rem >= 0) lmA = min(lmA, mask_rem + 1);
 #pragma unroll
   for (int lA = 1; lA <= kLeafTable; ++lA) {
@@ -243,11 +253,18 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
     const uint32_t np = npre8 << bA;  // byte stride between consecutive last-dimension cells
     const int lmB_all = (int)((lmBs >> (4 * (lA - 1))) & 15u);
     const int lmB = mask_rem >= 0 ? min(lmB_all, mask_rem - (lA - 1) + 1) : lmB_all;
+    // slice of group lA: precomputed by the packer as a 16-bit count of npre8-byte cells
+    const uint32_t ow = lA <= 2 ? offs.x : (lA <= 4 ? offs.y : (lA <= 6 ? offs.z : offs.w));
+    const uint32_t ocells = (lA & 1) ? (ow & 0xffffu) : (ow >> 16);
+    const uint32_t sbase = sbase0 + ocells * npre8;
+    const char *gbase = gbase0 + (uint64_t)ocells * npre8;
     uint32_t off[R];
     double inner1[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const uint32_t OA = lA == 1 ? O[k] : ((O[k] << bA) | pt.ceA[k][lA]);
+      uint32_t O7;
+      if constexpr (D >= 3) O7 = pr.O[k][D - 3]; else O7 = 0u;
+      const uint32_t OA = lA == 1 ? O7 : ((O7 << bA) | pt.ceA[k][lA]);
       off[k] = OA * 8u;
       if constexpr (SMEM) {
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner1[k]) : "r"(sbase + off[k]));
@@ -271,13 +288,12 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) inner2[k] = lA == 1 ? inner1[k] : fma(pt.phA[k][lA], inner1[k], inner2[k]);
-    // next group starts after this one's cells: 1, 3, 5, 9, ... = off(lmB + 1) cells of np bytes each
-    const uint32_t cells = lmB_all < 2 ? 1u : ((1u << (lmB_all - 1)) + 1u);
-    if constexpr (SMEM) sbase += cells * np;
-    else gbase += (uint64_t)cells * np;
   }
 #pragma unroll
-  for (int k = 0; k < R; ++k) acc[k] = fma(P[k], inner2[k], acc[k]);
+  for (int k = 0; k < R; ++k) {
+    if constexpr (D >= 3) acc[k] = fma(pr.P[k][D - 3], inner2[k], acc[k]);
+    else acc[k] += inner2[k];
+  }
 }
 
 // GENERIC group: explicit leaf records (any levels, dense or hashed), global memory
@@ -317,9 +333,13 @@ __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamP
 }
 
 template <int D, int R, bool MASKED>
-__global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_stream(const DeviceGrid g, const EvalArgs a) {
+__global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPerSm)
+    k_eval_stream(const DeviceGrid g, const EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
+  constexpr int NT = StreamCfg<R>::kThreads;
+  double *xs = reinterpret_cast<double *>(smem_raw + sizeof(StreamSmem));
+  uint32_t *qs = reinterpret_cast<uint32_t *>(xs + (size_t)(D - 1) * R * NT);
   const int64_t tile_pts = (int64_t)blockDim.x * R;
   const int64_t stride = (int64_t)gridDim.x * tile_pts;
   const uint32_t ntiles = g.n_tiles;
@@ -333,13 +353,15 @@ __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_strea
 
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
     StreamPoints<D, R> pt;
+    pt.xs = xs;
+    pt.qs = qs;
     bool inside[R];
     int64_t m[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       m[k] = base + (int64_t)k * blockDim.x + threadIdx.x;
       const int64_t mm = m[k] < a.M ? m[k] : a.M - 1;  // tail lanes redo the last point, never store
-      inside[k] = stream_load_point<D, R>(g, a.X, mm, a.sp, a.sd, pt, k);
+      inside[k] = stream_load_point<D, R>(g, a.X, mm, a.sp, a.sd, pt, k, xs, qs);
     }
     if (threadIdx.x == 0) {
       issue_tile(g, sm, 0, 0);
@@ -361,6 +383,7 @@ __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_strea
       for (uint32_t j = 0; j < nrec; ++j) {
         const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.rec[buf][j]);        // base1, npre8, meta, nchild
         const uint4 rb = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 1);  // lev_lo, lev_hi, s_hi, bod
+        const uint4 rc = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 2);  // SUPER: slice offsets
         const int used = (int)((ra.z >> 16) & 0xffu);
         const int k0 = (int)((ra.z >> 8) & 0xffu);
         int kfrom = k0;
@@ -388,18 +411,11 @@ __global__ void __launch_bounds__(kStreamThreads, (R == 1 ? 2 : 1)) k_eval_strea
         }
         const int rem = MASKED ? a.rem - used : INT_MAX / 2;  // budget left below the prefix
         if (ra.z & kGrpSuper) {
-          double P7[R];
-          uint32_t O7[R];
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            if constexpr (D >= 3) { P7[k] = pr.P[k][D - 3]; O7[k] = pr.O[k][D - 3]; }
-            else { P7[k] = 1.0; O7[k] = 0u; }
-          }
           const int lmA = (int)(ra.z & 0xffu);
           if (!(ra.z & kGrpGlobal))
-            group_super<D, R, true>(g, pt, P7, O7, tile_addr, ra.x - tl.c0, ra.x, ra.y, lmA, ra.w, MASKED ? rem : -1, acc);
+            group_super<D, R, true>(g, pt, pr, tile_addr, ra.x - tl.c0, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           else
-            group_super<D, R, false>(g, pt, P7, O7, tile_addr, 0u, ra.x, ra.y, lmA, ra.w, MASKED ? rem : -1, acc);
+            group_super<D, R, false>(g, pt, pr, tile_addr, 0u, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           continue;
         }
         {
@@ -449,11 +465,11 @@ static int sm_count() {
 
 cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
   if (a.M <= 0) return cudaSuccess;
-  const int threads = kStreamThreads;
   const int sms = sm_count();
-  const size_t smem = sizeof(StreamSmem);
-  bool two = a.M >= (int64_t)sms * threads * 4;
+  bool two = a.M >= (int64_t)sms * StreamCfg<2>::kThreads * 4;
   if (const char *e = getenv("ASG_STREAM_R")) two = (e[0] == '2');  // experiment knob
+  const int threads = two ? StreamCfg<2>::kThreads : StreamCfg<1>::kThreads;
+  const size_t smem = sizeof(StreamSmem) + (size_t)(g.D - 1) * (two ? 2 : 1) * threads * 12;
   const int per_block = threads * (two ? 2 : 1);
   // persistent-style grid: every CTA re-streams the whole grid per batch of points, so use as few
   // batches as possible: one CTA per resident slot, grid-stride over the points

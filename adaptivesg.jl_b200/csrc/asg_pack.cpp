@@ -257,6 +257,7 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
         const int pb = (int)(r.w & 0xffu);
         const int lA = (int)(r.y & 0xffu);
         GroupRec &q = out.grp[j];
+        std::memset(&q, 0, sizeof(q));
         q.npre8 = 8u << pb;
         q.lev_lo = (uint32_t)(grp_levels[j] & 0x3fffffffull);
         q.lev_hi = (uint32_t)(grp_levels[j] >> 30);
@@ -302,8 +303,13 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
             else if (j > cb && span_lo[j] != span_hi[j - 1]) super = false;
             else lmBs |= (q.meta & 0xfu) << (4 * (j - cb));
           }
+          // slice starts are stored as 16-bit cell counts (cells of group lA = 1, npre8 bytes each)
+          if (super && (span_lo[ce - 1] - span_lo[cb]) / (out.grp[cb].npre8 / 8u) > 0xffffu) super = false;
           if (super) {
             GroupRec q = out.grp[cb];
+            const uint32_t np_cells = q.npre8 / 8u;
+            for (int a = 0; a < 8; ++a) q.offs[a] = 0;
+            for (uint32_t j = cb; j < ce; ++j) q.offs[j - cb] = (uint16_t)((span_lo[j] - span_lo[cb]) / np_cells);
             q.meta = (uint32_t)lmA | (q.meta & 0x00ffff00u) | kGrpSuper;  // k0 and used of the first child (lA = 1)
             q.nchild = lmBs;
             merged.push_back(q);
