@@ -34,7 +34,7 @@ struct __align__(16) StreamSmem {
   GroupRec rec[2][kTileRecs];
   unsigned long long bar[2];
   // followed by the unit-cube coordinates / cell keys of the prefix dimensions of every point of the
-  // CTA: double xs[D-1][R][threads]; uint32_t qs[D-1][R][threads]  (read only at non-trivial stages)
+  // CTA: double xs[D][R][threads]; uint32_t qs[D][R][threads]  (read only at non-trivial stages)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,9 +86,12 @@ struct StreamPoints {
   uint32_t w[R][kLeafTable + 1];   // last dimension: off(l) + cell_l
   double phA[R][kLeafTable + 1];   // dimension D-2: hat of level l   (SUPER records)
   uint32_t ceA[R][kLeafTable + 1]; // dimension D-2: cell of level l
-  double xl[R];                   // last dimension coordinate / key (generic groups)
-  uint32_t ql[R];
 };
+
+// keep a table entry in its register: without this ptxas re-derives cells from the coordinate
+// (DMUL + F2I + SEL per use) to save registers, which costs far more issue slots than it saves
+__device__ __forceinline__ void pin_u32(uint32_t &v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin_f64(double &v) { asm volatile("" : "+d"(v)); }
 
 template <int D, int R>
 __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp,
@@ -106,17 +109,17 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
   for (int d = 0; d < D; ++d) {
     const double v = inside ? u[d] : 0.5;  // walked at the centre; the result is replaced by the exact 0.0
     const uint32_t q = v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);  // floor(v*2^30), exact
-    if (d < D - 1) {
-      xs[(d * R + k) * NT + threadIdx.x] = v;
-      qs[(d * R + k) * NT + threadIdx.x] = q;
-      if (d == D - 2) {
+    xs[(d * R + k) * NT + threadIdx.x] = v;  // all D dimensions: the last one is read by generic groups only
+    qs[(d * R + k) * NT + threadIdx.x] = q;
+    if (d == D - 2) {
 #pragma unroll
-        for (int l = 2; l <= kLeafTable; ++l)
-          hat_cell(v, q, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phA[k][l], pt.ceA[k][l]);
+      for (int l = 2; l <= kLeafTable; ++l) {
+        hat_cell(v, q, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phA[k][l], pt.ceA[k][l]);
+        pin_f64(pt.phA[k][l]);
+        pin_u32(pt.ceA[k][l]);
       }
-    } else {
-      pt.xl[k] = v;
-      pt.ql[k] = q;
+    }
+    if (d == D - 1) {
       pt.ph[k][0] = pt.ph[k][1] = 1.0;
       pt.w[k][0] = pt.w[k][1] = 0u;
 #pragma unroll
@@ -124,6 +127,8 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
         uint32_t cell;
         hat_cell(v, q, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.ph[k][l], cell);
         pt.w[k][l] = (l == 2 ? 1u : ((1u << (l - 2)) + 1u)) + cell;  // off(l) = 0,1,3,5,9,17,33,65
+        pin_f64(pt.ph[k][l]);
+        pin_u32(pt.w[k][l]);
       }
     }
   }
@@ -258,17 +263,18 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
     const uint32_t ocells = (lA & 1) ? (ow & 0xffffu) : (ow >> 16);
     const uint32_t sbase = sbase0 + ocells * npre8;
     const char *gbase = gbase0 + (uint64_t)ocells * npre8;
-    uint32_t off[R];
+    uint32_t off[R];  // SMEM: shared byte address of the level-1 leaf; !SMEM: byte offset from gbase
     double inner1[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       uint32_t O7;
       if constexpr (D >= 3) O7 = pr.O[k][D - 3]; else O7 = 0u;
       const uint32_t OA = lA == 1 ? O7 : ((O7 << bA) | pt.ceA[k][lA]);
-      off[k] = OA * 8u;
       if constexpr (SMEM) {
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner1[k]) : "r"(sbase + off[k]));
+        off[k] = OA * 8u + sbase;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner1[k]) : "r"(off[k]));
       } else {
+        off[k] = OA * 8u;
         inner1[k] = __ldg(reinterpret_cast<const double *>(gbase + off[k]));
       }
     }
@@ -279,7 +285,7 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
       for (int k = 0; k < R; ++k) {
         double c;
         if constexpr (SMEM) {
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(sbase + off[k] + pt.w[k][lB] * np));
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c) : "r"(pt.w[k][lB] * np + off[k]));  // one IMAD
         } else {
           c = __ldg(reinterpret_cast<const double *>(gbase + off[k] + (uint64_t)pt.w[k][lB] * np));
         }
@@ -321,7 +327,9 @@ __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamP
       const double s = pow2_lm1(l);
       const uint32_t odd = l > 2 ? 1u : 0u;
 #pragma unroll
-      for (int k = 0; k < R; ++k) hat_cell(pt.xl[k], pt.ql[k], b, odd, s, ph[k], cell[k]);
+      for (int k = 0; k < R; ++k)
+        hat_cell(pt.xs[((D - 1) * R + k) * StreamCfg<R>::kThreads + threadIdx.x],
+                 pt.qs[((D - 1) * R + k) * StreamCfg<R>::kThreads + threadIdx.x], b, odd, s, ph[k], cell[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) { cell[k] = 0u; ph[k] = 1.0; }
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
   StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
   constexpr int NT = StreamCfg<R>::kThreads;
   double *xs = reinterpret_cast<double *>(smem_raw + sizeof(StreamSmem));
-  uint32_t *qs = reinterpret_cast<uint32_t *>(xs + (size_t)(D - 1) * R * NT);
+  uint32_t *qs = reinterpret_cast<uint32_t *>(xs + (size_t)D * R * NT);
   const int64_t tile_pts = (int64_t)blockDim.x * R;
   const int64_t stride = (int64_t)gridDim.x * tile_pts;
   const uint32_t ntiles = g.n_tiles;
@@ -469,7 +477,7 @@ cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStrea
   bool two = a.M >= (int64_t)sms * StreamCfg<2>::kThreads * 4;
   if (const char *e = getenv("ASG_STREAM_R")) two = (e[0] == '2');  // experiment knob
   const int threads = two ? StreamCfg<2>::kThreads : StreamCfg<1>::kThreads;
-  const size_t smem = sizeof(StreamSmem) + (size_t)(g.D - 1) * (two ? 2 : 1) * threads * 12;
+  const size_t smem = sizeof(StreamSmem) + (size_t)g.D * (two ? 2 : 1) * threads * 12;
   const int per_block = threads * (two ? 2 : 1);
   // persistent-style grid: every CTA re-streams the whole grid per batch of points, so use as few
   // batches as possible: one CTA per resident slot, grid-stride over the points
