@@ -149,7 +149,17 @@ def cpu_reference_rate(Gh, seconds_target, threads=0, steps=1, warmup=0):
     return n / statistics.mean(times), cores, n, statistics.mean(times), y, X
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL prints its version banner from C) also
+    write to fd 1, so keep a private copy of the real stdout for the JSON line and point fd 1 at stderr."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -191,7 +201,7 @@ def main():
                                        "OpenMP over points; Julia Threads.nthreads() not measurable (no Julia)"},
             "e2e": {"value": rate, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=out_stream, flush=True)
         return
 
     import torch
@@ -387,7 +397,7 @@ def main():
         "gather_ms": gather_ms,
         "checksum": checksum,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
