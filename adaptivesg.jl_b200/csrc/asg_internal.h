@@ -64,8 +64,8 @@ struct __align__(16) GroupRec {
   uint32_t nchild;  // GENERIC: number of leaf records; SUPER: lmB of lA = 1..8, 4 bits each
   uint32_t lev_lo;  // levels of dimensions 0..D-2, 5 bits each (dims 0..5 here,
   uint32_t lev_hi;  //  dims 6..11 here)
-  uint32_t s_hi;    // dimension D-2: high word of the double 2^(l-1) (unused when l == 1)
-  uint32_t bod;     // dimension D-2: bits 0..7 cell bits b | bit 8 (l > 2) | bits 16..23 pb
+  uint32_t s_hi;    // dimension D-2 (SUPER: D-3): high word of the double 2^(l-1) (unused when l == 1)
+  uint32_t bod;     // same dimension: bits 0..7 cell bits b | bit 8 (l > 2); bits 16..23 pb
   uint16_t offs[8]; // SUPER: start of the slice of group lA = 1..8, in cells of npre8 bytes, relative to base1
 };
 static_assert(sizeof(GroupRec) == 48, "GroupRec is streamed as three 16-byte words");

@@ -135,17 +135,22 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
   return inside;
 }
 
-// prefix products P[k][K], positions O[k][K] of R points over the D-1 prefix dimensions
+// Saved prefix products / positions of R points for dimensions 0..D-4. The running value `cur`
+// (product over the dimensions walked so far) lives in its own registers: a record restarts it from
+// the saved value of dimension k0-1, walks dimensions k0..D-3 and saves every dimension but the last,
+// whose value is consumed at once by the group evaluation.
 template <int D, int R>
 struct PrefixRegs {
-  double P[R][D - 1];
-  uint32_t O[R][D - 1];
+  static constexpr int NS = D > 3 ? D - 3 : 1;
+  double P[R][NS];
+  uint32_t O[R][NS];
 };
 
-// stage K: derive P[K], O[K] from P[K-1], O[K-1] for the level l of dimension K
+// stage K: multiply the running prefix by the hat of the level-l node of dimension K that supports
+// the point (nothing to do for l == 1), then save it for later restarts unless K is the last prefix dim
 template <int D, int R, int K>
-__device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, int l, int b, uint32_t odd,
-                                      double s) {
+__device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, double (&cur)[R],
+                                      uint32_t (&cO)[R], int l, int b, uint32_t odd, double s) {
   if (l > 1) {
     constexpr int NT = StreamCfg<R>::kThreads;
     const uint32_t twob = 1u << b;
@@ -154,45 +159,46 @@ __device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D
       double ph;
       uint32_t cell;
       hat_cell(pt.xs[(K * R + k) * NT + threadIdx.x], pt.qs[(K * R + k) * NT + threadIdx.x], b, odd, s, ph, cell);
-      if constexpr (K == 0) {
-        pr.P[k][0] = ph;
-        pr.O[k][0] = cell;
-      } else {
-        pr.P[k][K] = pr.P[k][K - 1] * ph;
-        pr.O[k][K] = pr.O[k][K - 1] * twob + cell;  // (O << b) | cell as one IMAD
-      }
+      cur[k] *= ph;
+      cO[k] = cO[k] * twob + cell;  // (O << b) | cell as one IMAD
     }
-  } else {
+  }
+  if constexpr (K <= D - 4) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      if constexpr (K == 0) {
-        pr.P[k][0] = 1.0;
-        pr.O[k][0] = 0u;
-      } else {
-        pr.P[k][K] = pr.P[k][K - 1];
-        pr.O[k][K] = pr.O[k][K - 1];
-      }
+      pr.P[k][K] = cur[k];
+      pr.O[k][K] = cO[k];
     }
   }
 }
 
 template <int D, int R, int K>
-__device__ __forceinline__ void stage_from_levels(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, uint32_t lev_lo,
+__device__ __forceinline__ void stage_from_levels(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr,
+                                                  double (&cur)[R], uint32_t (&cO)[R], uint32_t lev_lo,
                                                   uint32_t lev_hi) {
   const int l = (int)(((K < 6 ? lev_lo : lev_hi) >> (5 * (K % 6))) & 31u);
-  stage<D, R, K>(pt, pr, l, bits_of(l), l > 2 ? 1u : 0u, pow2_lm1(l));
+  stage<D, R, K>(pt, pr, cur, cO, l, bits_of(l), l > 2 ? 1u : 0u, pow2_lm1(l));
+}
+
+template <int D, int R, int K>
+__device__ __forceinline__ void restart(const PrefixRegs<D, R> &pr, double (&cur)[R], uint32_t (&cO)[R]) {
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    if constexpr (K == 0) { cur[k] = 1.0; cO[k] = 0u; }
+    else { cur[k] = pr.P[k][K - 1]; cO[k] = pr.O[k][K - 1]; }
+  }
 }
 
 // FULL group from the shared-memory tile: 32-bit shared addresses, LDS gathers
 template <int D, int R>
-__device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, const PrefixRegs<D, R> &pr,
-                                                uint32_t tile_addr, uint32_t slot0, uint32_t npre8, int lm,
-                                                double (&acc)[R]) {
+__device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, const double (&P)[R],
+                                                const uint32_t (&O)[R], uint32_t tile_addr, uint32_t slot0,
+                                                uint32_t npre8, int lm, double (&acc)[R]) {
   uint32_t a0[R];
   double inner[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    a0[k] = tile_addr + (slot0 + pr.O[k][D - 2]) * 8u;
+    a0[k] = tile_addr + (slot0 + O[k]) * 8u;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner[k]) : "r"(a0[k]));  // level 1: phi = 1, cell = 0
   }
 #pragma unroll
@@ -206,19 +212,19 @@ __device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, co
     }
   }
 #pragma unroll
-  for (int k = 0; k < R; ++k) acc[k] = fma(pr.P[k][D - 2], inner[k], acc[k]);
+  for (int k = 0; k < R; ++k) acc[k] = fma(P[k], inner[k], acc[k]);
 }
 
 // FULL group whose slice is too large for a tile: same arithmetic, coefficients from global memory
 template <int D, int R>
 __device__ __forceinline__ void group_full_global(const DeviceGrid &g, const StreamPoints<D, R> &pt,
-                                                  const PrefixRegs<D, R> &pr, uint32_t base1, uint32_t npre8, int lm,
-                                                  double (&acc)[R]) {
+                                                  const double (&P)[R], const uint32_t (&O)[R], uint32_t base1,
+                                                  uint32_t npre8, int lm, double (&acc)[R]) {
   const double *A0[R];
   double inner[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    A0[k] = g.coef + (base1 + pr.O[k][D - 2]);
+    A0[k] = g.coef + (base1 + O[k]);
     inner[k] = __ldg(A0[k]);
   }
 #pragma unroll
@@ -232,21 +238,21 @@ __device__ __forceinline__ void group_full_global(const DeviceGrid &g, const Str
     }
   }
 #pragma unroll
-  for (int k = 0; k < R; ++k) acc[k] = fma(pr.P[k][D - 2], inner[k], acc[k]);
+  for (int k = 0; k < R; ++k) acc[k] = fma(P[k], inner[k], acc[k]);
 }
 
 // SUPER record: levels 1..lmA of dimension D-2 x levels 1..lmB(lA) of dimension D-1, both unrolled
 // against the register tables. P, O are the prefix product / position over dimensions 0..D-3.
 // mask_rem < 0: no depth mask; otherwise budget left for the last two dimensions.
 template <int D, int R, bool SMEM>
-__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt,
-                                            const PrefixRegs<D, R> &pr, uint32_t tile_addr, uint32_t slot0,
-                                            uint32_t base1, uint32_t npre8, int lmA, uint32_t lmBs, const uint4 &offs,
-                                            int mask_rem, double (&acc)[R]) {
+__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
+                                            const uint32_t (&O)[R], uint32_t sbase0, uint32_t base1, uint32_t npre8,
+                                            int lmA, uint32_t lmBs, const uint4 &offs, int mask_rem,
+                                            double (&acc)[R]) {
+  // sbase0: SMEM: shared byte address of the first slice
   double inner2[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) inner2[k] = 0.0;
-  const uint32_t sbase0 = tile_addr + slot0 * 8u;                        // SMEM: byte address of the first slice
   const char *gbase0 = reinterpret_cast<const char *>(g.coef + base1);  // !SMEM
   if (mask_rem >= 0) lmA = min(lmA, mask_rem + 1);
 #pragma unroll
@@ -267,9 +273,7 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
     double inner1[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      uint32_t O7;
-      if constexpr (D >= 3) O7 = pr.O[k][D - 3]; else O7 = 0u;
-      const uint32_t OA = lA == 1 ? O7 : ((O7 << bA) | pt.ceA[k][lA]);
+      const uint32_t OA = lA == 1 ? O[k] : ((O[k] << bA) | pt.ceA[k][lA]);
       if constexpr (SMEM) {
         off[k] = OA * 8u + sbase;
         asm volatile("ld.shared.f64 %0, [%1];" : "=d"(inner1[k]) : "r"(off[k]));
@@ -296,24 +300,21 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
     for (int k = 0; k < R; ++k) inner2[k] = lA == 1 ? inner1[k] : fma(pt.phA[k][lA], inner1[k], inner2[k]);
   }
 #pragma unroll
-  for (int k = 0; k < R; ++k) {
-    if constexpr (D >= 3) acc[k] = fma(pr.P[k][D - 3], inner2[k], acc[k]);
-    else acc[k] += inner2[k];
-  }
+  for (int k = 0; k < R; ++k) acc[k] = fma(P[k], inner2[k], acc[k]);
 }
 
 // GENERIC group: explicit leaf records (any levels, dense or hashed), global memory
 template <int D, int R>
-__device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R> &pt,
-                                              const PrefixRegs<D, R> &pr, uint32_t jb, uint32_t n, int rem, int pb,
+__device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
+                                              const uint32_t (&O)[R], uint32_t jb, uint32_t n, int rem, int pb,
                                               double (&acc)[R]) {
   EvalSink<R> sink;
   Prefix<R> pf;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     sink.acc[k] = acc[k];
-    pf.P[k] = pr.P[k][D - 2];
-    pf.O[k] = pr.O[k][D - 2];
+    pf.P[k] = P[k];
+    pf.O[k] = O[k];
   }
   const TrieRec *rec = g.rec[D - 1];
   for (uint32_t j = jb; j < jb + n; ++j) {
@@ -379,19 +380,25 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
     double acc[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) acc[k] = 0.0;
-    int kmin = 0;  // prefix registers are valid from dimension 0 .. kmin-1 (nothing at the start)
+    int kmin = 0;  // saved prefix registers are valid for dimensions 0 .. kmin-1 (nothing at the start)
 
     for (uint32_t t = 0; t < ntiles; ++t) {
       const int buf = (int)(t & 1u);
       const StreamTile tl = g.tiles[t];
       mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
-      const uint32_t tile_addr = smem_u32(sm.coef[buf]);
+      // shared addresses of this tile, pinned so that they are not re-derived per record
+      uint32_t rbase = smem_u32(sm.rec[buf]);
+      uint32_t tbias = smem_u32(sm.coef[buf]) - tl.c0 * 8u;  // shared byte address of coefficient slot 0
+      pin_u32(rbase);
+      pin_u32(tbias);
       const uint32_t nrec = tl.r1 - tl.r0;
       for (uint32_t j = 0; j < nrec; ++j) {
-        const uint4 ra = *reinterpret_cast<const uint4 *>(&sm.rec[buf][j]);        // base1, npre8, meta, nchild
-        const uint4 rb = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 1);  // lev_lo, lev_hi, s_hi, bod
-        const uint4 rc = *(reinterpret_cast<const uint4 *>(&sm.rec[buf][j]) + 2);  // SUPER: slice offsets
+        uint4 ra, rb, rc;  // {base1, npre8, meta, nchild} {lev_lo, lev_hi, s_hi, bod} {slice offsets}
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(rbase));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(rbase));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+32];" : "=r"(rc.x), "=r"(rc.y), "=r"(rc.z), "=r"(rc.w) : "r"(rbase));
+        rbase += (uint32_t)sizeof(GroupRec);
         const int used = (int)((ra.z >> 16) & 0xffu);
         const int k0 = (int)((ra.z >> 8) & 0xffu);
         int kfrom = k0;
@@ -401,41 +408,80 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
             continue;
           }
           kfrom = min(k0, kmin);
-          kmin = D;  // after this record every prefix register is valid
+          kmin = D;  // after this record every saved prefix register is valid
         }
-        // stages kfrom .. D-3 (rare) from the packed levels, stage D-2 (every record) from precomputed fields
-        switch (kfrom) {
-          case 0: if constexpr (D - 2 > 0) stage_from_levels<D, R, 0>(pt, pr, rb.x, rb.y);
-          case 1: if constexpr (D - 2 > 1) stage_from_levels<D, R, (D - 2 > 1 ? 1 : 0)>(pt, pr, rb.x, rb.y);
-          case 2: if constexpr (D - 2 > 2) stage_from_levels<D, R, (D - 2 > 2 ? 2 : 0)>(pt, pr, rb.x, rb.y);
-          case 3: if constexpr (D - 2 > 3) stage_from_levels<D, R, (D - 2 > 3 ? 3 : 0)>(pt, pr, rb.x, rb.y);
-          case 4: if constexpr (D - 2 > 4) stage_from_levels<D, R, (D - 2 > 4 ? 4 : 0)>(pt, pr, rb.x, rb.y);
-          case 5: if constexpr (D - 2 > 5) stage_from_levels<D, R, (D - 2 > 5 ? 5 : 0)>(pt, pr, rb.x, rb.y);
-          case 6: if constexpr (D - 2 > 6) stage_from_levels<D, R, (D - 2 > 6 ? 6 : 0)>(pt, pr, rb.x, rb.y);
-          case 7: if constexpr (D - 2 > 7) stage_from_levels<D, R, (D - 2 > 7 ? 7 : 0)>(pt, pr, rb.x, rb.y);
-          case 8: if constexpr (D - 2 > 8) stage_from_levels<D, R, (D - 2 > 8 ? 8 : 0)>(pt, pr, rb.x, rb.y);
-          case 9: if constexpr (D - 2 > 9) stage_from_levels<D, R, (D - 2 > 9 ? 9 : 0)>(pt, pr, rb.x, rb.y);
-          default: break;
+        // running prefix: restart from the saved value below kfrom, walk dimensions kfrom .. D-3
+        double cur[R];
+        uint32_t cO[R];
+        if constexpr (D >= 3) {
+          kfrom = min(kfrom, D - 3);  // the value of dimension D-3 is never saved: always redo that stage
+          switch (kfrom) {
+            case 0: restart<D, R, 0>(pr, cur, cO); break;
+            case 1: if constexpr (D - 3 >= 1) restart<D, R, (D - 3 >= 1 ? 1 : 0)>(pr, cur, cO); break;
+            case 2: if constexpr (D - 3 >= 2) restart<D, R, (D - 3 >= 2 ? 2 : 0)>(pr, cur, cO); break;
+            case 3: if constexpr (D - 3 >= 3) restart<D, R, (D - 3 >= 3 ? 3 : 0)>(pr, cur, cO); break;
+            case 4: if constexpr (D - 3 >= 4) restart<D, R, (D - 3 >= 4 ? 4 : 0)>(pr, cur, cO); break;
+            case 5: if constexpr (D - 3 >= 5) restart<D, R, (D - 3 >= 5 ? 5 : 0)>(pr, cur, cO); break;
+            case 6: if constexpr (D - 3 >= 6) restart<D, R, (D - 3 >= 6 ? 6 : 0)>(pr, cur, cO); break;
+            case 7: if constexpr (D - 3 >= 7) restart<D, R, (D - 3 >= 7 ? 7 : 0)>(pr, cur, cO); break;
+            case 8: if constexpr (D - 3 >= 8) restart<D, R, (D - 3 >= 8 ? 8 : 0)>(pr, cur, cO); break;
+            default: if constexpr (D - 3 >= 9) restart<D, R, (D - 3 >= 9 ? 9 : 0)>(pr, cur, cO); break;
+          }
+          switch (kfrom) {  // fall through: stages kfrom .. D-4 from the packed levels
+            case 0: if constexpr (D - 4 >= 0) stage_from_levels<D, R, 0>(pt, pr, cur, cO, rb.x, rb.y);
+            case 1: if constexpr (D - 4 >= 1) stage_from_levels<D, R, (D - 4 >= 1 ? 1 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 2: if constexpr (D - 4 >= 2) stage_from_levels<D, R, (D - 4 >= 2 ? 2 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 3: if constexpr (D - 4 >= 3) stage_from_levels<D, R, (D - 4 >= 3 ? 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 4: if constexpr (D - 4 >= 4) stage_from_levels<D, R, (D - 4 >= 4 ? 4 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 5: if constexpr (D - 4 >= 5) stage_from_levels<D, R, (D - 4 >= 5 ? 5 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 6: if constexpr (D - 4 >= 6) stage_from_levels<D, R, (D - 4 >= 6 ? 6 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 7: if constexpr (D - 4 >= 7) stage_from_levels<D, R, (D - 4 >= 7 ? 7 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 8: if constexpr (D - 4 >= 8) stage_from_levels<D, R, (D - 4 >= 8 ? 8 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            default: break;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < R; ++k) { cur[k] = 1.0; cO[k] = 0u; }
         }
         const int rem = MASKED ? a.rem - used : INT_MAX / 2;  // budget left below the prefix
         if (ra.z & kGrpSuper) {
+          // stage D-3 (every record) from the fields the packer precomputed: s_hi, bod describe dimension D-3
+          if constexpr (D >= 3) {
+            const int l3 = (int)(((D - 3 < 6 ? rb.x : rb.y) >> (5 * ((D - 3) % 6))) & 31u);
+            stage<D, R, D - 3>(pt, pr, cur, cO, l3, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
+          }
           const int lmA = (int)(ra.z & 0xffu);
           if (!(ra.z & kGrpGlobal))
-            group_super<D, R, true>(g, pt, pr, tile_addr, ra.x - tl.c0, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
+            group_super<D, R, true>(g, pt, cur, cO, ra.x * 8u + tbias, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           else
-            group_super<D, R, false>(g, pt, pr, tile_addr, 0u, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
+            group_super<D, R, false>(g, pt, cur, cO, 0u, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           continue;
         }
+        // per-group record (irregular parts): stage D-3 from the packed levels, stage D-2 from s_hi / bod
+        if constexpr (D >= 3) stage_from_levels<D, R, (D >= 3 ? D - 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
         {
           const int lA = (int)(((D - 2 < 6 ? rb.x : rb.y) >> (5 * ((D - 2) % 6))) & 31u);
-          stage<D, R, D - 2>(pt, pr, lA, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
+          if (lA > 1) {
+            constexpr int NT2 = StreamCfg<R>::kThreads;
+            const int b = (int)(rb.w & 0xffu);
+            const uint32_t twob = 1u << b;
+#pragma unroll
+            for (int k = 0; k < R; ++k) {
+              double ph;
+              uint32_t cell;
+              hat_cell(pt.xs[((D - 2) * R + k) * NT2 + threadIdx.x], pt.qs[((D - 2) * R + k) * NT2 + threadIdx.x], b,
+                       (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0), ph, cell);
+              cur[k] *= ph;
+              cO[k] = cO[k] * twob + cell;
+            }
+          }
         }
         if (ra.z & kGrpFull) {
           const int lm = min((int)(ra.z & 0xffu), rem + 1);
-          if (!(ra.z & kGrpGlobal)) group_full_smem<D, R>(pt, pr, tile_addr, ra.x - tl.c0, ra.y, lm, acc);
-          else group_full_global<D, R>(g, pt, pr, ra.x, ra.y, lm, acc);
+          if (!(ra.z & kGrpGlobal)) group_full_smem<D, R>(pt, cur, cO, tbias, ra.x, ra.y, lm, acc);
+          else group_full_global<D, R>(g, pt, cur, cO, ra.x, ra.y, lm, acc);
         } else {
-          group_generic<D, R>(g, pt, pr, ra.x, ra.w, rem, (int)((rb.w >> 16) & 0xffu), acc);
+          group_generic<D, R>(g, pt, cur, cO, ra.x, ra.w, rem, (int)((rb.w >> 16) & 0xffu), acc);
         }
       }
       __syncthreads();  // every warp is done with buffer `buf`

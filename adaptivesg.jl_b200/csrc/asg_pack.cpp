@@ -312,6 +312,11 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
             for (uint32_t j = cb; j < ce; ++j) q.offs[j - cb] = (uint16_t)((span_lo[j] - span_lo[cb]) / np_cells);
             q.meta = (uint32_t)lmA | (q.meta & 0x00ffff00u) | kGrpSuper;  // k0 and used of the first child (lA = 1)
             q.nchild = lmBs;
+            if (D >= 3) {  // s_hi / bod of a SUPER record describe the level of dimension D-3 (walked by every record)
+              const int l3 = (int)((grp_levels[cb] >> (5 * (D - 3))) & 31u);
+              q.s_hi = (uint32_t)(1023 + l3 - 1) << 20;
+              q.bod = (uint32_t)cell_bits(l3) | (l3 > 2 ? 0x100u : 0u) | (q.bod & 0x00ff0000u);
+            }
             merged.push_back(q);
             mlo.push_back(span_lo[cb]);
             mhi.push_back(span_hi[ce - 1]);

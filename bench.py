@@ -368,6 +368,15 @@ def main():
             # ncu capture is of a shorter launch: scale its measured DRAM bytes to this launch's point count
             roofline["traffic"] = pj["dram_bytes_per_launch"] * pts_per_launch / pj["points_per_launch"]
             roofline["traffic_source"] = os.path.basename(prof)
+            k0 = pj["kernels"][0]
+            # the gate is read from ncu on the kernel actually run -- the binding pipe
+            pipes = {"issue_slots": k0.get("issue_slots_busy_pct"), "smem_lsu_wavefronts": k0.get("smem_wavefronts_pct"),
+                     "alu": k0.get("pipe_alu_pct"), "fma_int": k0.get("pipe_fma_pct"), "fp64": k0.get("pipe_fp64_pct"),
+                     "lsu": k0.get("pipe_lsu_pct"), "dram": k0.get("dram_throughput_pct")}
+            pipes = {k: v for k, v in pipes.items() if v is not None}
+            roofline["ncu_pipe_utilisation_pct"] = pipes
+            roofline["ncu_binding_pipe"] = max(pipes, key=pipes.get) if pipes else None
+            roofline["ncu_kernel"] = k0.get("kernel")
         except Exception:
             pass
 
