@@ -25,7 +25,7 @@ from ._capi import AsgError, InvalidNodeError, check, f64p, i64p
 __all__ = [
     "SparseGridInterpolant", "rsg", "train", "adapt", "coefficients", "basis", "dehierarchization_matrix",
     "hierarchization_matrix", "serialize", "deserialize", "maxlevels", "stack", "nodedepth", "isvalid",
-    "allindices_of_level", "child", "isbig2add", "AsgError", "InvalidNodeError",
+    "allindices_of_level", "child", "isbig2add", "hierarchize", "AsgError", "InvalidNodeError",
 ]
 
 _NODE_FIELDS = ("levels", "indices", "depths", "coefs", "lb", "ub")
@@ -370,6 +370,33 @@ def hierarchization_matrix(G, safe: bool = True, dropzeros: bool = True, atol: f
 
     E = dehierarchization_matrix(G, safe=safe, dropzeros=dropzeros, atol=atol).tocsc()
     return sps.csc_matrix(spla.spsolve(E, sps.identity(E.shape[0], format="csc")))
+
+
+def hierarchize(G: SparseGridInterpolant, fvals=None) -> np.ndarray:
+    """``E \\ fvals`` without forming or factoring E (the reference's route is
+    ``hierarchization_matrix``, src/class.jl:591-604, a sparse LU against a dense N x N identity).
+
+    E = basis(G) is unit lower-triangular under a depth sort (src/class.jl:517-519), so the solve is a
+    forward substitution by depth: for l = 1, 2, ...: ``coefs[depth == l] = fvals - G_{depth < l}(x_nodes)``
+    -- the residual step of ``train!`` (src/train.jl:176-183) with the nodal values given instead of
+    computed from ``f``. One fused GPU surplus call per depth writes the coefficients on the device;
+    the grid's ``coefs`` are overwritten. Returns ``G.coefs``."""
+    fv = np.ascontiguousarray(G.fvals if fvals is None else fvals, dtype=np.float64)
+    N = len(G.levels)
+    assert fv.shape == (N,), "one nodal value per node"
+    if len(G.coefs) != N:
+        G.coefs = np.zeros(N)
+    h = G._ensure()
+    lib = _capi.load()
+    for lnow in range(1, int(np.max(G.depths, initial=0)) + 1):
+        idx = np.flatnonzero(G.depths == lnow).astype(np.int64)
+        if len(idx) == 0:
+            continue
+        f = np.ascontiguousarray(fv[idx])
+        al = np.empty(len(idx), dtype=np.float64)
+        check(lib.asg_surplus_nodes(h, len(idx), _ptr(idx, i64p), _ptr(f, f64p), lnow - 1, 1, _ptr(al, f64p)))
+        G.coefs[idx] = al  # host copy in step with the device copy written by the kernel
+    return G.coefs
 
 
 # -------------------------------------------------------------------------------------------------

@@ -385,3 +385,71 @@ def test_full_size_properties(asg):
     # coefficient 1 on the root only -> G == 1 everywhere inside; basis row sums to the constant
     G.coefs = np.where(G.depths == 1, 1.0, 0.0)
     assert np.all(G.evaluate(X[:1000]) == 1.0)
+
+
+def test_hierarchize_forward_substitution(asg, oracle, cfg2):
+    """coefs = E \\ fvals by depth-ordered forward substitution on the GPU."""
+    G = asg.SparseGridInterpolant(3)
+    asg.train(G, sinsum, 6, 6)
+    want = G.coefs.copy()
+    G.coefs = np.zeros(len(G))
+    got = asg.hierarchize(G)
+    assert_close(got, want, np.abs(G.fvals) + 1, "hierarchize == train coefficients")
+    # against the explicit solve with the dehierarchization matrix (what the reference would do)
+    import scipy.sparse.linalg as spla
+    nodal = np.random.default_rng(0).standard_normal(len(G))
+    E = asg.dehierarchization_matrix(G).tocsc()
+    ref = spla.spsolve(E, nodal)
+    got = asg.hierarchize(G, nodal).copy()
+    assert_close(got, ref, 10 * (np.abs(nodal) + 1), "hierarchize == E \\ v")
+    assert_close(G.evaluate(asg.stack(G)), nodal, np.abs(nodal) + 1, "interpolates the nodal values")
+    # adaptive grid with hashed subspaces
+    A = _mirror(asg, cfg2)
+    A.coefs = np.zeros(len(A))
+    assert_close(asg.hierarchize(A), cfg2.coefs, 4 * (np.abs(cfg2.fvals) + 1), "adaptive hierarchize")
+
+
+@pytest.mark.parametrize("D", [11, 12, 13, 16])
+def test_high_dimensions(asg, oracle, D):
+    """D = 11, 12: subspace engine (largest instantiated kernels); D > 12: sweep engine fallback."""
+    OG = oracle.OracleGrid(D)
+    OG.rsg(3, 3)
+    rng = np.random.default_rng(D)
+    OG.coefs = rng.standard_normal(len(OG))
+    G = _mirror(asg, OG)
+    X = np.vstack([rng.random((3000, D)), _edge_points(D, OG.lb, OG.ub, rng, 16)])
+    want, sc = OG.evaluate(X, return_abssum=True)
+    assert_close(G.evaluate(X), want, sc, f"D={D}")
+    assert G.info()["path"] == (2 if D <= 12 else 1)
+    big = rng.random((400000, D)) if D <= 12 else None      # two points per thread path
+    if big is not None:
+        yb = G.evaluate(big)
+        assert_close(yb[:2000], OG.evaluate(big[:2000]), None, f"D={D} large batch")
+    B = asg.basis(X[:50], G).toarray()
+    assert np.array_equal(B != 0, OG.basis(X[:50]) != 0)
+
+
+def test_concurrent_handles_threads(asg, cfg1, cfg_nonunit):
+    """different handles used from different host threads at the same time (per-handle mutex)"""
+    import threading
+    grids = [_mirror(asg, cfg1), _mirror(asg, cfg_nonunit), _mirror(asg, cfg1)]
+    ogs = [cfg1, cfg_nonunit, cfg1]
+    rng = np.random.default_rng(3)
+    Xs = [og.lb + (og.ub - og.lb) * rng.random((20000, og.D)) for og in ogs]
+    wants = [og.evaluate(X) for og, X in zip(ogs, Xs)]
+    for G in grids:
+        G._ensure()
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got = grids[i].evaluate(Xs[i])
+                if np.max(np.abs(got - wants[i])) > 1e-13:
+                    errs.append(i)
+        except Exception as e:  # pragma: no cover
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
