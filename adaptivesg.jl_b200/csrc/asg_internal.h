@@ -78,7 +78,7 @@ constexpr uint32_t kGrpGlobal = 1u << 25;  // coefficients are read from global 
 struct StreamTile {  // records [r0, r1) reference FULL-group coefficient slots inside [c0, c1)
   uint32_t r0, r1, c0, c1;
 };
-constexpr int kTileCoefs = 4096;  // doubles per shared-memory coefficient tile (32 KB)
+constexpr int kTileCoefs = 2048;  // doubles per shared-memory coefficient tile (16 KB)
 constexpr int kTileRecs = 128;    // records per tile (6 KB)
 
 // Everything the kernels need, passed by value as a kernel parameter.

@@ -23,10 +23,15 @@
 namespace asg {
 
 // threads per CTA: one point per thread -> 2 CTAs of 256 per SM; two points per thread -> 1 CTA of 384
-template <int R>
+// Two configurations. V = 0 (one point per thread, small batches): saved prefix products in registers,
+// cell keys in shared memory, 2 CTAs of 256 threads per SM. V = 1 (two points per thread, large batches):
+// the saved prefix products live in shared memory too and cells are re-derived from the coordinates,
+// which keeps the kernel at 128 registers so that one CTA of 512 threads (16 warps, 1024 points) owns an SM
+// and the warp-uniform bookkeeping of a record is shared by 64 points.
+template <int R, int V = 0>
 struct StreamCfg {
-  static constexpr int kThreads = R == 1 ? 256 : 384;
-  static constexpr int kCtasPerSm = R == 1 ? 2 : 1;
+  static constexpr int kThreads = V == 1 ? 512 : (R == 1 ? 256 : 384);
+  static constexpr int kCtasPerSm = V == 1 ? 1 : (R == 1 ? 2 : 1);
 };
 
 struct __align__(16) StreamSmem {
@@ -77,11 +82,23 @@ __device__ __forceinline__ void issue_tile(const DeviceGrid &g, StreamSmem &sm, 
   if (cbytes) tma_load_1d(sm.coef[buf], g.coef + tl.c0, cbytes, &sm.bar[buf]);
 }
 
-template <int D, int R>
+template <int D, int R, int V = 0>
 struct StreamPoints {
-  static constexpr int DP = D - 1;  // prefix dimensions 0..D-2: coordinates live in shared memory
-  const double *xs;                 // xs[(K*R + k)*threads + tid]
-  const uint32_t *qs;
+  static constexpr int NT = StreamCfg<R, V>::kThreads;
+  const double *xs;                 // coordinates of all D dimensions: xs[(K*R + k)*NT + tid]
+  const uint32_t *qs;               // 30-bit cell keys, same layout (V == 0 only)
+  double *Ps;                       // V == 1: saved prefix products  Ps[(K*R + k)*NT + tid], K = 0..D-4
+  uint32_t *Os;                     // V == 1: saved prefix positions
+  // unit-cube coordinate and cell (top b bits of the key) of point k in dimension K
+  __device__ __forceinline__ double x(int K, int k) const { return xs[(K * R + k) * NT + threadIdx.x]; }
+  __device__ __forceinline__ uint32_t cell(int K, int k, int b, double xv) const {
+    if constexpr (V == 0) {
+      return qs[(K * R + k) * NT + threadIdx.x] >> (kKeyBits - b);
+    } else {  // floor(x * 2^b), clamped for x == 1 (exact: scaling by a power of two, truncation of a value >= 0)
+      const uint32_t c = (uint32_t)(xv * __hiloint2double((1023 + b) << 20, 0));
+      return min(c, (1u << b) - 1u);
+    }
+  }
   double ph[R][kLeafTable + 1];    // last dimension: hat of level l (levels 2..8)
   uint32_t w[R][kLeafTable + 1];   // last dimension: off(l) + cell_l
   double phA[R][kLeafTable + 1];   // dimension D-2: hat of level l   (SUPER records)
@@ -93,10 +110,10 @@ struct StreamPoints {
 __device__ __forceinline__ void pin_u32(uint32_t &v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void pin_f64(double &v) { asm volatile("" : "+d"(v)); }
 
-template <int D, int R>
+template <int D, int R, int V>
 __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp,
-                                                  int64_t sd, StreamPoints<D, R> &pt, int k, double *xs, uint32_t *qs) {
-  constexpr int NT = StreamCfg<R>::kThreads;
+                                                  int64_t sd, StreamPoints<D, R, V> &pt, int k, double *xs, uint32_t *qs) {
+  constexpr int NT = StreamCfg<R, V>::kThreads;
   bool inside = true;
   double u[D];
 #pragma unroll
@@ -110,7 +127,7 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
     const double v = inside ? u[d] : 0.5;  // walked at the centre; the result is replaced by the exact 0.0
     const uint32_t q = v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);  // floor(v*2^30), exact
     xs[(d * R + k) * NT + threadIdx.x] = v;  // all D dimensions: the last one is read by generic groups only
-    qs[(d * R + k) * NT + threadIdx.x] = q;
+    if constexpr (V == 0) qs[(d * R + k) * NT + threadIdx.x] = q;
     if (d == D - 2) {
 #pragma unroll
       for (int l = 2; l <= kLeafTable; ++l) {
@@ -138,27 +155,39 @@ __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const dou
 // Saved prefix products / positions of R points for dimensions 0..D-4. The running value `cur`
 // (product over the dimensions walked so far) lives in its own registers: a record restarts it from
 // the saved value of dimension k0-1, walks dimensions k0..D-3 and saves every dimension but the last,
-// whose value is consumed at once by the group evaluation.
-template <int D, int R>
+// whose value is consumed at once by the group evaluation. V == 0: saved values in registers;
+// V == 1: in shared memory (pt.Ps / pt.Os).
+template <int D, int R, int V>
 struct PrefixRegs {
-  static constexpr int NS = D > 3 ? D - 3 : 1;
+  static constexpr int NS = (V == 0 && D > 3) ? D - 3 : 1;
   double P[R][NS];
   uint32_t O[R][NS];
 };
 
+// hat of the supporting node of level l >= 2 in dimension K for point k
+template <int D, int R, int V>
+__device__ __forceinline__ void hat_of(const StreamPoints<D, R, V> &pt, int K, int k, int b, uint32_t odd, double s,
+                                       double &ph, uint32_t &cell) {
+  const double xv = pt.x(K, k);
+  cell = pt.cell(K, k, b, xv);
+  const uint32_t i = (cell << 1) + odd;
+  const double t = fma(xv, s, -u32_to_f64(i));  // x*2^(l-1) - i, one rounding as in the reference
+  ph = 1.0 - fabs(t);
+}
+
 // stage K: multiply the running prefix by the hat of the level-l node of dimension K that supports
 // the point (nothing to do for l == 1), then save it for later restarts unless K is the last prefix dim
-template <int D, int R, int K>
-__device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr, double (&cur)[R],
+template <int D, int R, int V, int K>
+__device__ __forceinline__ void stage(const StreamPoints<D, R, V> &pt, PrefixRegs<D, R, V> &pr, double (&cur)[R],
                                       uint32_t (&cO)[R], int l, int b, uint32_t odd, double s) {
+  constexpr int NT = StreamCfg<R, V>::kThreads;
   if (l > 1) {
-    constexpr int NT = StreamCfg<R>::kThreads;
     const uint32_t twob = 1u << b;
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       double ph;
       uint32_t cell;
-      hat_cell(pt.xs[(K * R + k) * NT + threadIdx.x], pt.qs[(K * R + k) * NT + threadIdx.x], b, odd, s, ph, cell);
+      hat_of<D, R, V>(pt, K, k, b, odd, s, ph, cell);
       cur[k] *= ph;
       cO[k] = cO[k] * twob + cell;  // (O << b) | cell as one IMAD
     }
@@ -166,32 +195,43 @@ __device__ __forceinline__ void stage(const StreamPoints<D, R> &pt, PrefixRegs<D
   if constexpr (K <= D - 4) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      pr.P[k][K] = cur[k];
-      pr.O[k][K] = cO[k];
+      if constexpr (V == 0) {
+        pr.P[k][K] = cur[k];
+        pr.O[k][K] = cO[k];
+      } else {
+        pt.Ps[(K * R + k) * NT + threadIdx.x] = cur[k];
+        pt.Os[(K * R + k) * NT + threadIdx.x] = cO[k];
+      }
     }
   }
 }
 
-template <int D, int R, int K>
-__device__ __forceinline__ void stage_from_levels(const StreamPoints<D, R> &pt, PrefixRegs<D, R> &pr,
+template <int D, int R, int V, int K>
+__device__ __forceinline__ void stage_from_levels(const StreamPoints<D, R, V> &pt, PrefixRegs<D, R, V> &pr,
                                                   double (&cur)[R], uint32_t (&cO)[R], uint32_t lev_lo,
                                                   uint32_t lev_hi) {
   const int l = (int)(((K < 6 ? lev_lo : lev_hi) >> (5 * (K % 6))) & 31u);
-  stage<D, R, K>(pt, pr, cur, cO, l, bits_of(l), l > 2 ? 1u : 0u, pow2_lm1(l));
+  stage<D, R, V, K>(pt, pr, cur, cO, l, bits_of(l), l > 2 ? 1u : 0u, pow2_lm1(l));
 }
 
-template <int D, int R, int K>
-__device__ __forceinline__ void restart(const PrefixRegs<D, R> &pr, double (&cur)[R], uint32_t (&cO)[R]) {
+template <int D, int R, int V, int K>
+__device__ __forceinline__ void restart(const StreamPoints<D, R, V> &pt, const PrefixRegs<D, R, V> &pr,
+                                        double (&cur)[R], uint32_t (&cO)[R]) {
+  constexpr int NT = StreamCfg<R, V>::kThreads;
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     if constexpr (K == 0) { cur[k] = 1.0; cO[k] = 0u; }
-    else { cur[k] = pr.P[k][K - 1]; cO[k] = pr.O[k][K - 1]; }
+    else if constexpr (V == 0) { cur[k] = pr.P[k][K - 1]; cO[k] = pr.O[k][K - 1]; }
+    else {
+      cur[k] = pt.Ps[((K - 1) * R + k) * NT + threadIdx.x];
+      cO[k] = pt.Os[((K - 1) * R + k) * NT + threadIdx.x];
+    }
   }
 }
 
 // FULL group from the shared-memory tile: 32-bit shared addresses, LDS gathers
-template <int D, int R>
-__device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, const double (&P)[R],
+template <int D, int R, int V>
+__device__ __forceinline__ void group_full_smem(const StreamPoints<D, R, V> &pt, const double (&P)[R],
                                                 const uint32_t (&O)[R], uint32_t tile_addr, uint32_t slot0,
                                                 uint32_t npre8, int lm, double (&acc)[R]) {
   uint32_t a0[R];
@@ -216,8 +256,8 @@ __device__ __forceinline__ void group_full_smem(const StreamPoints<D, R> &pt, co
 }
 
 // FULL group whose slice is too large for a tile: same arithmetic, coefficients from global memory
-template <int D, int R>
-__device__ __forceinline__ void group_full_global(const DeviceGrid &g, const StreamPoints<D, R> &pt,
+template <int D, int R, int V>
+__device__ __forceinline__ void group_full_global(const DeviceGrid &g, const StreamPoints<D, R, V> &pt,
                                                   const double (&P)[R], const uint32_t (&O)[R], uint32_t base1,
                                                   uint32_t npre8, int lm, double (&acc)[R]) {
   const double *A0[R];
@@ -244,8 +284,8 @@ __device__ __forceinline__ void group_full_global(const DeviceGrid &g, const Str
 // SUPER record: levels 1..lmA of dimension D-2 x levels 1..lmB(lA) of dimension D-1, both unrolled
 // against the register tables. P, O are the prefix product / position over dimensions 0..D-3.
 // mask_rem < 0: no depth mask; otherwise budget left for the last two dimensions.
-template <int D, int R, bool SMEM>
-__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
+template <int D, int R, int V, bool SMEM>
+__device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoints<D, R, V> &pt, const double (&P)[R],
                                             const uint32_t (&O)[R], uint32_t sbase0, uint32_t base1, uint32_t npre8,
                                             int lmA, uint32_t lmBs, const uint4 &offs, int mask_rem,
                                             double (&acc)[R]) {
@@ -304,8 +344,8 @@ __device__ __forceinline__ void group_super(const DeviceGrid &g, const StreamPoi
 }
 
 // GENERIC group: explicit leaf records (any levels, dense or hashed), global memory
-template <int D, int R>
-__device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R> &pt, const double (&P)[R],
+template <int D, int R, int V>
+__device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamPoints<D, R, V> &pt, const double (&P)[R],
                                               const uint32_t (&O)[R], uint32_t jb, uint32_t n, int rem, int pb,
                                               double (&acc)[R]) {
   EvalSink<R> sink;
@@ -328,9 +368,7 @@ __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamP
       const double s = pow2_lm1(l);
       const uint32_t odd = l > 2 ? 1u : 0u;
 #pragma unroll
-      for (int k = 0; k < R; ++k)
-        hat_cell(pt.xs[((D - 1) * R + k) * StreamCfg<R>::kThreads + threadIdx.x],
-                 pt.qs[((D - 1) * R + k) * StreamCfg<R>::kThreads + threadIdx.x], b, odd, s, ph[k], cell[k]);
+      for (int k = 0; k < R; ++k) hat_of<D, R, V>(pt, D - 1, k, b, odd, s, ph[k], cell[k]);
     } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) { cell[k] = 0u; ph[k] = 1.0; }
@@ -341,14 +379,17 @@ __device__ __forceinline__ void group_generic(const DeviceGrid &g, const StreamP
   for (int k = 0; k < R; ++k) acc[k] = sink.acc[k];
 }
 
-template <int D, int R, bool MASKED>
-__global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPerSm)
+template <int D, int R, bool MASKED, int V>
+__global__ void __launch_bounds__(StreamCfg<R, V>::kThreads, StreamCfg<R, V>::kCtasPerSm)
     k_eval_stream(const DeviceGrid g, const EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StreamSmem &sm = *reinterpret_cast<StreamSmem *>(smem_raw);
-  constexpr int NT = StreamCfg<R>::kThreads;
+  constexpr int NT = StreamCfg<R, V>::kThreads;
+  constexpr int NSV = D > 3 ? D - 3 : 1;  // saved prefix dimensions (V == 1: in shared memory)
   double *xs = reinterpret_cast<double *>(smem_raw + sizeof(StreamSmem));
-  uint32_t *qs = reinterpret_cast<uint32_t *>(xs + (size_t)D * R * NT);
+  double *Ps = xs + (size_t)D * R * NT;                                                // V == 1
+  uint32_t *Os = reinterpret_cast<uint32_t *>(Ps + (size_t)NSV * R * NT);             // V == 1
+  uint32_t *qs = reinterpret_cast<uint32_t *>(xs + (size_t)D * R * NT);               // V == 0
   const int64_t tile_pts = (int64_t)blockDim.x * R;
   const int64_t stride = (int64_t)gridDim.x * tile_pts;
   const uint32_t ntiles = g.n_tiles;
@@ -361,22 +402,24 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
   uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
 
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
-    StreamPoints<D, R> pt;
+    StreamPoints<D, R, V> pt;
     pt.xs = xs;
     pt.qs = qs;
+    pt.Ps = Ps;
+    pt.Os = Os;
     bool inside[R];
     int64_t m[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       m[k] = base + (int64_t)k * blockDim.x + threadIdx.x;
       const int64_t mm = m[k] < a.M ? m[k] : a.M - 1;  // tail lanes redo the last point, never store
-      inside[k] = stream_load_point<D, R>(g, a.X, mm, a.sp, a.sd, pt, k, xs, qs);
+      inside[k] = stream_load_point<D, R, V>(g, a.X, mm, a.sp, a.sd, pt, k, xs, qs);
     }
     if (threadIdx.x == 0) {
       issue_tile(g, sm, 0, 0);
       if (ntiles > 1) issue_tile(g, sm, 1, 1);
     }
-    PrefixRegs<D, R> pr;
+    PrefixRegs<D, R, V> pr;
     double acc[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) acc[k] = 0.0;
@@ -416,27 +459,27 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
         if constexpr (D >= 3) {
           kfrom = min(kfrom, D - 3);  // the value of dimension D-3 is never saved: always redo that stage
           switch (kfrom) {
-            case 0: restart<D, R, 0>(pr, cur, cO); break;
-            case 1: if constexpr (D - 3 >= 1) restart<D, R, (D - 3 >= 1 ? 1 : 0)>(pr, cur, cO); break;
-            case 2: if constexpr (D - 3 >= 2) restart<D, R, (D - 3 >= 2 ? 2 : 0)>(pr, cur, cO); break;
-            case 3: if constexpr (D - 3 >= 3) restart<D, R, (D - 3 >= 3 ? 3 : 0)>(pr, cur, cO); break;
-            case 4: if constexpr (D - 3 >= 4) restart<D, R, (D - 3 >= 4 ? 4 : 0)>(pr, cur, cO); break;
-            case 5: if constexpr (D - 3 >= 5) restart<D, R, (D - 3 >= 5 ? 5 : 0)>(pr, cur, cO); break;
-            case 6: if constexpr (D - 3 >= 6) restart<D, R, (D - 3 >= 6 ? 6 : 0)>(pr, cur, cO); break;
-            case 7: if constexpr (D - 3 >= 7) restart<D, R, (D - 3 >= 7 ? 7 : 0)>(pr, cur, cO); break;
-            case 8: if constexpr (D - 3 >= 8) restart<D, R, (D - 3 >= 8 ? 8 : 0)>(pr, cur, cO); break;
-            default: if constexpr (D - 3 >= 9) restart<D, R, (D - 3 >= 9 ? 9 : 0)>(pr, cur, cO); break;
+            case 0: restart<D, R, V, 0>(pt, pr, cur, cO); break;
+            case 1: if constexpr (D - 3 >= 1) restart<D, R, V, (D - 3 >= 1 ? 1 : 0)>(pt, pr, cur, cO); break;
+            case 2: if constexpr (D - 3 >= 2) restart<D, R, V, (D - 3 >= 2 ? 2 : 0)>(pt, pr, cur, cO); break;
+            case 3: if constexpr (D - 3 >= 3) restart<D, R, V, (D - 3 >= 3 ? 3 : 0)>(pt, pr, cur, cO); break;
+            case 4: if constexpr (D - 3 >= 4) restart<D, R, V, (D - 3 >= 4 ? 4 : 0)>(pt, pr, cur, cO); break;
+            case 5: if constexpr (D - 3 >= 5) restart<D, R, V, (D - 3 >= 5 ? 5 : 0)>(pt, pr, cur, cO); break;
+            case 6: if constexpr (D - 3 >= 6) restart<D, R, V, (D - 3 >= 6 ? 6 : 0)>(pt, pr, cur, cO); break;
+            case 7: if constexpr (D - 3 >= 7) restart<D, R, V, (D - 3 >= 7 ? 7 : 0)>(pt, pr, cur, cO); break;
+            case 8: if constexpr (D - 3 >= 8) restart<D, R, V, (D - 3 >= 8 ? 8 : 0)>(pt, pr, cur, cO); break;
+            default: if constexpr (D - 3 >= 9) restart<D, R, V, (D - 3 >= 9 ? 9 : 0)>(pt, pr, cur, cO); break;
           }
           switch (kfrom) {  // fall through: stages kfrom .. D-4 from the packed levels
-            case 0: if constexpr (D - 4 >= 0) stage_from_levels<D, R, 0>(pt, pr, cur, cO, rb.x, rb.y);
-            case 1: if constexpr (D - 4 >= 1) stage_from_levels<D, R, (D - 4 >= 1 ? 1 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 2: if constexpr (D - 4 >= 2) stage_from_levels<D, R, (D - 4 >= 2 ? 2 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 3: if constexpr (D - 4 >= 3) stage_from_levels<D, R, (D - 4 >= 3 ? 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 4: if constexpr (D - 4 >= 4) stage_from_levels<D, R, (D - 4 >= 4 ? 4 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 5: if constexpr (D - 4 >= 5) stage_from_levels<D, R, (D - 4 >= 5 ? 5 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 6: if constexpr (D - 4 >= 6) stage_from_levels<D, R, (D - 4 >= 6 ? 6 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 7: if constexpr (D - 4 >= 7) stage_from_levels<D, R, (D - 4 >= 7 ? 7 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
-            case 8: if constexpr (D - 4 >= 8) stage_from_levels<D, R, (D - 4 >= 8 ? 8 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 0: if constexpr (D - 4 >= 0) stage_from_levels<D, R, V, 0>(pt, pr, cur, cO, rb.x, rb.y);
+            case 1: if constexpr (D - 4 >= 1) stage_from_levels<D, R, V, (D - 4 >= 1 ? 1 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 2: if constexpr (D - 4 >= 2) stage_from_levels<D, R, V, (D - 4 >= 2 ? 2 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 3: if constexpr (D - 4 >= 3) stage_from_levels<D, R, V, (D - 4 >= 3 ? 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 4: if constexpr (D - 4 >= 4) stage_from_levels<D, R, V, (D - 4 >= 4 ? 4 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 5: if constexpr (D - 4 >= 5) stage_from_levels<D, R, V, (D - 4 >= 5 ? 5 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 6: if constexpr (D - 4 >= 6) stage_from_levels<D, R, V, (D - 4 >= 6 ? 6 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 7: if constexpr (D - 4 >= 7) stage_from_levels<D, R, V, (D - 4 >= 7 ? 7 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+            case 8: if constexpr (D - 4 >= 8) stage_from_levels<D, R, V, (D - 4 >= 8 ? 8 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
             default: break;
           }
         } else {
@@ -448,29 +491,27 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
           // stage D-3 (every record) from the fields the packer precomputed: s_hi, bod describe dimension D-3
           if constexpr (D >= 3) {
             const int l3 = (int)(((D - 3 < 6 ? rb.x : rb.y) >> (5 * ((D - 3) % 6))) & 31u);
-            stage<D, R, D - 3>(pt, pr, cur, cO, l3, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
+            stage<D, R, V, D - 3>(pt, pr, cur, cO, l3, (int)(rb.w & 0xffu), (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0));
           }
           const int lmA = (int)(ra.z & 0xffu);
           if (!(ra.z & kGrpGlobal))
-            group_super<D, R, true>(g, pt, cur, cO, ra.x * 8u + tbias, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
+            group_super<D, R, V, true>(g, pt, cur, cO, ra.x * 8u + tbias, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           else
-            group_super<D, R, false>(g, pt, cur, cO, 0u, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
+            group_super<D, R, V, false>(g, pt, cur, cO, 0u, ra.x, ra.y, lmA, ra.w, rc, MASKED ? rem : -1, acc);
           continue;
         }
         // per-group record (irregular parts): stage D-3 from the packed levels, stage D-2 from s_hi / bod
-        if constexpr (D >= 3) stage_from_levels<D, R, (D >= 3 ? D - 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
+        if constexpr (D >= 3) stage_from_levels<D, R, V, (D >= 3 ? D - 3 : 0)>(pt, pr, cur, cO, rb.x, rb.y);
         {
           const int lA = (int)(((D - 2 < 6 ? rb.x : rb.y) >> (5 * ((D - 2) % 6))) & 31u);
           if (lA > 1) {
-            constexpr int NT2 = StreamCfg<R>::kThreads;
             const int b = (int)(rb.w & 0xffu);
             const uint32_t twob = 1u << b;
 #pragma unroll
             for (int k = 0; k < R; ++k) {
               double ph;
               uint32_t cell;
-              hat_cell(pt.xs[((D - 2) * R + k) * NT2 + threadIdx.x], pt.qs[((D - 2) * R + k) * NT2 + threadIdx.x], b,
-                       (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0), ph, cell);
+              hat_of<D, R, V>(pt, D - 2, k, b, (rb.w >> 8) & 1u, __hiloint2double((int)rb.z, 0), ph, cell);
               cur[k] *= ph;
               cO[k] = cO[k] * twob + cell;
             }
@@ -478,10 +519,10 @@ __global__ void __launch_bounds__(StreamCfg<R>::kThreads, StreamCfg<R>::kCtasPer
         }
         if (ra.z & kGrpFull) {
           const int lm = min((int)(ra.z & 0xffu), rem + 1);
-          if (!(ra.z & kGrpGlobal)) group_full_smem<D, R>(pt, cur, cO, tbias, ra.x, ra.y, lm, acc);
-          else group_full_global<D, R>(g, pt, cur, cO, ra.x, ra.y, lm, acc);
+          if (!(ra.z & kGrpGlobal)) group_full_smem<D, R, V>(pt, cur, cO, tbias, ra.x, ra.y, lm, acc);
+          else group_full_global<D, R, V>(g, pt, cur, cO, ra.x, ra.y, lm, acc);
         } else {
-          group_generic<D, R>(g, pt, cur, cO, ra.x, ra.w, rem, (int)((rb.w >> 16) & 0xffu), acc);
+          group_generic<D, R, V>(g, pt, cur, cO, ra.x, ra.w, rem, (int)((rb.w >> 16) & 0xffu), acc);
         }
       }
       __syncthreads();  // every warp is done with buffer `buf`
@@ -520,27 +561,32 @@ static int sm_count() {
 cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
   if (a.M <= 0) return cudaSuccess;
   const int sms = sm_count();
-  bool two = a.M >= (int64_t)sms * StreamCfg<2>::kThreads * 4;
-  if (const char *e = getenv("ASG_STREAM_R")) two = (e[0] == '2');  // experiment knob
-  const int threads = two ? StreamCfg<2>::kThreads : StreamCfg<1>::kThreads;
-  const size_t smem = sizeof(StreamSmem) + (size_t)g.D * (two ? 2 : 1) * threads * 12;
-  const int per_block = threads * (two ? 2 : 1);
+  // two configurations: small batches -> one point per thread, saved prefixes in registers, 2 CTAs x 256
+  // threads per SM; large batches -> two points per thread, saved prefixes in shared memory, 1 CTA x 512
+  const int nsv = g.D > 3 ? g.D - 3 : 1;
+  const size_t smem2 = sizeof(StreamSmem) + ((size_t)g.D * 8 + (size_t)nsv * 12) * 2 * StreamCfg<2, 1>::kThreads;
+  bool two = a.M >= (int64_t)sms * StreamCfg<2, 1>::kThreads * 4 && smem2 <= 227 * 1024;
+  if (const char *e = getenv("ASG_STREAM_R")) two = (e[0] == '2') && smem2 <= 227 * 1024;  // experiment knob
+  const int R = two ? 2 : 1;
+  const int threads = two ? StreamCfg<2, 1>::kThreads : StreamCfg<1, 0>::kThreads;
+  const size_t smem = two ? smem2 : sizeof(StreamSmem) + (size_t)g.D * 12 * threads;
+  const int per_block = threads * R;
   // persistent-style grid: every CTA re-streams the whole grid per batch of points, so use as few
   // batches as possible: one CTA per resident slot, grid-stride over the points
-  const int resident = two ? 1 : 2;
+  const int resident = two ? StreamCfg<2, 1>::kCtasPerSm : StreamCfg<1, 0>::kCtasPerSm;
   int64_t need = (a.M + per_block - 1) / per_block;
   const int64_t cap = (int64_t)sms * resident;
   const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
   const bool masked = a.rem < INT_MAX / 4;
-#define LAUNCH(DD, RR, MM)                                                                                      \
-  do {                                                                                                          \
-    cudaFuncSetAttribute(k_eval_stream<DD, RR, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k_eval_stream<DD, RR, MM><<<blocks, threads, smem, st>>>(g, a);                                             \
+#define LAUNCH(DD, RR, MM, VV)                                                                                    \
+  do {                                                                                                            \
+    cudaFuncSetAttribute(k_eval_stream<DD, RR, MM, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    k_eval_stream<DD, RR, MM, VV><<<blocks, threads, smem, st>>>(g, a);                                           \
   } while (0)
 #define CALL(DD)                                                                                          \
   do {                                                                                                    \
-    if (two) { if (masked) LAUNCH(DD, 2, true); else LAUNCH(DD, 2, false); }                              \
-    else     { if (masked) LAUNCH(DD, 1, true); else LAUNCH(DD, 1, false); }                              \
+    if (two) { if (masked) LAUNCH(DD, 2, true, 1); else LAUNCH(DD, 2, false, 1); }                        \
+    else     { if (masked) LAUNCH(DD, 1, true, 0); else LAUNCH(DD, 1, false, 0); }                        \
   } while (0)
   ASG_DISPATCH_D2(g.D, CALL)
 #undef CALL

@@ -233,6 +233,13 @@ def main():
     gen = torch.Generator(device=dev)
     gen.manual_seed(42 + rank)
     X = torch.rand((M, D), dtype=torch.float64, device=dev, generator=gen)
+    if os.environ.get("ASG_BENCH_SORT"):  # experiment: points pre-sorted by a coarse cell key (2 bits per dimension)
+        bits = int(os.environ["ASG_BENCH_SORT"])
+        key = torch.zeros(M, dtype=torch.int64, device=dev)
+        for d in range(D):
+            key = (key << bits) | (X[:, d] * (1 << bits)).to(torch.int64).clamp_(0, (1 << bits) - 1)
+        X = X[torch.argsort(key)].contiguous()
+        del key
     out = torch.empty(M, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
 
