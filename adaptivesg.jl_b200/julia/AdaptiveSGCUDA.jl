@@ -13,7 +13,7 @@ module AdaptiveSGCUDA
 using SparseArrays, Printf
 
 export SparseGridInterpolant, rsg!, train!, adapt!, coefficients, basis, dehierarchization_matrix,
-       hierarchization_matrix, serialize, deserialize, maxlevels, sync!, nodedepth, isvalid,
+       hierarchization_matrix, hierarchize!, serialize, deserialize, maxlevels, sync!, nodedepth, isvalid,
        allindices_of_level, child, scale, get_x
 
 const LIB = get(ENV, "ASG_CUDA_LIB", "libasg_cuda")
@@ -214,6 +214,25 @@ basis(G::SparseGridInterpolant{D}; kw...) where {D} =
 dehierarchization_matrix(G::SparseGridInterpolant; kw...) = basis(G; kw...)
 hierarchization_matrix(G::SparseGridInterpolant; kw...) =                 # src/class.jl:591-604 (host solve)
     (E = dehierarchization_matrix(G; kw...); sparse(E \ Matrix{Float64}(SparseArrays.I, size(E)...)))
+
+"""
+    hierarchize!(G, fvals = G.fvals)
+
+`G.coefs = E \\ fvals` by forward substitution over depths (E is unit lower-triangular under a depth
+sort): one fused surplus call per depth, no LU. Additive API (the reference offers only the dense
+`hierarchization_matrix`, src/class.jl:591-604).
+"""
+function hierarchize!(G::SparseGridInterpolant, fvals::Vector{Float64} = G.fvals)
+    h = ensure!(G)
+    for lnow in 1:maximum(G.depths; init = 0)
+        idx = findall(G.depths .== lnow); isempty(idx) && continue
+        f = fvals[idx]; al = similar(f); idx0 = Int64.(idx .- 1)
+        check(ccall((:asg_surplus_nodes, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Int64, Int32, Ptr{Float64}),
+                    h, length(idx), idx0, f, lnow - 1, 1, al))
+        G.coefs[idx] = al
+    end
+    return G.coefs
+end
 
 # ---------------------------------------------------------------------------------------------
 # I/O (src/io.jl:9-72): same Dict schema; deserialize leaves the mirror unsynced

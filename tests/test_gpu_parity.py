@@ -453,3 +453,49 @@ def test_concurrent_handles_threads(asg, cfg1, cfg_nonunit):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs
+
+
+def test_device_pointer_entry_points(asg, cfg1):
+    """asg_eval_device / asg_surplus_device / asg_basis_dense_device with buffers resident in HBM (torch
+    only supplies the device memory and the stream; no host copies inside the calls)."""
+    import ctypes as C
+    import torch
+    G = _mirror(asg, cfg1)
+    h = G._ensure()
+    lib = asg._capi.load()
+    rng = np.random.default_rng(17)
+    Xh = rng.random((5000, 3))
+    fh = rng.standard_normal(5000)
+    want = cfg1.evaluate(Xh)
+    X = torch.from_numpy(Xh).cuda()
+    f = torch.from_numpy(fh).cuda()
+    out = torch.empty(5000, dtype=torch.float64, device="cuda")
+    side = torch.cuda.Stream()
+    for stream in (torch.cuda.current_stream(), side):
+        with torch.cuda.stream(stream):
+            out.zero_()
+            asg._capi.check(lib.asg_eval_device(h, C.c_void_p(X.data_ptr()), 5000, 3, 1, -1, C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(stream.cuda_stream)))
+        stream.synchronize()
+        assert_close(out.cpu().numpy(), want, None, "eval_device")
+    ms = C.c_double()
+    asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))
+    assert 0.0 < ms.value < 1000.0
+    # column-major device matrix (Julia layout): strides (1, M)
+    Xc = X.t().contiguous()
+    asg._capi.check(lib.asg_eval_device(h, C.c_void_p(Xc.data_ptr()), 5000, 1, 5000, 4, C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), cfg1.evaluate(Xh, max_depth=4), None, "eval_device masked, column-major")
+    asg._capi.check(lib.asg_surplus_device(h, C.c_void_p(X.data_ptr()), 5000, 3, 1, C.c_void_p(f.data_ptr()), -1,
+                                           C.c_void_p(out.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert_close(out.cpu().numpy(), fh - want, np.abs(fh) + 1, "surplus_device")
+    N = len(G)
+    Bd = torch.full((200, N), -7.0, dtype=torch.float64, device="cuda")
+    asg._capi.check(lib.asg_basis_dense_device(h, C.c_void_p(X.data_ptr()), 200, 3, 1, 1e-16, 1,
+                                               C.c_void_p(Bd.data_ptr()), N, 1, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(Bd.cpu().numpy(), cfg1.basis(Xh[:200]))
+    n0 = asg.launch_count()
+    G.evaluate(Xh)
+    assert asg.launch_count() > n0                       # the CUDA path is what ran
