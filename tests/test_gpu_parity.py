@@ -381,7 +381,16 @@ def test_full_size_properties(asg):
     Xb = rng.random((400000, D))
     yb = G.evaluate(Xb)
     ysmall = np.concatenate([G.evaluate(Xb[k:k + 50000]) for k in range(0, 100000, 50000)])
-    assert np.array_equal(yb[:100000], ysmall)
+    assert np.max(np.abs(yb[:100000] - ysmall)) < 1e-13
+    # the same for the depth-masked walk and the fused surplus epilogue (train!'s call shape)
+    fb = rng.standard_normal(len(Xb))
+    for L in (3, 6):
+        ym = G.evaluate(Xb, max_depth=L)
+        ysm = G.evaluate(Xb[:50000], max_depth=L)
+        assert np.max(np.abs(ym[:50000] - ysm)) < 1e-13
+        assert np.max(np.abs(G.surplus(Xb, fb, max_depth=L) - (fb - ym))) < 1e-13
+    G.set_path("sweep")
+    assert np.max(np.abs(G.evaluate(Xb[:128], max_depth=6) - G.set_path("auto").evaluate(Xb, max_depth=6)[:128])) < 1e-12
     # coefficient 1 on the root only -> G == 1 everywhere inside; basis row sums to the constant
     G.coefs = np.where(G.depths == 1, 1.0, 0.0)
     assert np.all(G.evaluate(X[:1000]) == 1.0)
