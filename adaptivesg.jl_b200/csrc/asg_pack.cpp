@@ -357,6 +357,22 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
         t.r1 = (uint32_t)j;
         out.tiles.push_back(t);
       }
+      // self-check of the stream the kernels will trust blindly: every SUPER / FULL record that reads from a
+      // tile must have its whole slice inside that tile's [c0, c1) window, windows must fit the buffers
+      for (const StreamTile &t : out.tiles) {
+        if (t.c1 - t.c0 > (uint32_t)kTileCoefs || t.r1 - t.r0 > (uint32_t)kTileRecs || (t.c0 & 1u) || (t.c1 & 1u) ||
+            (uint64_t)t.c1 > out.coef.size() + 2) {
+          err = "internal error: stream tile out of bounds";
+          return ASG_ESTATE;
+        }
+        for (uint32_t r = t.r0; r < t.r1; ++r) {
+          const GroupRec &q = out.grp[r];
+          if ((q.meta & (kGrpFull | kGrpSuper)) && !(q.meta & kGrpGlobal) && (span_lo[r] < t.c0 || span_hi[r] > t.c1)) {
+            err = "internal error: record slice outside its tile";
+            return ASG_ESTATE;
+          }
+        }
+      }
       out.coef_pad = 2;
       out.coef.resize(out.coef.size() + 2, 0.0);  // tiles round their end up to an even slot
       out.orig.resize(out.orig.size() + 2, -1);

@@ -508,3 +508,35 @@ def test_device_pointer_entry_points(asg, cfg1):
     n0 = asg.launch_count()
     G.evaluate(Xh)
     assert asg.launch_count() > n0                       # the CUDA path is what ran
+
+
+def test_fuzz_irregular_grids(asg, oracle):
+    """random node subsets of regular grids in D = 1..7: mixtures of SUPER / per-group / generic records,
+    dense and hashed subspaces, missing levels -- all three subspace walks and the sweep engine against the oracle"""
+    rng = np.random.default_rng(2025)
+    kinds = set()
+    for trial in range(24):
+        D = int(rng.integers(1, 8))
+        OG = oracle.OracleGrid(D, lb=-rng.random(D), ub=1.0 + rng.random(D))
+        OG.rsg(int(rng.integers(2, 7)), tuple(int(v) for v in rng.integers(2, 7, size=D)))
+        keep = rng.random(len(OG)) < rng.choice([1.0, 0.95, 0.6, 0.25])
+        keep[0] = True
+        OG.levels, OG.indices, OG.depths = OG.levels[keep], OG.indices[keep], OG.depths[keep]
+        OG.coefs = rng.standard_normal(len(OG.levels))
+        OG.fvals = np.zeros(len(OG.levels))
+        G = _mirror(asg, OG)
+        info = G.info()
+        assert info["canonical"] == 1
+        kinds.add((info["regular"], info["hash_slots"] > 0))
+        X = np.vstack([OG.lb + (OG.ub - OG.lb) * rng.random((1500, D)), _edge_points(D, OG.lb, OG.ub, rng, 8)])
+        L = int(rng.integers(1, int(OG.depths.max()) + 1))
+        want, sc = OG.evaluate(X, return_abssum=True)
+        wantm, scm = OG.evaluate(X, max_depth=L, return_abssum=True)
+        for path in ("subspace", "trie", "sweep"):
+            G.set_path(path)
+            assert_close(G.evaluate(X), want, sc, f"fuzz {trial} D={D} {path}")
+            assert_close(G.evaluate(X, max_depth=L), wantm, scm, f"fuzz {trial} D={D} {path} depth<={L}")
+        G.set_path("auto")
+        B = asg.basis(X[:40], G).toarray()
+        assert np.array_equal(B != 0, OG.basis(X[:40]) != 0)
+    assert len(kinds) >= 3          # regular, irregular dense, irregular hashed were all exercised
