@@ -539,4 +539,10 @@ def test_fuzz_irregular_grids(asg, oracle):
         G.set_path("auto")
         B = asg.basis(X[:40], G).toarray()
         assert np.array_equal(B != 0, OG.basis(X[:40]) != 0)
+        if trial % 4 == 0:  # large batch: the two-points-per-thread configuration on the same irregular grid
+            Xb = OG.lb + (OG.ub - OG.lb) * rng.random((320000, D))
+            yb = G.evaluate(Xb)
+            wb, sb = OG.evaluate(Xb[:3000], return_abssum=True)
+            assert_close(yb[:3000], wb, sb, f"fuzz {trial} D={D} large batch")
+            assert_close(G.evaluate(Xb, max_depth=L)[:3000], OG.evaluate(Xb[:3000], max_depth=L), sb, "large batch masked")
     assert len(kinds) >= 3          # regular, irregular dense, irregular hashed were all exercised
