@@ -198,6 +198,9 @@ __device__ __forceinline__ void stage(const StreamPoints<D, R, V> &pt, PrefixReg
       if constexpr (V == 0) {
         pr.P[k][K] = cur[k];
         pr.O[k][K] = cO[k];
+      } else if constexpr (K == D - 4) {  // the deepest saved level stays in registers: half of all restarts use it
+        pr.P[k][0] = cur[k];
+        pr.O[k][0] = cO[k];
       } else {
         pt.Ps[(K * R + k) * NT + threadIdx.x] = cur[k];
         pt.Os[(K * R + k) * NT + threadIdx.x] = cO[k];
@@ -222,6 +225,7 @@ __device__ __forceinline__ void restart(const StreamPoints<D, R, V> &pt, const P
   for (int k = 0; k < R; ++k) {
     if constexpr (K == 0) { cur[k] = 1.0; cO[k] = 0u; }
     else if constexpr (V == 0) { cur[k] = pr.P[k][K - 1]; cO[k] = pr.O[k][K - 1]; }
+    else if constexpr (K - 1 == D - 4) { cur[k] = pr.P[k][0]; cO[k] = pr.O[k][0]; }
     else {
       cur[k] = pt.Ps[((K - 1) * R + k) * NT + threadIdx.x];
       cO[k] = pt.Os[((K - 1) * R + k) * NT + threadIdx.x];
