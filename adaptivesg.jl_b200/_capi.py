@@ -20,7 +20,7 @@ ASG_ECUDA = -4
 ASG_ENOMEM = -5
 ASG_EUNSUPPORTED = -6
 ASG_ESTATE = -7
-ASG_PATH_AUTO, ASG_PATH_SWEEP, ASG_PATH_SUBSPACE, ASG_PATH_TRIE = 0, 1, 2, 3
+ASG_PATH_AUTO, ASG_PATH_SWEEP, ASG_PATH_SUBSPACE, ASG_PATH_TRIE, ASG_PATH_STREAM, ASG_PATH_BLOCK = 0, 1, 2, 3, 4, 5
 
 _CODE_NAMES = {
     ASG_EINVAL: "ASG_EINVAL", ASG_EINVALID_NODE: "ASG_EINVALID_NODE", ASG_ENODEVICE: "ASG_ENODEVICE",
@@ -45,6 +45,7 @@ class GridInfo(C.Structure):
         ("N", C.c_int64), ("max_depth", C.c_int64), ("subspaces", C.c_int64), ("dense_subspaces", C.c_int64),
         ("trie_nodes", C.c_int64), ("coef_slots", C.c_int64), ("hash_slots", C.c_int64),
         ("device_bytes", C.c_int64), ("generation", C.c_int64), ("regular", C.c_int64),
+        ("block", C.c_int64), ("block_slots", C.c_int64), ("block_records", C.c_int64),
     ]
 
     def as_dict(self):

@@ -89,7 +89,9 @@ struct asg_grid {
   int64_t N = 0;
   std::vector<int64_t> levels, indices;
   std::vector<double> coefs;
-  std::vector<int64_t> slot_of_node;
+  std::vector<int64_t> slot_of_node, bslot_of_node;
+  bool blk_ok = false;
+  std::string blk_why;
   bool uploaded = false, canonical = false, finite = true, regular = false;
   RsgParams rp{};
   std::string why;
@@ -100,6 +102,9 @@ struct asg_grid {
   DevBuf<TrieRec> d_rec;
   DevBuf<GroupRec> d_grp;
   DevBuf<StreamTile> d_tiles;
+  DevBuf<double> d_bcoef;
+  DevBuf<BlockRec> d_brec;
+  DevBuf<BlockTile> d_btiles;
   DevBuf<double> d_coef, d_sw_coef;
   DevBuf<int32_t> d_orig, d_horig, d_sw_depth;
   DevBuf<HashEnt> d_hent;
@@ -110,17 +115,26 @@ struct asg_grid {
   DevBuf<long long> s_i64a, s_i64b;
   DevBuf<double> s_tmp, s_tmp2;
   DevBuf<int> s_flag;
+  // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
+  DevBuf<uint32_t> s_key[2], s_key2[2], s_idx[2], s_perm[2];
+  DevBuf<unsigned char> s_sorttmp[2];
+  cudaEvent_t sort_ev[2] = {nullptr, nullptr};  // last use of the slot's scratch
   int path() const {
     if (forced_path == ASG_PATH_SWEEP) return ASG_PATH_SWEEP;
     return (canonical && finite) ? ASG_PATH_SUBSPACE : ASG_PATH_SWEEP;
   }
-  // which walk of the subspace engine: 0 = flat group stream (default), 1 = record-free regular walk,
+  // which walk of the subspace engine: 3 = BLOCK walk (default where the layout exists), 0 = flat group
+  // stream (other canonical grids, ASG_EVAL_KERNEL=stream), 1 = record-free regular walk (=rsg),
   // 2 = recursive trie walk (ASG_PATH_TRIE, D == 1, or ASG_EVAL_KERNEL=trie)
   int walk() const {
     static const char *env = getenv("ASG_EVAL_KERNEL");
     if (forced_path == ASG_PATH_TRIE || D < 2 || dg.n_tiles == 0) return 2;
+    if (forced_path == ASG_PATH_STREAM) return 0;
+    if (forced_path == ASG_PATH_BLOCK) return (blk_ok && block_kernel_fits(dg)) ? 3 : 0;
     if (env && env[0] == 't') return 2;
     if (env && env[0] == 'r' && regular) return 1;
+    if (env && env[0] == 's') return 0;
+    if (blk_ok && block_kernel_fits(dg)) return 3;
     return 0;
   }
 };
@@ -200,6 +214,20 @@ int device_upload(asg_grid *g, const PackResult &pk) {
     dg.orig = g->d_orig.p;
     dg.hent = g->d_hent.p;
     dg.horig = g->d_horig.p;
+    if (pk.blk_ok) {
+      if (int rc = g->d_bcoef.reserve(pk.bcoef.size())) return rc;
+      if (int rc = g->d_brec.reserve(pk.brec.size())) return rc;
+      if (int rc = g->d_btiles.reserve(pk.btiles.size())) return rc;
+      CK(cudaMemcpyAsync(g->d_bcoef.p, pk.bcoef.data(), pk.bcoef.size() * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(g->d_brec.p, pk.brec.data(), pk.brec.size() * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(g->d_btiles.p, pk.btiles.data(), pk.btiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, st));
+      dg.bcoef = g->d_bcoef.p;
+      dg.brec = g->d_brec.p;
+      dg.btiles = g->d_btiles.p;
+      dg.n_brec = (uint32_t)pk.brec.size();
+      dg.n_btiles = (uint32_t)pk.btiles.size();
+      dg.blk_slots = pk.blk_slots;
+    }
   }
   CK(cudaStreamSynchronize(st));
   return ASG_OK;
@@ -220,6 +248,9 @@ int repack(asg_grid *g) {
   rc = device_upload(g, pk);
   if (rc != ASG_OK) return rc;
   g->slot_of_node.swap(pk.slot_of_node);
+  g->bslot_of_node.swap(pk.bslot_of_node);
+  g->blk_ok = pk.canonical && pk.blk_ok;
+  g->blk_why = pk.blk_why;
   g->uploaded = true;
   asg_grid_info_t &I = g->info;
   const int64_t gen = I.generation + 1;
@@ -239,6 +270,10 @@ int repack(asg_grid *g) {
                              g->d_sw_depth.bytes());
   I.generation = gen;
   I.regular = pk.regular ? 1 : 0;
+  I.block = g->blk_ok ? 1 : 0;
+  I.block_slots = g->blk_ok ? (int64_t)pk.bcoef.size() - 2 : 0;
+  I.block_records = g->blk_ok ? (int64_t)pk.brec.size() : 0;
+  if (g->blk_ok) I.device_bytes += (int64_t)(g->d_bcoef.bytes() + g->d_brec.bytes() + g->d_btiles.bytes());
   return ASG_OK;
 }
 
@@ -264,15 +299,48 @@ int rem_of(int64_t max_depth) {
   return (int)std::min<int64_t>(max_depth - 1, INT_MAX / 2);  // depth <= L  <=>  sum(l-1) <= L-1
 }
 
-cudaError_t run_eval(asg_grid *g, const EvalArgs &a, cudaStream_t st) {
+// minimum batch for which the BLOCK walk orders its points by cell key first (ASG_SORT_POINTS=0 disables,
+// =<n> sets the threshold)
+int64_t sort_threshold() {
+  static const int64_t thr = [] {
+    const char *e = getenv("ASG_SORT_POINTS");
+    if (!e) return (int64_t)1 << 20;
+    const long long v = atoll(e);
+    return v <= 0 ? INT64_MAX : (int64_t)v;
+  }();
+  return thr;
+}
+
+int run_eval(asg_grid *g, const EvalArgs &a_in, cudaStream_t st, int slot = 0) {
   int64_t l = 0;
   cudaError_t e;
+  EvalArgs a = a_in;
   if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(g->dg, a, st, &l);
+  else if (g->walk() == 3) {
+    bool sorted = false;
+    if (a.M >= sort_threshold() && a.M < ((int64_t)1 << 31)) {
+      const size_t tb = sort_points_temp_bytes(a.M);
+      if (int rc = g->s_key[slot].reserve((size_t)a.M)) return rc;
+      if (int rc = g->s_key2[slot].reserve((size_t)a.M)) return rc;
+      if (int rc = g->s_idx[slot].reserve((size_t)a.M)) return rc;
+      if (int rc = g->s_perm[slot].reserve((size_t)a.M)) return rc;
+      if (int rc = g->s_sorttmp[slot].reserve(tb)) return rc;
+      if (!g->sort_ev[slot]) CK(cudaEventCreateWithFlags(&g->sort_ev[slot], cudaEventDisableTiming));
+      else CK(cudaStreamWaitEvent(st, g->sort_ev[slot], 0));  // an earlier launch on another stream may still read the scratch
+      CK(sort_points(g->dg, a.X, a.M, a.sp, a.sd, g->s_key[slot].p, g->s_key2[slot].p, g->s_idx[slot].p, g->s_perm[slot].p,
+                     g->s_sorttmp[slot].p, tb, st, &l));
+      a.perm = g->s_perm[slot].p;
+      sorted = true;
+    }
+    e = launch_eval_block(g->dg, a, st, &l);
+    if (sorted && e == cudaSuccess) CK(cudaEventRecord(g->sort_ev[slot], st));
+  }
   else if (g->walk() == 0) e = launch_eval_stream(g->dg, a, st, &l);
   else if (g->walk() == 1) e = launch_eval_rsg(g->dg, g->rp, a, st, &l);
   else e = launch_eval_subspace(g->dg, a, st, &l);
   bump(l);
-  return e;
+  CK(e);
+  return ASG_OK;
 }
 
 // Stage rows [m0, m0+cnt) of a strided host matrix into a dense device block and return the device
@@ -334,7 +402,7 @@ int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim,
       a.fvals = g->s_f[slot].p;
     }
     a.out = g->s_out[slot].p;
-    CK(run_eval(g, a, st));
+    if (int rc = run_eval(g, a, st, slot)) return rc;
     CK(cudaMemcpyAsync(out + m0, g->s_out[slot].p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(ctx.pipe[0]));
@@ -457,9 +525,13 @@ int32_t asg_grid_destroy(asg_grid *g) {
     std::lock_guard<std::recursive_mutex> lk(g->mu);
     if (ctx.ready) {
       cudaSetDevice(ctx.device);
-      g->d_rec.release(); g->d_grp.release(); g->d_tiles.release(); g->d_coef.release(); g->d_sw_coef.release(); g->d_orig.release(); g->d_horig.release();
+      g->d_rec.release(); g->d_grp.release(); g->d_tiles.release(); g->d_bcoef.release(); g->d_brec.release(); g->d_btiles.release(); g->d_coef.release(); g->d_sw_coef.release(); g->d_orig.release(); g->d_horig.release();
       g->d_sw_depth.release(); g->d_hent.release(); g->d_sw.release(); g->d_sw_low.release();
       for (int s = 0; s < 2; ++s) { g->s_X[s].release(); g->s_out[s].release(); g->s_f[s].release(); }
+      for (int s = 0; s < 2; ++s) {
+        g->s_key[s].release(); g->s_key2[s].release(); g->s_idx[s].release(); g->s_perm[s].release(); g->s_sorttmp[s].release();
+        if (g->sort_ev[s]) cudaEventDestroy(g->sort_ev[s]);
+      }
       g->s_i64a.release(); g->s_i64b.release(); g->s_tmp.release(); g->s_tmp2.release(); g->s_flag.release();
     }
   }
@@ -535,6 +607,12 @@ static int scatter_coefs_locked(asg_grid *g, int64_t n, const int64_t *idx, int6
     CK(cudaMemcpyAsync(g->s_i64b.p, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
     if (any_dense) CK(launch_scatter_f64(g->d_coef.p, g->s_i64b.p, dsrc, n, st, &l));
     if (any_hash) CK(launch_scatter_hash(g->d_hent.p, g->s_i64b.p, dsrc, n, st, &l));
+    if (g->blk_ok) {  // the BLOCK layout holds its own copy of the coefficients
+      for (int64_t k = 0; k < n; ++k) slots[(size_t)k] = g->bslot_of_node[(size_t)nodes[(size_t)k]];
+      CK(cudaStreamSynchronize(st));  // s_i64b is about to be overwritten
+      CK(cudaMemcpyAsync(g->s_i64b.p, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+      CK(launch_scatter_f64(g->d_bcoef.p, g->s_i64b.p, dsrc, n, st, &l));
+    }
   }
   bump(l);
   CK(cudaStreamSynchronize(st));
@@ -591,10 +669,11 @@ int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info) {
 int32_t asg_grid_set_path(asg_grid *g, int32_t path) {
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  if (path != ASG_PATH_AUTO && path != ASG_PATH_SWEEP && path != ASG_PATH_SUBSPACE && path != ASG_PATH_TRIE)
-    return set_err(ASG_EINVAL, "bad path");
-  if ((path == ASG_PATH_SUBSPACE || path == ASG_PATH_TRIE) && g->uploaded && !(g->canonical && g->finite))
+  if (path < ASG_PATH_AUTO || path > ASG_PATH_BLOCK) return set_err(ASG_EINVAL, "bad path");
+  if (path >= ASG_PATH_SUBSPACE && g->uploaded && !(g->canonical && g->finite))
     return set_err(ASG_EUNSUPPORTED, "grid is not canonical (" + g->why + "): only the sweep engine applies");
+  if (path == ASG_PATH_BLOCK && g->uploaded && !(g->blk_ok && block_kernel_fits(g->dg)))
+    return set_err(ASG_EUNSUPPORTED, "grid has no BLOCK layout (" + g->blk_why + ")");
   g->forced_path = path;
   return ASG_OK;
 }
@@ -623,7 +702,7 @@ int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, in
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), nullptr, dout};
   CK(cudaEventRecord(ctx.ev0, st));
-  CK(run_eval(g, a, st));
+  if (int rc = run_eval(g, a, st)) return rc;
   CK(cudaEventRecord(ctx.ev1, st));
   ctx.last_timed = true;
   return ASG_OK;
@@ -638,7 +717,7 @@ int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp,
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), dfvals, dalpha};
   CK(cudaEventRecord(ctx.ev0, st));
-  CK(run_eval(g, a, st));
+  if (int rc = run_eval(g, a, st)) return rc;
   CK(cudaEventRecord(ctx.ev1, st));
   ctx.last_timed = true;
   return ASG_OK;
@@ -777,7 +856,7 @@ int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const doub
   if (int rc = g->s_out[0].reserve((size_t)n)) return rc;
   CK(cudaMemcpyAsync(g->s_f[0].p, fvals, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   EvalArgs a{g->s_tmp.p, n, D, 1, rem_of(max_depth), g->s_f[0].p, g->s_out[0].p};
-  CK(run_eval(g, a, st));
+  if (int rc = run_eval(g, a, st)) return rc;
   CK(cudaMemcpyAsync(alpha, g->s_out[0].p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (store) {
@@ -940,7 +1019,11 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->coef_slots = (int64_t)pk.coef.size() - pk.coef_pad;
   info->hash_slots = (int64_t)pk.hent.size();
   info->regular = pk.regular ? 1 : 0;
+  info->block = (pk.canonical && pk.blk_ok) ? 1 : 0;
+  info->block_slots = info->block ? (int64_t)pk.bcoef.size() - 2 : 0;
+  info->block_records = info->block ? (int64_t)pk.brec.size() : 0;
   if (!pk.canonical) t_err = pk.why;
+  else if (!pk.blk_ok) t_err = "no BLOCK layout: " + pk.blk_why;
   return ASG_OK;
 }
 

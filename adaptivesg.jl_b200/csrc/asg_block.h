@@ -1,0 +1,84 @@
+// asg_block.h -- BLOCK layout of the subspace engine (asg_kernels_block.cu, asg_pack.cpp).
+//
+// The evaluation  G(x) = sum_n c_n prod_d phi(x01_d; l_nd, i_nd)  (src/class.jl:629-643) visits one
+// supporting node per subspace (level vector). The level vectors form a trie over the dimensions; the
+// cost of a walk is (nodes of the trie at depth k) x (instructions per node at depth k), and on
+// regular grids the three deepest dimensions hold 95 % of the trie. The BLOCK layout therefore cuts the
+// dimensions into a PREFIX (dimensions 0..D-4, data driven, one 16-byte record per prefix level
+// vector) and a SUFFIX (dimensions A = D-3, B = D-2, C = D-1) that is a complete regular sparse grid
+// of budget r = max sum(l-1) under its prefix. The suffix walk is compiled: the kernel is templated on
+// r, every level of A, B, C is a compile-time constant, all slot offsets below are immediates and the
+// only warp-uniform bookkeeping left is one record fetch and one switch per prefix vector.
+//
+// Storage of one record (prefix level vector p with pb position bits, suffix budget r):
+//   2^pb chunks of size3(r) doubles, chunk O = prefix position (cells of dimensions 0..D-4
+//   concatenated, dimension 0 most significant). Inside a chunk, recursively:
+//     for lA = 1..r+1:  2^b(lA) cells of A, each a 2-D block of size2(r - eA) doubles;     e = l - 1
+//       for lB = 1..r-eA+1:  2^b(lB) cells of B, each a POLE of n1(r - eA - eB) doubles;
+//         the pole holds the 1-D hierarchy of dimension C: level 1 at 0, level l >= 2 at
+//         off1(l) + cell  (off1 = 1, 3, 5, 9, 17, 33, 65)
+//   slot = cbase + O*size3(r) + offA(lA, r) + cA*size2(r-eA) + offB(lB, r-eA) + cB*n1(r-eA-eB) + off1(lC) + cC
+// Nodes that the grid does not hold (level caps, adapt! output) are stored as 0.0; a grid takes the
+// BLOCK layout only while that padding stays below the number of real nodes.
+//
+// A record whose chunks exceed a shared-memory tile is split along A into S2 records, one per level lA
+// (lA is applied as a data-driven stage, the 2-D suffix is compiled). Each S2 record has its own storage:
+// 2^(pb + b(lA)) 2-D blocks of size2(r - eA) doubles, block number = (O << b(lA)) | cA.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ASG_HD __host__ __device__
+#else
+#define ASG_HD
+#endif
+
+namespace asg {
+
+constexpr int kBlkMaxBudget = 7;     // suffix budget r <= 7  <=>  suffix levels <= 8 (register tables)
+constexpr int kBlkTileCoefs = 3072;  // doubles per shared-memory coefficient tile (24 KB)
+constexpr int kBlkTileRecs = 256;    // records per tile (4 KB)
+constexpr int kBlkMaxSlots = 8;      // saved prefix products: slots 0..7 (slot s = s non-trivial prefix dims)
+
+ASG_HD constexpr int blk_bits(int l) { return l == 1 ? 0 : (l == 2 ? 1 : l - 2); }
+// nodes of the 1-D hierarchy with levels 1..r+1: 1, 3, 5, 9, 17, 33, 65, 129
+ASG_HD constexpr uint32_t blk_n1(int r) { return r < 0 ? 0u : (r == 0 ? 1u : (1u << r) + 1u); }
+// offset of level l inside a pole: 0, 1, 3, 5, 9, ...
+ASG_HD constexpr uint32_t blk_off1(int l) { return l == 1 ? 0u : blk_n1(l - 2); }
+ASG_HD constexpr uint32_t blk_offB(int lB, int rA) {  // 2-D block of budget rA: start of level lB of dimension B
+  uint32_t s = 0;
+  for (int l = 1; l < lB; ++l) s += (1u << blk_bits(l)) * blk_n1(rA - (l - 1));
+  return s;
+}
+ASG_HD constexpr uint32_t blk_size2(int r) { return r < 0 ? 0u : blk_offB(r + 2, r); }  // 1, 5, 13, 29, 65, 145, 321, 705
+ASG_HD constexpr uint32_t blk_offA(int lA, int r) {  // chunk of budget r: start of level lA of dimension A
+  uint32_t s = 0;
+  for (int l = 1; l < lA; ++l) s += (1u << blk_bits(l)) * blk_size2(r - (l - 1));
+  return s;
+}
+ASG_HD constexpr uint32_t blk_size3(int r) { return r < 0 ? 0u : blk_offA(r + 2, r); }  // 1, 7, 25, 69, 177, 441, 1073, 2561
+static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "suffix block sizes");
+
+// One 16-byte record per prefix level vector, in lexicographic (depth-first) order. Every record but
+// the first applies exactly ONE stage: the level of its last non-trivial prefix dimension k0; its
+// input is the prefix product / position saved by the record that has level 1 there (stack slot =
+// number of non-trivial dimensions before k0).
+struct __align__(16) BlockRec {
+  uint32_t cbase;  // first coefficient slot of the record (chunk 0)
+  uint32_t meta;   // see kBr*
+  uint32_t s_hi;   // stage: high word of the double 2^(l-1); 0 for the root record (phi = 1)
+  uint32_t used;   // sum(l-1) over the prefix (S2: including dimension A): depth mask
+};
+constexpr uint32_t kBrNone = 15u;        // meta bits 0..3: suffix budget r, or kBrNone = stage only (no nodes)
+constexpr int kBrSlotShift = 4;          // bits 4..7: stack slot to restart from
+constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
+constexpr uint32_t kBrS2 = 1u << 9;      // 2-D suffix (dimension A is this record's stage or at level 1)
+constexpr int kBrDimShift = 12;          // bits 12..15: stage dimension k0
+constexpr int kBrBitsShift = 16;         // bits 16..21: cell bits b of the stage level
+constexpr uint32_t kBrOdd = 1u << 24;    // stage level > 2 (index = 2*cell + 1)
+
+struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)
+  uint32_t r0, r1, c0, c1;
+};
+
+}  // namespace asg

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "asg_cuda.h"
+#include "asg_block.h"
 
 namespace asg {
 
@@ -96,6 +97,12 @@ struct DeviceGrid {
   const GroupRec *grp;              // flat group stream
   const StreamTile *tiles;
   uint32_t n_grp, n_tiles;
+  // BLOCK layout (asg_block.h): present when the grid is (nearly) regular in its last three dimensions
+  const double *bcoef;
+  const BlockRec *brec;
+  const BlockTile *btiles;
+  uint32_t n_brec, n_btiles;
+  int blk_slots;                    // saved prefix slots the walk needs (<= kBlkMaxSlots)
   // sweep engine (caller's node order)
   int64_t N;
   const SweepDim *sw;       // [N][D]
@@ -133,6 +140,14 @@ struct PackResult {
   std::vector<StreamTile> tiles;
   bool regular = false;               // node set is exactly a regular sparse grid: RsgParams valid
   RsgParams rp{};
+  // BLOCK layout (asg_block.h)
+  bool blk_ok = false;
+  std::string blk_why;                // why the grid does not take the BLOCK layout
+  std::vector<double> bcoef;          // + 2 zero slots at the end (tile copies are 16-byte granular)
+  std::vector<BlockRec> brec;
+  std::vector<BlockTile> btiles;
+  std::vector<int64_t> bslot_of_node;
+  int blk_slots = 0;
   // sweep engine
   std::vector<SweepDim> sw;
   std::vector<uint64_t> sw_low;
@@ -144,6 +159,14 @@ struct PackResult {
 int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, const double *coefs,
               PackResult &out, std::string &err);
 
+// BLOCK layout of a canonical grid (asg_pack_block.cpp). lv: N x D level bytes, cells: N x D cell numbers,
+// perm: nodes sorted by level vector. Fills the blk_* members; blk_ok = false (and blk_why) if the grid
+// does not qualify. selfcheck: walk the records on the host at a few points and compare with the direct sum.
+int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm, const double *coefs,
+                bool selfcheck, PackResult &out, std::string &err);
+// host model of the BLOCK walk of asg_kernels_block.cu for one unit-cube point (packer self-check, tests)
+double block_walk_host(int D, const PackResult &pk, const double *x01, int rem);
+
 // ---- kernel launchers (asg_kernels_*.cu) -------------------------------------------------------
 struct EvalArgs {
   const double *X;   // device
@@ -151,6 +174,7 @@ struct EvalArgs {
   int rem;             // depth budget: sum(l-1) <= rem  (INT_MAX/2: no mask)
   const double *fvals; // optional: out = fvals - G
   double *out;
+  const uint32_t *perm = nullptr;  // optional: thread j handles point perm[j] (points pre-sorted by cell key)
 };
 struct BasisArgs {
   const double *X;
@@ -168,6 +192,13 @@ struct BasisArgs {
 
 cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+bool block_kernel_fits(const DeviceGrid &g);  // shared memory of the BLOCK walk fits an SM for this grid
+// bit-interleaved cell-key ordering of the query points (asg_sort.cu): perm_out[j] = j-th point in key order
+size_t sort_points_temp_bytes(int64_t M);
+cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t sp, int64_t sd, uint32_t *keys,
+                        uint32_t *keys_alt, uint32_t *idx, uint32_t *perm_out, void *temp, size_t temp_bytes,
+                        cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);

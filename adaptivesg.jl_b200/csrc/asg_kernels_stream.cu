@@ -42,34 +42,6 @@ struct __align__(16) StreamSmem {
   // CTA: double xs[D][R][threads]; uint32_t qs[D][R][threads]  (read only at non-trivial stages)
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // producer side (one thread): start the copies of tile t into buffer `buf`
 __device__ __forceinline__ void issue_tile(const DeviceGrid &g, StreamSmem &sm, uint32_t t, int buf) {
   const StreamTile tl = g.tiles[t];
@@ -104,11 +76,6 @@ struct StreamPoints {
   double phA[R][kLeafTable + 1];   // dimension D-2: hat of level l   (SUPER records)
   uint32_t ceA[R][kLeafTable + 1]; // dimension D-2: cell of level l
 };
-
-// keep a table entry in its register: without this ptxas re-derives cells from the coordinate
-// (DMUL + F2I + SEL per use) to save registers, which costs far more issue slots than it saves
-__device__ __forceinline__ void pin_u32(uint32_t &v) { asm volatile("" : "+r"(v)); }
-__device__ __forceinline__ void pin_f64(double &v) { asm volatile("" : "+d"(v)); }
 
 template <int D, int R, int V>
 __device__ __forceinline__ bool stream_load_point(const DeviceGrid &g, const double *X, int64_t m, int64_t sp,

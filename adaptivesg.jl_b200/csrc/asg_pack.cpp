@@ -15,6 +15,7 @@
 //      output) as a small open-addressing hash table keyed by the position.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -45,7 +46,8 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
 
   std::vector<uint8_t> lv;   // N x D level bytes (canonical path only)
   std::vector<uint32_t> pos; // position inside the subspace
-  if (canonical) { lv.resize((size_t)N * D); pos.resize((size_t)N); }
+  std::vector<uint32_t> cells;  // N x D cell numbers (BLOCK layout)
+  if (canonical) { lv.resize((size_t)N * D); pos.resize((size_t)N); cells.resize((size_t)N * D); }
 
   int max_level = 0;
   int64_t max_depth = 0;
@@ -85,6 +87,7 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
         else p |= cell << tb;
         tb += b;
         lv[(size_t)n * D + d] = (uint8_t)l;
+        cells[(size_t)n * D + d] = (uint32_t)cell;
       }
     }
     const int64_t depth = dsum - D + 1;
@@ -376,6 +379,11 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
       out.coef_pad = 2;
       out.coef.resize(out.coef.size() + 2, 0.0);  // tiles round their end up to an even slot
       out.orig.resize(out.orig.size() + 2, -1);
+    }
+    if (canonical) {
+      static const bool force_check = getenv("ASG_PACK_SELFCHECK") != nullptr;
+      const int rc = pack_blocks(D, N, lv.data(), cells.data(), perm.data(), coefs, force_check || N <= 50000, out, err);
+      if (rc != ASG_OK) return rc;
     }
     if (canonical) {
       for (int k = 0; k < D; ++k) {

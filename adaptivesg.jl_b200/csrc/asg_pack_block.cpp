@@ -1,0 +1,350 @@
+// asg_pack_block.cpp -- host-side construction of the BLOCK layout (asg_block.h) of a canonical grid,
+// and a host model of the walk the kernel performs over it (used as the packer's self-check).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+
+#include "asg_internal.h"
+
+namespace asg {
+
+namespace {
+
+struct PrefixInfo {
+  int r = -1;           // suffix budget: max sum(l-1) over dimensions A, B, C of the nodes under this prefix
+  int pb = 0;           // position bits of the prefix
+  int used = 0;         // sum(l-1) of the prefix
+  int nt = 0;           // non-trivial dimensions (level > 1)
+  int k0 = 0;           // last non-trivial dimension
+  bool parent_of = false;  // some other prefix restarts from this one
+  bool split = false;   // S2 records (one per level of A)
+  uint32_t cbase = 0;   // S3: first slot; S2: see cbaseA
+  uint32_t cbaseA[kBlkMaxBudget + 1] = {0};  // S2: first slot of level lA = 1..r+1
+};
+
+using Key = std::vector<uint8_t>;
+
+Key parent_of(const Key &p) {
+  Key q = p;
+  for (int k = (int)q.size() - 1; k >= 0; --k)
+    if (q[(size_t)k] > 1) { q[(size_t)k] = 1; break; }
+  return q;
+}
+
+inline double hat_host(double x, int l, uint32_t cell) {  // phi of the supporting node, as the kernel forms it
+  if (l == 1) return 1.0;
+  const uint32_t i = 2u * cell + (l > 2 ? 1u : 0u);
+  const double t = std::fma(x, std::ldexp(1.0, l - 1), -(double)i);
+  return 1.0 - std::fabs(t);
+}
+inline uint32_t cell_host(double x, int l) {
+  const int b = blk_bits(l);
+  const uint32_t c = (uint32_t)(x * std::ldexp(1.0, b));
+  return std::min(c, (1u << b) - 1u);
+}
+
+}  // namespace
+
+int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm, const double *coefs,
+                bool selfcheck, PackResult &out, std::string &err) {
+  out.blk_ok = false;
+  out.blk_why.clear();
+  out.bcoef.clear(); out.brec.clear(); out.btiles.clear(); out.bslot_of_node.clear();
+  auto no = [&](const char *w) { out.blk_why = w; return ASG_OK; };
+  if (D < 4) return no("D < 4");
+  if (D - 3 > 15) return no("D > 18");
+  if (N <= 0) return no("empty grid");
+  const int K = D - 3;  // prefix dimensions 0..K-1; A = K, B = K+1, C = K+2
+
+  // 1. prefix level vectors and their suffix budgets
+  std::map<Key, PrefixInfo> pre;
+  {
+    Key cur;
+    PrefixInfo *pi = nullptr;
+    for (int64_t k = 0; k < N; ++k) {
+      const uint8_t *L = lv + (size_t)perm[k] * D;
+      if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
+        cur.assign(L, L + K);
+        pi = &pre[cur];
+      }
+      const int eS = (L[K] - 1) + (L[K + 1] - 1) + (L[K + 2] - 1);
+      if (eS > kBlkMaxBudget) return no("suffix budget > 7");
+      pi->r = std::max(pi->r, eS);
+    }
+  }
+  // 2. closure under "reset the last non-trivial dimension": the records a walk restarts from must exist
+  {
+    std::vector<Key> todo;
+    for (auto &kv : pre) todo.push_back(kv.first);
+    while (!todo.empty()) {
+      Key p = todo.back();
+      todo.pop_back();
+      bool triv = true;
+      for (uint8_t l : p) triv = triv && l == 1;
+      if (triv) continue;
+      Key q = parent_of(p);
+      auto it = pre.find(q);
+      if (it == pre.end()) {
+        pre[q] = PrefixInfo();
+        todo.push_back(q);
+        it = pre.find(q);
+      }
+      it->second.parent_of = true;
+    }
+    if (pre.find(Key((size_t)K, 1)) == pre.end()) pre[Key((size_t)K, 1)] = PrefixInfo();
+  }
+  // 3. geometry, storage
+  uint64_t total = 0;
+  int max_slot = 0;
+  const uint64_t cap = (uint64_t)kBlkTileCoefs - 2;  // a tile window is aligned down / up to even slots
+  for (auto &kv : pre) {
+    const Key &p = kv.first;
+    PrefixInfo &I = kv.second;
+    I.pb = I.used = I.nt = 0;
+    I.k0 = 0;
+    for (int d = 0; d < K; ++d) {
+      const int l = p[(size_t)d];
+      if (l > 1) { I.nt++; I.k0 = d; }
+      I.pb += blk_bits(l);
+      I.used += l - 1;
+    }
+    if (I.pb > 24) return no("prefix position needs more than 24 bits");
+    if (I.r >= 0) {
+      const uint64_t s3 = ((uint64_t)blk_size3(I.r)) << I.pb;
+      if (s3 <= cap) {
+        I.cbase = (uint32_t)total;
+        total += s3;
+      } else {
+        I.split = true;
+        for (int lA = 1; lA <= I.r + 1; ++lA) {
+          const uint64_t s2 = ((uint64_t)blk_size2(I.r - (lA - 1))) << (I.pb + blk_bits(lA));
+          if (s2 > cap) return no("a suffix block exceeds the shared-memory tile");
+          I.cbaseA[lA - 1] = (uint32_t)total;
+          total += s2;
+        }
+        if (I.r >= 1) I.parent_of = true;  // its own lA >= 2 records restart from it
+      }
+      if (total > 0x7fffffffull) return no("too many block slots");
+    }
+    if (I.parent_of) max_slot = std::max(max_slot, I.nt);
+  }
+  if (max_slot >= kBlkMaxSlots) return no("more than 7 non-trivial prefix dimensions on a path");
+  if (total > 2ull * (uint64_t)N + 4096ull) return no("padding exceeds the number of nodes");
+  out.blk_slots = max_slot + 1;
+  out.bcoef.assign((size_t)total + 2, 0.0);
+  out.bslot_of_node.assign((size_t)N, -1);
+  std::vector<double> synth;  // self-check of a coefficient-free pack (asg_pack_info): use synthetic values
+  if (selfcheck && !coefs) {
+    synth.resize((size_t)N);
+    for (int64_t n = 0; n < N; ++n) synth[(size_t)n] = std::sin(1.0 + 0.37 * (double)n) + 0.25;
+    coefs = synth.data();
+  }
+  // 4. node slots
+  {
+    Key cur;
+    const PrefixInfo *pi = nullptr;
+    for (int64_t k = 0; k < N; ++k) {
+      const int64_t n = perm[k];
+      const uint8_t *L = lv + (size_t)n * D;
+      const uint32_t *C = cells + (size_t)n * D;
+      if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
+        cur.assign(L, L + K);
+        pi = &pre[cur];
+      }
+      uint64_t O = 0;
+      for (int d = 0; d < K; ++d) O = (O << blk_bits(L[d])) | C[d];
+      const int lA = L[K], lB = L[K + 1], lC = L[K + 2];
+      const int rA = pi->r - (lA - 1), rB = rA - (lB - 1);
+      const uint64_t in2 = (uint64_t)blk_offB(lB, rA) + (uint64_t)C[K + 1] * blk_n1(rB) + blk_off1(lC) + C[K + 2];
+      uint64_t slot;
+      if (!pi->split) {
+        slot = pi->cbase + O * blk_size3(pi->r) + blk_offA(lA, pi->r) + (uint64_t)C[K] * blk_size2(rA) + in2;
+      } else {
+        const uint64_t O2 = (O << blk_bits(lA)) | C[K];
+        slot = pi->cbaseA[lA - 1] + O2 * blk_size2(rA) + in2;
+      }
+      if (slot >= total || out.bslot_of_node[(size_t)n] != -1) {  // duplicates were rejected before: packer bug
+        err = "internal error: block slot out of range or assigned twice";
+        return ASG_ESTATE;
+      }
+      out.bslot_of_node[(size_t)n] = (int64_t)slot;
+      out.bcoef[(size_t)slot] = coefs ? coefs[n] : 0.0;
+    }
+  }
+  // 5. records in lexicographic order + the slot span each one reads
+  std::vector<uint32_t> lo, hi;
+  for (auto &kv : pre) {
+    const Key &p = kv.first;
+    const PrefixInfo &I = kv.second;
+    BlockRec q{};
+    const int l0 = I.nt ? p[(size_t)I.k0] : 1;
+    q.s_hi = I.nt ? (uint32_t)(1023 + l0 - 1) << 20 : 0u;
+    q.used = (uint32_t)I.used;
+    q.meta = ((uint32_t)(I.nt ? I.nt - 1 : 0) << kBrSlotShift) | ((uint32_t)I.k0 << kBrDimShift) |
+             ((uint32_t)blk_bits(l0) << kBrBitsShift) | (l0 > 2 ? kBrOdd : 0u) |
+             ((I.parent_of && I.nt) ? kBrSave : 0u);
+    if (I.r < 0) {
+      q.meta |= kBrNone;
+      q.cbase = 0;
+      out.brec.push_back(q);
+      lo.push_back(0); hi.push_back(0);
+    } else if (!I.split) {
+      q.meta |= (uint32_t)I.r;
+      q.cbase = I.cbase;
+      out.brec.push_back(q);
+      lo.push_back(I.cbase);
+      hi.push_back(I.cbase + (blk_size3(I.r) << I.pb));
+    } else {
+      for (int lA = 1; lA <= I.r + 1; ++lA) {
+        BlockRec s = q;
+        const int rA = I.r - (lA - 1);
+        s.cbase = I.cbaseA[lA - 1];
+        if (lA == 1) {
+          s.meta |= (uint32_t)rA | kBrS2;
+          // root prefix: nothing to save for, the lA >= 2 records restart from slot 0 as well
+        } else {  // stage = level lA of dimension A, restart from the prefix product this prefix saved
+          s.meta = (uint32_t)rA | kBrS2 | ((uint32_t)I.nt << kBrSlotShift) | ((uint32_t)K << kBrDimShift) |
+                   ((uint32_t)blk_bits(lA) << kBrBitsShift) | (lA > 2 ? kBrOdd : 0u);
+          s.s_hi = (uint32_t)(1023 + lA - 1) << 20;
+          s.used = (uint32_t)(I.used + lA - 1);
+        }
+        out.brec.push_back(s);
+        lo.push_back(s.cbase);
+        hi.push_back(s.cbase + (blk_size2(rA) << (I.pb + blk_bits(lA))));
+      }
+    }
+  }
+  // 6. tiles: consecutive records whose spans fit one coefficient buffer
+  {
+    size_t j = 0;
+    const size_t nrec = out.brec.size();
+    while (j < nrec) {
+      BlockTile t{(uint32_t)j, (uint32_t)j, 0u, 0u};
+      bool have = false;
+      while (j < nrec && (int)(j - t.r0) < kBlkTileRecs) {
+        if (hi[j] > lo[j]) {
+          const uint32_t a = lo[j] & ~1u, b = (hi[j] + 1u) & ~1u;
+          if (!have) {
+            t.c0 = a; t.c1 = b; have = true;
+          } else {
+            const uint32_t na = std::min(t.c0, a), nb = std::max(t.c1, b);
+            if (nb - na > (uint32_t)kBlkTileCoefs) break;
+            t.c0 = na; t.c1 = nb;
+          }
+        }
+        ++j;
+      }
+      t.r1 = (uint32_t)j;
+      out.btiles.push_back(t);
+    }
+    for (const BlockTile &t : out.btiles) {
+      if (t.c1 - t.c0 > (uint32_t)kBlkTileCoefs || t.r1 - t.r0 > (uint32_t)kBlkTileRecs || (t.c0 & 1u) || (t.c1 & 1u) ||
+          (uint64_t)t.c1 > out.bcoef.size()) {
+        err = "internal error: block tile out of bounds";
+        return ASG_ESTATE;
+      }
+      for (uint32_t r = t.r0; r < t.r1; ++r)
+        if (hi[r] > lo[r] && (lo[r] < t.c0 || hi[r] > t.c1)) {
+          err = "internal error: block record outside its tile";
+          return ASG_ESTATE;
+        }
+    }
+  }
+  out.blk_ok = true;
+  // 7. self-check: the walk over the records must reproduce the direct sum over the nodes
+  if (selfcheck) {
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() {
+      s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+      return (double)(s >> 11) * (1.0 / 9007199254740992.0);
+    };
+    std::vector<double> x((size_t)D);
+    for (int trial = 0; trial < 6; ++trial) {
+      for (int d = 0; d < D; ++d) x[(size_t)d] = trial == 0 ? 1.0 : (trial == 1 ? 0.0 : (trial == 2 ? 0.5 : rnd()));
+      for (int rem : {INT32_MAX / 2, 3}) {
+        long double want = 0.0L, scale = 0.0L;
+        for (int64_t n = 0; n < N; ++n) {
+          const uint8_t *L = lv + (size_t)n * D;
+          int e = 0;
+          for (int d = 0; d < D; ++d) e += L[d] - 1;
+          if (e > rem) continue;
+          double v = coefs ? coefs[n] : 0.0;
+          for (int d = 0; d < D && v != 0.0; ++d) {
+            const uint32_t c = cell_host(x[(size_t)d], L[d]);
+            v *= (c == cells[(size_t)n * D + d]) ? hat_host(x[(size_t)d], L[d], c) : 0.0;
+          }
+          want += v;
+          scale += std::fabs(v);
+        }
+        const double got = block_walk_host(D, out, x.data(), rem);
+        if (!(std::fabs((double)(got - want)) <= 1e-13 * std::max<double>(1.0, (double)scale))) {
+          err = "internal error: BLOCK walk self-check failed (got " + std::to_string(got) + ", want " +
+                std::to_string((double)want) + ")";
+          out.blk_ok = false;
+          return ASG_ESTATE;
+        }
+      }
+    }
+  }
+  if (!synth.empty()) std::fill(out.bcoef.begin(), out.bcoef.end(), 0.0);
+  return ASG_OK;
+}
+
+// The walk of asg_kernels_block.cu, one point, plain loops: records in order, one stage per record from
+// the saved slot, then the regular suffix of budget min(r, rem - used) with the layout of asg_block.h.
+double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) {
+  const int K = D - 3;
+  double P[kBlkMaxSlots + 2];
+  uint64_t O[kBlkMaxSlots + 2];
+  P[0] = 1.0;
+  O[0] = 0;
+  double acc = 0.0;
+  const double xA = x01[K], xB = x01[K + 1], xC = x01[K + 2];
+  for (const BlockRec &q : pk.brec) {
+    if ((int)q.used > rem) continue;
+    const int slot = (int)((q.meta >> kBrSlotShift) & 15u);
+    const int k0 = (int)((q.meta >> kBrDimShift) & 15u);
+    const int b = (int)((q.meta >> kBrBitsShift) & 63u);
+    const uint32_t odd = (q.meta & kBrOdd) ? 1u : 0u;
+    double s;
+    {
+      const uint64_t bits = (uint64_t)q.s_hi << 32;
+      std::memcpy(&s, &bits, 8);
+    }
+    const double x = x01[k0];
+    const uint32_t cell = std::min((uint32_t)(x * std::ldexp(1.0, b)), (1u << b) - 1u);
+    const double t = std::fma(x, s, -(double)(2u * cell + odd));
+    const double cur = P[slot] * (1.0 - std::fabs(t));
+    const uint64_t cO = (O[slot] << b) | cell;
+    if (q.meta & kBrSave) { P[slot + 1] = cur; O[slot + 1] = cO; }
+    const int rs = (int)(q.meta & 15u);
+    if (rs == (int)kBrNone) continue;
+    const int reff = std::min(rs, rem - (int)q.used);
+    const bool s2 = (q.meta & kBrS2) != 0;
+    const double *chunk = pk.bcoef.data() + q.cbase + cO * (s2 ? blk_size2(rs) : blk_size3(rs));
+    double inner3 = 0.0;
+    for (int lA = 1; lA <= (s2 ? 1 : reff + 1); ++lA) {
+      const int rA = rs - (lA - 1), reffA = reff - (lA - 1);
+      const uint32_t cA = cell_host(xA, lA);
+      const double *blk2 = s2 ? chunk : chunk + blk_offA(lA, rs) + (size_t)cA * blk_size2(rA);
+      double accA = 0.0;
+      for (int lB = 1; lB <= reffA + 1; ++lB) {
+        const int rB = rA - (lB - 1), reffB = reffA - (lB - 1);
+        const uint32_t cB = cell_host(xB, lB);
+        const double *pole = blk2 + blk_offB(lB, rA) + (size_t)cB * blk_n1(rB);
+        double inner = pole[0];
+        for (int lC = 2; lC <= reffB + 1; ++lC) {
+          const uint32_t cC = cell_host(xC, lC);
+          inner = std::fma(pole[blk_off1(lC) + cC], hat_host(xC, lC, cC), inner);
+        }
+        accA = lB == 1 ? inner : std::fma(hat_host(xB, lB, cB), inner, accA);
+      }
+      inner3 = lA == 1 ? accA : std::fma(hat_host(xA, lA, cA), accA, inner3);
+    }
+    acc = std::fma(cur, inner3, acc);
+  }
+  return acc;
+}
+
+}  // namespace asg

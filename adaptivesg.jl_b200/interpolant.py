@@ -123,7 +123,7 @@ class SparseGridInterpolant:
 
     def set_path(self, path: str = "auto"):
         code = {"auto": _capi.ASG_PATH_AUTO, "sweep": _capi.ASG_PATH_SWEEP, "subspace": _capi.ASG_PATH_SUBSPACE,
-                "trie": _capi.ASG_PATH_TRIE}[path]
+                "trie": _capi.ASG_PATH_TRIE, "stream": _capi.ASG_PATH_STREAM, "block": _capi.ASG_PATH_BLOCK}[path]
         check(_capi.load().asg_grid_set_path(self._ensure(), code))
         return self
 

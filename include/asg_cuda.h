@@ -49,6 +49,9 @@ extern "C" {
 #define ASG_PATH_SUBSPACE 2  /* subspace walk, one supporting node per subspace (record-free on     */
                              /* regular sparse grids, level-vector trie otherwise)                 */
 #define ASG_PATH_TRIE 3      /* subspace walk forced through the generic trie (tests: cross-check) */
+#define ASG_PATH_STREAM 4    /* subspace walk forced through the flat group stream (tests)         */
+#define ASG_PATH_BLOCK 5     /* subspace walk forced through the BLOCK layout; ASG_EUNSUPPORTED if */
+                             /* the grid has none (asg_grid_info().block == 0)                     */
 
 typedef struct asg_grid asg_grid;   /* opaque: device mirror of SparseGridInterpolant{D}, class.jl:281-319 */
 typedef struct asg_event asg_event; /* opaque: completion handle of an *_async call                        */
@@ -68,6 +71,9 @@ typedef struct asg_grid_info_t {
   int64_t device_bytes;    /* bytes resident in HBM for this grid                                   */
   int64_t generation;      /* bumped by every upload / append / set_coefs                           */
   int64_t regular;         /* 1: node set is exactly a regular sparse grid (record-free fast walk)  */
+  int64_t block;           /* 1: BLOCK layout present (compiled walk of the last three dimensions)  */
+  int64_t block_slots;     /* its coefficient slots incl. zero padding                              */
+  int64_t block_records;   /* its prefix records                                                    */
 } asg_grid_info_t;
 
 /* ---- context ------------------------------------------------------------------------------- */

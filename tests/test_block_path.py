@@ -1,0 +1,193 @@
+"""BLOCK layout (csrc/asg_block.h): packer checks on the CPU, parity of the compiled walk on the GPU.
+
+The BLOCK walk is the default evaluation kernel for grids that are (nearly) regular in their last three
+dimensions -- BASELINE.json configs[2] (D = 10, 652 065 nodes) among them; the flat group stream stays the
+kernel of every other canonical grid, so both are run against the oracle here on identical inputs.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_close, sinsum
+
+
+def _pack_info(asg, levels, indices):
+    gi = asg._capi.GridInfo()
+    Lv = np.ascontiguousarray(levels, dtype=np.int64)
+    Ix = np.ascontiguousarray(indices, dtype=np.int64)
+    rc = asg._capi.load().asg_pack_info(Lv.shape[1], len(Lv), Lv.ctypes.data_as(asg._capi.i64p),
+                                        Ix.ctypes.data_as(asg._capi.i64p), Lv.shape[1], 1, C.byref(gi))
+    return rc, gi.as_dict(), asg._capi.load().asg_last_error().decode()
+
+
+def test_block_layout_regular_grids(asg):
+    """asg_pack_info runs the packer's self-check (host model of the kernel's walk against the direct sum
+    over the nodes, with and without a depth mask) for every grid of at most 50 000 nodes."""
+    for D, depth, ml, nrec in [(4, 6, 6, 6), (5, 5, 5, 15), (6, 7, (6, 7, 8, 9, 10, 11), 83), (10, 5, 5, 330),
+                               (7, 4, (2, 3, 4, 4, 2, 3, 4), None), (12, 3, 3, None)]:
+        G = asg.SparseGridInterpolant(D)
+        asg.rsg(G, depth, ml)
+        rc, info, msg = _pack_info(asg, G.levels, G.indices)
+        assert rc == 0, msg
+        assert info["block"] == 1, msg
+        if nrec is not None:
+            assert info["block_slots"] == len(G)          # no padding unless level caps cut the last three dimensions
+            assert info["block_records"] == nrec          # one record per prefix level vector (dims 0..D-4)
+        else:
+            assert len(G) <= info["block_slots"] <= 2 * len(G) + 4096
+    # the benchmark grid: C(14, 7) = 3432 prefix vectors, no padding
+    os.environ["ASG_PACK_SELFCHECK"] = "1"
+    G = asg.SparseGridInterpolant(10)
+    asg.rsg(G, 8, 8)
+    rc, info, msg = _pack_info(asg, G.levels, G.indices)
+    assert rc == 0 and info["block"] == 1 and info["block_slots"] == 652065 and info["block_records"] == 3432, msg
+    # outside the layout's limits: D < 4, suffix levels > 8
+    for D, depth in [(3, 5), (4, 10)]:
+        G = asg.SparseGridInterpolant(D)
+        asg.rsg(G, depth, depth)
+        rc, info, msg = _pack_info(asg, G.levels, G.indices)
+        assert rc == 0 and info["canonical"] == 1 and info["block"] == 0 and "BLOCK" in msg
+
+
+def test_block_layout_irregular_grids(asg, oracle):
+    """node subsets (padding with zeros, virtual parent records) and an adapt! grid"""
+    rng = np.random.default_rng(77)
+    took = 0
+    for trial in range(20):
+        D = int(rng.integers(4, 9))
+        G = asg.SparseGridInterpolant(D)
+        asg.rsg(G, int(rng.integers(3, 7)), tuple(int(v) for v in rng.integers(2, 7, size=D)))
+        keep = rng.random(len(G)) < rng.choice([0.97, 0.8, 0.55])
+        keep[0] = True
+        rc, info, msg = _pack_info(asg, G.levels[keep], G.indices[keep])
+        assert rc == 0, msg                               # a failed self-check would be ASG_ESTATE
+        assert info["canonical"] == 1
+        if info["block"]:
+            took += 1
+            assert keep.sum() <= info["block_slots"] <= 2 * keep.sum() + 4096
+    assert took >= 5
+    OG = oracle.OracleGrid(4)
+    OG.train(sinsum, 5, 5)
+    OG.adapt(sinsum, 8, tol=3e-2)
+    rc, info, msg = _pack_info(asg, OG.levels, OG.indices)
+    assert rc == 0 and info["canonical"] == 1, msg
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------
+def _mirror(asg, OG):
+    G = asg.SparseGridInterpolant(OG.D, lb=OG.lb, ub=OG.ub)
+    G.levels, G.indices, G.depths = OG.levels.copy(), OG.indices.copy(), OG.depths.copy()
+    G.fvals, G.coefs = OG.fvals.copy(), OG.coefs.copy()
+    return G
+
+
+def _edge_points(D, lb, ub, rng):
+    from test_gpu_parity import _edge_points as e
+    return e(D, lb, ub, rng, 32)
+
+
+def _grids(oracle):
+    rng = np.random.default_rng(99)
+    out = []
+    for D, depth, ml, keepfrac, unit in [(4, 7, 7, 1.0, True), (10, 5, 5, 1.0, True), (6, 6, (4, 5, 6, 3, 6, 6), 1.0, False),
+                                         (5, 6, 6, 0.9, False), (7, 4, 4, 0.7, True), (4, 8, 8, 1.0, False),
+                                         (12, 3, 3, 1.0, True)]:
+        lb = np.zeros(D) if unit else -rng.random(D)
+        ub = np.ones(D) if unit else 1.0 + rng.random(D)
+        OG = oracle.OracleGrid(D, lb=lb, ub=ub)
+        OG.rsg(depth, ml)
+        if keepfrac < 1.0:
+            keep = rng.random(len(OG)) < keepfrac
+            keep[0] = True
+            OG.levels, OG.indices, OG.depths = OG.levels[keep], OG.indices[keep], OG.depths[keep]
+        OG.coefs = rng.standard_normal(len(OG.levels)) * 2.0 ** (-OG.depths.astype(float) / 2)
+        OG.fvals = np.zeros(len(OG.levels))
+        out.append(OG)
+    return out
+
+
+@pytest.mark.gpu
+def test_block_walk_parity(asg, oracle):
+    rng = np.random.default_rng(5)
+    for OG in _grids(oracle):
+        D = OG.D
+        G = _mirror(asg, OG)
+        info = G.info()
+        assert info["block"] == 1, (D, len(OG.levels))
+        X = np.vstack([OG.lb + (OG.ub - OG.lb) * rng.random((3000, D)), _edge_points(D, OG.lb, OG.ub, rng)])
+        want, sc = OG.evaluate(X, return_abssum=True)
+        L = int(rng.integers(1, int(OG.depths.max()) + 1))
+        wantm, scm = OG.evaluate(X, max_depth=L, return_abssum=True)
+        res = {}
+        for path in ("block", "stream"):
+            G.set_path(path)
+            n0 = asg.launch_count()
+            got = G.evaluate(X)
+            assert asg.launch_count() > n0
+            assert_close(got, want, sc, f"D={D} {path}")
+            outside = ~np.all((X >= OG.lb) & (X <= OG.ub), axis=1)
+            assert np.all(got[outside] == 0.0)
+            gm = G.evaluate(X, max_depth=L)
+            assert_close(gm, wantm, scm, f"D={D} {path} depth<={L}")
+            res[path] = got
+        # surplus = f - G through the same kernel; coefficient updates must reach the BLOCK copy too
+        G.set_path("block")
+        f = rng.standard_normal(len(X))
+        assert_close(G.surplus(X, f), f - want, sc + np.abs(f), f"D={D} surplus")
+        idx = rng.choice(len(OG.levels), size=min(50, len(OG.levels)), replace=False)
+        OG.coefs[idx] = rng.standard_normal(len(idx))
+        G.coefs[idx] = OG.coefs[idx]
+        lib = asg._capi.load()
+        idx64 = np.ascontiguousarray(idx, dtype=np.int64)
+        vals = np.ascontiguousarray(OG.coefs[idx])
+        asg._capi.check(lib.asg_grid_scatter_coefs(G._ensure(), len(idx64), idx64.ctypes.data_as(asg._capi.i64p),
+                                                   vals.ctypes.data_as(asg._capi.f64p)))
+        want2, sc2 = OG.evaluate(X, return_abssum=True)
+        assert_close(G.evaluate(X), want2, sc2, f"D={D} block after scatter_coefs")
+        G.set_path("stream")
+        assert_close(G.evaluate(X), want2, sc2, f"D={D} stream after scatter_coefs")
+
+
+@pytest.mark.gpu
+def test_block_walk_large_sorted_batch(asg, oracle):
+    """>= 2^20 points: two points per thread and the cell-key ordering of the points (asg_sort.cu). The
+    per-point arithmetic does not depend on the batch, so the results equal those of a small batch bit for bit."""
+    rng = np.random.default_rng(11)
+    OG = _grids(oracle)[1]                                   # D = 10, depth 5
+    G = _mirror(asg, OG)
+    G.set_path("block")
+    M = (1 << 20) + 12345
+    X = rng.random((M, 10))
+    X[::1000, 3] = 1.5                                       # some out-of-domain points
+    X[7::5000, 9] = np.nan
+    y = G.evaluate(X)
+    sel = np.concatenate([np.arange(0, 3000), np.arange(M - 3000, M)])
+    want, sc = OG.evaluate(X[sel], return_abssum=True)
+    assert_close(y[sel], want, sc, "large sorted batch")
+    assert np.array_equal(y[sel], G.evaluate(X[sel]))
+    assert np.all(y[::1000] == 0.0) and np.all(y[7::5000] == 0.0)
+    ym = G.evaluate(X, max_depth=3)
+    assert_close(ym[sel], OG.evaluate(X[sel], max_depth=3), sc, "large sorted batch, masked")
+    # column-major points (Julia's M x D matrices) take the same path
+    yf = G.evaluate(np.asfortranarray(X))
+    assert np.array_equal(y, yf, equal_nan=True)
+    G.set_path("stream")
+    ys = G.evaluate(X[sel])
+    assert_close(ys, want, sc, "stream")
+
+
+@pytest.mark.gpu
+def test_block_walk_train_cfg4(asg, oracle):
+    """train! on the D = 6 anisotropic grid of BASELINE.json configs[3] (15 089 nodes): every depth's surplus
+    step runs the masked BLOCK walk; coefficients must match the oracle's"""
+    OG = oracle.OracleGrid(6)
+    OG.train(sinsum, 7, tuple(range(6, 12)))
+    G = asg.SparseGridInterpolant(6)
+    asg.train(G, sinsum, 7, tuple(range(6, 12)))
+    assert G.info()["block"] == 1
+    assert np.array_equal(G.levels, OG.levels) and np.array_equal(G.indices, OG.indices)
+    assert np.max(np.abs(G.coefs - OG.coefs)) < 1e-13
