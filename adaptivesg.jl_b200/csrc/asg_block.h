@@ -37,7 +37,7 @@ namespace asg {
 
 constexpr int kBlkMaxBudget = 7;     // suffix budget r <= 7  <=>  suffix levels <= 8 (register tables)
 constexpr int kBlkTileCoefs = 3072;  // doubles per shared-memory coefficient tile (24 KB)
-constexpr int kBlkTileRecs = 256;    // records per tile (4 KB)
+constexpr int kBlkTileRecs = 128;    // records per tile (4 KB)
 constexpr int kBlkMaxSlots = 8;      // saved prefix products: slots 0..7 (slot s = s non-trivial prefix dims)
 
 ASG_HD constexpr int blk_bits(int l) { return l == 1 ? 0 : (l == 2 ? 1 : l - 2); }
@@ -59,23 +59,28 @@ ASG_HD constexpr uint32_t blk_offA(int lA, int r) {  // chunk of budget r: start
 ASG_HD constexpr uint32_t blk_size3(int r) { return r < 0 ? 0u : blk_offA(r + 2, r); }  // 1, 7, 25, 69, 177, 441, 1073, 2561
 static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "suffix block sizes");
 
-// One 16-byte record per prefix level vector, in lexicographic (depth-first) order. Every record but
-// the first applies exactly ONE stage: the level of its last non-trivial prefix dimension k0; its
-// input is the prefix product / position saved by the record that has level 1 there (stack slot =
-// number of non-trivial dimensions before k0).
+// One 32-byte record per prefix level vector, in lexicographic (depth-first) order, stored pre-decoded
+// (one field per word: the kernel does no shifting or masking on its critical path). Every record but
+// the first applies exactly ONE stage: the level of its last non-trivial prefix dimension k0; its input
+// is the prefix product / position saved by the record that has level 1 there (stack slot = number of
+// non-trivial dimensions before k0).
 struct __align__(16) BlockRec {
   uint32_t cbase;  // first coefficient slot of the record (chunk 0)
-  uint32_t meta;   // see kBr*
+  uint32_t sw;     // bits 0..7: kBrS3 + r | kBrS2 + r | kBrNone (compiled suffix to run); 8..15: flags; 16..31: used
+  uint32_t slot;   // stack slot to restart from
+  uint32_t k0;     // stage dimension
+  uint32_t b;      // stage: cell bits of the level
   uint32_t s_hi;   // stage: high word of the double 2^(l-1); 0 for the root record (phi = 1)
-  uint32_t used;   // sum(l-1) over the prefix (S2: including dimension A): depth mask
+  uint32_t lim;    // stage: 2^b - 1
+  uint32_t odd;    // stage: 1 if level > 2 (index = 2*cell + 1)
 };
-constexpr uint32_t kBrNone = 15u;        // meta bits 0..3: suffix budget r, or kBrNone = stage only (no nodes)
-constexpr int kBrSlotShift = 4;          // bits 4..7: stack slot to restart from
+static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words");
+constexpr uint32_t kBrS3 = 0u;    // sw = kBrS3 + r: 3-D suffix of budget r = 0..7
+constexpr uint32_t kBrS2 = 8u;    // sw = kBrS2 + r: 2-D suffix (dimension A is this record's stage or at level 1)
+constexpr uint32_t kBrNone = 16u; // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
-constexpr uint32_t kBrS2 = 1u << 9;      // 2-D suffix (dimension A is this record's stage or at level 1)
-constexpr int kBrDimShift = 12;          // bits 12..15: stage dimension k0
-constexpr int kBrBitsShift = 16;         // bits 16..21: cell bits b of the stage level
-constexpr uint32_t kBrOdd = 1u << 24;    // stage level > 2 (index = 2*cell + 1)
+constexpr uint32_t kBrSameIn = 1u << 9;  // same input slot and stage dimension as the previous record (siblings)
+constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2: including dimension A): depth mask
 
 struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)
   uint32_t r0, r1, c0, c1;

@@ -23,7 +23,7 @@
 
 namespace asg {
 
-constexpr int kBlkThreads = 512;
+constexpr int kBlkThreads = 512;  // default CTA size (ASG_BLOCK_THREADS = 384 | 512)
 constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulated in registers
 
 struct __align__(16) BlkSmem {
@@ -43,13 +43,14 @@ struct BlkPoint {
   double xA[R];                  // unit-cube coordinate of dimension D-3 (its hats are formed on the fly)
   uint32_t qA[R];                // and its 30-bit cell key
   uint32_t xsBC;                 // shared byte address of this thread's coordinate of dimension D-2 (point 0)
+  uint32_t xstride;              // bytes between consecutive points / dimensions in xs (threads * 8)
 };
 
 // coordinate of dimension D-2 (which = 0) or D-1 (which = 1) of point k, from shared memory (rare levels only)
 template <int R>
 __device__ __forceinline__ double blk_x_rare(const BlkPoint<R> &pt, int which, int k) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * kBlkThreads * 8)));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)(which * R + k) * pt.xstride));
   return v;
 }
 __device__ __forceinline__ uint32_t blk_key(double v) {  // floor(v * 2^30), clamped for v == 1 (exact)
@@ -119,7 +120,8 @@ __device__ __forceinline__ void blk_pole(const BlkPoint<R> &pt, const uint32_t (
   }
 }
 
-// 2-D block of storage budget RB at shared byte address t2[k] + IMM: levels LB.. of dimension B
+// 2-D block of storage budget RB at shared byte address t2[k] + IMM: levels LB.. of dimension B (Horner form:
+// one DFMA per pole, none for level 1)
 template <int RB, int LB, int IMM, int R, bool MASKED>
 __device__ __forceinline__ void blk_suffix2(const BlkPoint<R> &pt, const uint32_t (&t2)[R], int reff, double (&accA)[R]) {
   if constexpr (LB <= RB + 1) {
@@ -172,17 +174,73 @@ __device__ __forceinline__ void blk_suffix3(const BlkPoint<R> &pt, const uint32_
   }
 }
 
-template <int RS, bool S2, int R, bool MASKED>
-__device__ __forceinline__ void blk_record(const BlkPoint<R> &pt, const double (&cur)[R], const uint32_t (&cO)[R],
-                                           uint32_t cb, int reff, double (&acc)[R]) {
-  uint32_t t[R];
-  double v[R];
+// ---- the data-driven stage of a record ---------------------------------------------------------------
+template <int R>
+struct BlkStaged {     // a record after its stage: everything its compiled suffix needs
+  double cur[R];       // prefix product over dimensions 0..D-4 (S2: and A)
+  uint32_t t[R];       // cO * chunk bytes is formed by the suffix; here: prefix position
+  uint32_t sw;         // suffix code (kBrS3 + r, kBrS2 + r, kBrNone), flags, used
+  uint32_t cb;         // shared byte address of the record's chunk 0
+};
+template <int R>
+struct BlkRegs {       // input of the current run of sibling records, kept in registers
+  double Pin[R], xin[R];
+};
+
+// Fetch the record at shared address rbase and apply its stage: hat of the level-l node of dimension k0
+// that supports the point, on top of the prefix saved by the parent record (stack slot ra.z).
+template <int R, bool MASKED, int NT>
+__device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_t os_t, uint32_t xs_t, uint32_t tbias,
+                                          int rem, BlkRegs<R> &in, BlkStaged<R> &out) {
+  uint4 ra, rb;  // {cbase, sw, slot, k0} {b, s_hi, lim, odd}
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(rbase));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(rbase));
+  const uint32_t pa = ps_t + ra.z * (R * NT * 8u), oa = os_t + ra.z * (R * NT * 4u);
+  uint32_t Oin[R];
 #pragma unroll
-  for (int k = 0; k < R; ++k) t[k] = cO[k] * ((S2 ? blk_size2(RS) : blk_size3(RS)) * 8u) + cb;
+  for (int k = 0; k < R; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Oin[k]) : "r"(oa + k * (NT * 4u)));
+  if (!(ra.y & kBrSameIn)) {  // siblings (same parent, same stage dimension) keep these inputs in registers
+    const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      in.Pin[k] = lds_f64(pa + k * (NT * 8u));
+      in.xin[k] = lds_f64(xa + k * (NT * 8u));
+    }
+  }
+  const double s = __hiloint2double((int)rb.y, 0);                            // 2^(l-1), or 0 for the root record
+  const double s2b = __hiloint2double((int)((rb.x << 20) + 0x3ff00000u), 0);  // 2^b
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t cell = min((uint32_t)(in.xin[k] * s2b), rb.z);  // floor(x*2^b), clamped for x == 1 (exact)
+    const double tt = fma(in.xin[k], s, -u32_to_f64((cell << 1) + rb.w));  // x*2^(l-1) - i, one rounding (math.jl:347)
+    out.cur[k] = in.Pin[k] * (1.0 - fabs(tt));
+    out.t[k] = (Oin[k] << rb.x) | cell;
+  }
+  if (ra.y & kBrSave) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(pa + (R + k) * (NT * 8u)), "d"(out.cur[k]));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(oa + (R + k) * (NT * 4u)), "r"(out.t[k]));
+    }
+  }
+  out.sw = ra.y;
+  if (MASKED && (int)(ra.y >> kBrUsedShift) > rem) out.sw = (ra.y & ~0xffu) | kBrNone;  // depth mask: lies deeper
+  out.cb = ra.x * 8u + tbias;
+}
+
+// One record: the compiled suffix of the staged record. (Staging the NEXT record inside the same basic block,
+// so that ptxas interleaves the two dependency chains, was measured 5 % slower: registers.)
+template <int RS, bool S2, int R, bool MASKED>
+__device__ __forceinline__ void blk_record(const BlkPoint<R> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
+  uint32_t t[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) t[k] = st.t[k] * ((S2 ? blk_size2(RS) : blk_size3(RS)) * 8u) + st.cb;
+  const int reff = MASKED ? rem - (int)(st.sw >> kBrUsedShift) : 0;
+  double v[R];
   if constexpr (S2) blk_suffix2<RS, 1, 0, R, MASKED>(pt, t, reff, v);
   else blk_suffix3<RS, 1, R, MASKED>(pt, t, reff, v);
 #pragma unroll
-  for (int k = 0; k < R; ++k) acc[k] = fma(cur[k], v[k], acc[k]);
+  for (int k = 0; k < R; ++k) acc[k] = fma(st.cur[k], v[k], acc[k]);
 }
 
 // producer side (one thread): start the copies of tile t into buffer `buf`
@@ -197,11 +255,11 @@ __device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm,
   if (cbytes) tma_load_1d(sm.coef[buf], g.bcoef + tl.c0, cbytes, &sm.bar[buf]);
 }
 
-template <int R, bool MASKED>
-__global__ void __launch_bounds__(kBlkThreads, 1) k_eval_block(const DeviceGrid g, const EvalArgs a) {
+// registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
+template <int R, bool MASKED, int NT>
+__global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid g, const EvalArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BlkSmem &sm = *reinterpret_cast<BlkSmem *>(smem_raw);
-  constexpr int NT = kBlkThreads;
   const int D = g.D;
   const int K = D - 3;
   double *xs = reinterpret_cast<double *>(smem_raw + sizeof(BlkSmem));
@@ -209,9 +267,9 @@ __global__ void __launch_bounds__(kBlkThreads, 1) k_eval_block(const DeviceGrid 
   uint32_t *Os = reinterpret_cast<uint32_t *>(Ps + (size_t)g.blk_slots * R * NT);
   const uint32_t tid = threadIdx.x;
   // shared byte addresses of this thread's column in xs / Ps / Os
-  const uint32_t xs_t = smem_u32(xs) + tid * 8u;
-  const uint32_t ps_t = smem_u32(Ps) + tid * 8u;
-  const uint32_t os_t = smem_u32(Os) + tid * 4u;
+  uint32_t xs_t = smem_u32(xs) + tid * 8u;
+  uint32_t ps_t = smem_u32(Ps) + tid * 8u;
+  uint32_t os_t = smem_u32(Os) + tid * 4u;
   const int64_t tile_pts = (int64_t)NT * R;
   const int64_t stride = (int64_t)gridDim.x * tile_pts;
   const uint32_t ntiles = g.n_btiles;
@@ -231,6 +289,7 @@ __global__ void __launch_bounds__(kBlkThreads, 1) k_eval_block(const DeviceGrid 
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
     BlkPoint<R> pt;
     pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
+    pt.xstride = NT * 8u;
     uint32_t inside = 0u;  // bit k: point k lies in the domain
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -266,8 +325,9 @@ __global__ void __launch_bounds__(kBlkThreads, 1) k_eval_block(const DeviceGrid 
       if (ntiles > 1) blk_issue_tile(g, sm, 1, 1);
     }
     double acc[R];
+    BlkRegs<R> in;
 #pragma unroll
-    for (int k = 0; k < R; ++k) acc[k] = 0.0;
+    for (int k = 0; k < R; ++k) { acc[k] = 0.0; in.Pin[k] = 1.0; in.xin[k] = 0.5; }
 
     for (uint32_t t = 0; t < ntiles; ++t) {
       const int buf = (int)(t & 1u);
@@ -278,62 +338,29 @@ __global__ void __launch_bounds__(kBlkThreads, 1) k_eval_block(const DeviceGrid 
       uint32_t tbias = smem_u32(sm.coef[buf]) - tl.c0 * 8u;  // shared byte address of coefficient slot 0
       pin_u32(rbase);
       pin_u32(tbias);
-      const uint32_t nrec = tl.r1 - tl.r0;
-      for (uint32_t j = 0; j < nrec; ++j) {
-        uint4 rc;  // {cbase, meta, s_hi, used}
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rc.x), "=r"(rc.y), "=r"(rc.z), "=r"(rc.w) : "r"(rbase));
-        rbase += (uint32_t)sizeof(BlockRec);
-        if (MASKED && (int)rc.w > a.rem) continue;  // depth mask of _interpolate_until_level: the whole record lies deeper
-        const uint32_t meta = rc.y;
-        const uint32_t slot = (meta >> kBrSlotShift) & 15u;
-        const uint32_t k0 = (meta >> kBrDimShift) & 15u;
-        const uint32_t b = (meta >> kBrBitsShift) & 63u;
-        const uint32_t odd = (meta >> 24) & 1u;
-        const double s = __hiloint2double((int)rc.z, 0);                    // 2^(l-1), or 0 for the root record
-        const double s2b = __hiloint2double((int)((1023u + b) << 20), 0);  // 2^b
-        const uint32_t lim = (1u << b) - 1u;
-        // the stage: hat of the level-l node of dimension k0 that supports the point, on top of the saved prefix
-        double cur[R];
-        uint32_t cO[R];
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          const double Pin = lds_f64(ps_t + (slot * R + k) * (NT * 8u));
-          uint32_t Oin;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Oin) : "r"(os_t + (slot * R + k) * (NT * 4u)));
-          const double xv = lds_f64(xs_t + (k0 * R + k) * (NT * 8u));
-          const uint32_t cell = min((uint32_t)(xv * s2b), lim);  // floor(x*2^b), clamped for x == 1 (exact)
-          const double tt = fma(xv, s, -u32_to_f64((cell << 1) + odd));
-          cur[k] = Pin * (1.0 - fabs(tt));
-          cO[k] = (Oin << b) | cell;
-        }
-        if (meta & kBrSave) {
-#pragma unroll
-          for (int k = 0; k < R; ++k) {
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ps_t + ((slot + 1u) * R + k) * (NT * 8u)), "d"(cur[k]));
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(os_t + ((slot + 1u) * R + k) * (NT * 4u)), "r"(cO[k]));
-          }
-        }
-        const uint32_t cb = rc.x * 8u + tbias;
-        const int reff = MASKED ? a.rem - (int)rc.w : 0;
-        switch (meta & (15u | kBrS2)) {
-          case 0: blk_record<0, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 1: blk_record<1, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 2: blk_record<2, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 3: blk_record<3, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 4: blk_record<4, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 5: blk_record<5, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 6: blk_record<6, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case 7: blk_record<7, false, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 0: blk_record<0, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 1: blk_record<1, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 2: blk_record<2, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 3: blk_record<3, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 4: blk_record<4, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 5: blk_record<5, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 6: blk_record<6, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
-          case kBrS2 | 7: blk_record<7, true, R, MASKED>(pt, cur, cO, cb, reff, acc); break;
+      pin_u32(xs_t);  // keep the three column addresses in registers: ptxas would re-derive them per record
+      pin_u32(ps_t);
+      pin_u32(os_t);
+      const uint32_t rend = rbase + (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
+      for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
+        BlkStaged<R> st;
+        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, in, st);
+#define BLK_CASE(CODE, RS, S2) \
+  case CODE: blk_record<RS, S2, R, MASKED>(pt, st, a.rem, acc); break;
+        // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
+        // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
+        const uint32_t code = st.sw & 0xffu;
+        if (code == kBrS3 + 0) blk_record<0, false, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == kBrS3 + 1) blk_record<1, false, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == kBrS3 + 2) blk_record<2, false, R, MASKED>(pt, st, a.rem, acc);
+        else switch (code) {
+          BLK_CASE(kBrS3 + 3, 3, false)
+          BLK_CASE(kBrS3 + 4, 4, false) BLK_CASE(kBrS3 + 5, 5, false) BLK_CASE(kBrS3 + 6, 6, false) BLK_CASE(kBrS3 + 7, 7, false)
+          BLK_CASE(kBrS2 + 0, 0, true) BLK_CASE(kBrS2 + 1, 1, true) BLK_CASE(kBrS2 + 2, 2, true) BLK_CASE(kBrS2 + 3, 3, true)
+          BLK_CASE(kBrS2 + 4, 4, true) BLK_CASE(kBrS2 + 5, 5, true) BLK_CASE(kBrS2 + 6, 6, true) BLK_CASE(kBrS2 + 7, 7, true)
           default: break;  // kBrNone: a stage-only record
         }
+#undef BLK_CASE
       }
       __syncthreads();  // every warp is done with buffer `buf`
       if (tid == 0 && t + 2 < ntiles) blk_issue_tile(g, sm, t + 2, buf);
@@ -361,32 +388,48 @@ static int blk_sm_count() {
   return sms;
 }
 
-static size_t blk_smem_bytes(const DeviceGrid &g, int R) {
-  return sizeof(BlkSmem) + ((size_t)g.D * 8 + (size_t)g.blk_slots * 12) * R * kBlkThreads;
+static size_t blk_smem_bytes(const DeviceGrid &g, int R, int threads) {
+  return sizeof(BlkSmem) + ((size_t)g.D * 8 + (size_t)g.blk_slots * 12) * R * threads;
 }
 
-bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_bytes(g, 1) <= 227 * 1024; }
+static int blk_threads() {
+  static const int nt = [] {
+    const char *e = getenv("ASG_BLOCK_THREADS");  // experiment knob
+    const int v = e ? atoi(e) : kBlkThreads;
+    return (v == 384 || v == 512) ? v : kBlkThreads;
+  }();
+  return nt;
+}
+
+bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_bytes(g, 1, blk_threads()) <= 227 * 1024; }
+
+template <int R, bool MASKED, int NT>
+static void blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(k_eval_block<R, MASKED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_eval_block<R, MASKED, NT><<<blocks, NT, smem, st>>>(g, a);
+}
+template <int NT>
+static void blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, int blocks, size_t smem,
+                          cudaStream_t st) {
+  if (two) { if (masked) blk_launch<2, true, NT>(g, a, blocks, smem, st); else blk_launch<2, false, NT>(g, a, blocks, smem, st); }
+  else     { if (masked) blk_launch<1, true, NT>(g, a, blocks, smem, st); else blk_launch<1, false, NT>(g, a, blocks, smem, st); }
+}
 
 cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
   if (a.M <= 0) return cudaSuccess;
   const int sms = blk_sm_count();
+  const int nt = blk_threads();
   // two points per thread when the batch fills the machine and the shared memory fits, else one
-  bool two = a.M >= (int64_t)sms * kBlkThreads * 2 && blk_smem_bytes(g, 2) <= 227 * 1024;
-  if (const char *e = getenv("ASG_BLOCK_R")) two = (e[0] == '2') && blk_smem_bytes(g, 2) <= 227 * 1024;  // experiment knob
+  bool two = a.M >= (int64_t)sms * nt * 2 && blk_smem_bytes(g, 2, nt) <= 227 * 1024;
+  if (const char *e = getenv("ASG_BLOCK_R")) two = (e[0] == '2') && blk_smem_bytes(g, 2, nt) <= 227 * 1024;  // experiment knob
   const int R = two ? 2 : 1;
-  const size_t smem = blk_smem_bytes(g, R);
-  const int64_t per_block = (int64_t)kBlkThreads * R;
+  const size_t smem = blk_smem_bytes(g, R, nt);
+  const int64_t per_block = (int64_t)nt * R;
   const int64_t need = (a.M + per_block - 1) / per_block;
   const int blocks = (int)(need < sms ? need : sms);
   const bool masked = a.rem < INT_MAX / 4;
-#define LAUNCH(RR, MM)                                                                                        \
-  do {                                                                                                        \
-    cudaFuncSetAttribute(k_eval_block<RR, MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
-    k_eval_block<RR, MM><<<blocks, kBlkThreads, smem, st>>>(g, a);                                            \
-  } while (0)
-  if (two) { if (masked) LAUNCH(2, true); else LAUNCH(2, false); }
-  else     { if (masked) LAUNCH(1, true); else LAUNCH(1, false); }
-#undef LAUNCH
+  if (nt == 384) blk_launch_nt<384>(g, a, two, masked, blocks, smem, st);
+  else blk_launch_nt<512>(g, a, two, masked, blocks, smem, st);
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -174,23 +174,33 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
   }
   // 5. records in lexicographic order + the slot span each one reads
   std::vector<uint32_t> lo, hi;
+  auto stage_of = [](BlockRec &q, int slot, int k0, int l, bool save, int used) {
+    q.slot = (uint32_t)slot;
+    q.k0 = (uint32_t)k0;
+    q.b = (uint32_t)blk_bits(l);
+    q.s_hi = l > 1 ? (uint32_t)(1023 + l - 1) << 20 : 0u;  // l == 1 only for the root: s = 0 gives phi = 1
+    q.lim = (1u << blk_bits(l)) - 1u;
+    q.odd = l > 2 ? 1u : 0u;
+    q.sw = (save ? kBrSave : 0u) | ((uint32_t)used << kBrUsedShift);
+  };
+  Key prev_parent;
+  int prev_k0 = -1;
   for (auto &kv : pre) {
     const Key &p = kv.first;
     const PrefixInfo &I = kv.second;
     BlockRec q{};
     const int l0 = I.nt ? p[(size_t)I.k0] : 1;
-    q.s_hi = I.nt ? (uint32_t)(1023 + l0 - 1) << 20 : 0u;
-    q.used = (uint32_t)I.used;
-    q.meta = ((uint32_t)(I.nt ? I.nt - 1 : 0) << kBrSlotShift) | ((uint32_t)I.k0 << kBrDimShift) |
-             ((uint32_t)blk_bits(l0) << kBrBitsShift) | (l0 > 2 ? kBrOdd : 0u) |
-             ((I.parent_of && I.nt) ? kBrSave : 0u);
+    stage_of(q, I.nt ? I.nt - 1 : 0, I.k0, l0, I.parent_of && I.nt, I.used);
+    const Key par = parent_of(p);
+    if (I.nt && prev_k0 == I.k0 && par == prev_parent) q.sw |= kBrSameIn;  // sibling of the previous record
+    prev_parent = par;
+    prev_k0 = I.nt ? I.k0 : -1;
     if (I.r < 0) {
-      q.meta |= kBrNone;
-      q.cbase = 0;
+      q.sw |= kBrNone;
       out.brec.push_back(q);
       lo.push_back(0); hi.push_back(0);
     } else if (!I.split) {
-      q.meta |= (uint32_t)I.r;
+      q.sw |= kBrS3 + (uint32_t)I.r;
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
@@ -199,20 +209,17 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       for (int lA = 1; lA <= I.r + 1; ++lA) {
         BlockRec s = q;
         const int rA = I.r - (lA - 1);
-        s.cbase = I.cbaseA[lA - 1];
-        if (lA == 1) {
-          s.meta |= (uint32_t)rA | kBrS2;
-          // root prefix: nothing to save for, the lA >= 2 records restart from slot 0 as well
-        } else {  // stage = level lA of dimension A, restart from the prefix product this prefix saved
-          s.meta = (uint32_t)rA | kBrS2 | ((uint32_t)I.nt << kBrSlotShift) | ((uint32_t)K << kBrDimShift) |
-                   ((uint32_t)blk_bits(lA) << kBrBitsShift) | (lA > 2 ? kBrOdd : 0u);
-          s.s_hi = (uint32_t)(1023 + lA - 1) << 20;
-          s.used = (uint32_t)(I.used + lA - 1);
+        if (lA > 1) {  // stage = level lA of dimension A, restart from the prefix product this prefix saved
+          stage_of(s, I.nt, K, lA, false, I.used + lA - 1);
+          if (lA > 2) s.sw |= kBrSameIn;
         }
+        s.sw |= kBrS2 + (uint32_t)rA;
+        s.cbase = I.cbaseA[lA - 1];
         out.brec.push_back(s);
         lo.push_back(s.cbase);
         hi.push_back(s.cbase + (blk_size2(rA) << (I.pb + blk_bits(lA))));
       }
+      prev_k0 = -1;  // the next prefix record follows S2 records of another dimension
     }
   }
   // 6. tiles: consecutive records whose spans fit one coefficient buffer
@@ -301,27 +308,31 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
   O[0] = 0;
   double acc = 0.0;
   const double xA = x01[K], xB = x01[K + 1], xC = x01[K + 2];
+  double Pin = 1.0, xin = 0.0;
+  uint64_t Oin = 0;
   for (const BlockRec &q : pk.brec) {
-    if ((int)q.used > rem) continue;
-    const int slot = (int)((q.meta >> kBrSlotShift) & 15u);
-    const int k0 = (int)((q.meta >> kBrDimShift) & 15u);
-    const int b = (int)((q.meta >> kBrBitsShift) & 63u);
-    const uint32_t odd = (q.meta & kBrOdd) ? 1u : 0u;
+    const int used = (int)(q.sw >> kBrUsedShift);
+    if (used > rem) continue;
+    if (!(q.sw & kBrSameIn)) {  // siblings keep the input of the previous record in registers
+      Pin = P[q.slot];
+      Oin = O[q.slot];
+      xin = x01[q.k0];
+    }
     double s;
     {
       const uint64_t bits = (uint64_t)q.s_hi << 32;
       std::memcpy(&s, &bits, 8);
     }
-    const double x = x01[k0];
-    const uint32_t cell = std::min((uint32_t)(x * std::ldexp(1.0, b)), (1u << b) - 1u);
-    const double t = std::fma(x, s, -(double)(2u * cell + odd));
-    const double cur = P[slot] * (1.0 - std::fabs(t));
-    const uint64_t cO = (O[slot] << b) | cell;
-    if (q.meta & kBrSave) { P[slot + 1] = cur; O[slot + 1] = cO; }
-    const int rs = (int)(q.meta & 15u);
-    if (rs == (int)kBrNone) continue;
-    const int reff = std::min(rs, rem - (int)q.used);
-    const bool s2 = (q.meta & kBrS2) != 0;
+    const uint32_t cell = std::min((uint32_t)(xin * std::ldexp(1.0, (int)q.b)), q.lim);
+    const double t = std::fma(xin, s, -(double)(2u * cell + q.odd));
+    const double cur = Pin * (1.0 - std::fabs(t));
+    const uint64_t cO = (Oin << q.b) | cell;
+    if (q.sw & kBrSave) { P[q.slot + 1] = cur; O[q.slot + 1] = cO; }
+    const uint32_t code = q.sw & 0xffu;
+    if (code >= kBrNone) continue;
+    const bool s2 = code >= kBrS2;
+    const int rs = (int)(code & 7u);
+    const int reff = std::min(rs, rem - used);
     const double *chunk = pk.bcoef.data() + q.cbase + cO * (s2 ? blk_size2(rs) : blk_size3(rs));
     double inner3 = 0.0;
     for (int lA = 1; lA <= (s2 ? 1 : reff + 1); ++lA) {
