@@ -90,6 +90,7 @@ SIGNATURES = {
     "asg_pack_info": [C.c_int32, C.c_int64, i64p, i64p, C.c_int64, C.c_int64, C.POINTER(GridInfo)],
     "asg_measure_fp64_peak": [f64p],
     "asg_last_kernel_ms": [f64p],
+    "asg_last_walk_ms": [f64p],
 }
 STRING_GETTERS = ("asg_last_error", "asg_version")
 

@@ -31,7 +31,9 @@ struct Context {
   int device = -1;
   cudaStream_t stream = nullptr;      // library stream (device-pointer entry points)
   cudaStream_t pipe[2] = {nullptr, nullptr};  // host-buffer pipelines (double buffering)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the last *_device call
+  cudaEvent_t evw0 = nullptr, evw1 = nullptr;  // around its walk kernel alone (BLOCK walk: after the point ordering)
+  bool walk_timed = false;
   std::atomic<long long> launches{0};
   double last_ms = 0.0;
   bool last_timed = false;
@@ -311,8 +313,9 @@ int64_t sort_threshold() {
   return thr;
 }
 
-int run_eval(asg_grid *g, const EvalArgs &a_in, cudaStream_t st, int slot = 0) {
+int run_eval(asg_grid *g, const EvalArgs &a_in, cudaStream_t st, int slot = 0, bool timed = false) {
   int64_t l = 0;
+  if (timed) ctx.walk_timed = false;
   cudaError_t e;
   EvalArgs a = a_in;
   if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(g->dg, a, st, &l);
@@ -332,7 +335,9 @@ int run_eval(asg_grid *g, const EvalArgs &a_in, cudaStream_t st, int slot = 0) {
       a.perm = g->s_perm[slot].p;
       sorted = true;
     }
+    if (timed) CK(cudaEventRecord(ctx.evw0, st));
     e = launch_eval_block(g->dg, a, st, &l);
+    if (timed) { CK(cudaEventRecord(ctx.evw1, st)); ctx.walk_timed = true; }
     if (sorted && e == cudaSuccess) CK(cudaEventRecord(g->sort_ev[slot], st));
   }
   else if (g->walk() == 0) e = launch_eval_stream(g->dg, a, st, &l);
@@ -461,6 +466,8 @@ int32_t asg_init(int32_t device) {
   CK(cudaStreamCreateWithFlags(&ctx.pipe[1], cudaStreamNonBlocking));
   CK(cudaEventCreate(&ctx.ev0));
   CK(cudaEventCreate(&ctx.ev1));
+  CK(cudaEventCreate(&ctx.evw0));
+  CK(cudaEventCreate(&ctx.evw1));
   ctx.device = device;
   ctx.ready = true;
   return ASG_OK;
@@ -476,6 +483,8 @@ int32_t asg_shutdown(void) {
   cudaStreamDestroy(ctx.pipe[1]);
   cudaEventDestroy(ctx.ev0);
   cudaEventDestroy(ctx.ev1);
+  cudaEventDestroy(ctx.evw0);
+  cudaEventDestroy(ctx.evw1);
   ctx.ready = false;
   ctx.device = -1;
   return ASG_OK;
@@ -702,7 +711,7 @@ int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, in
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), nullptr, dout};
   CK(cudaEventRecord(ctx.ev0, st));
-  if (int rc = run_eval(g, a, st)) return rc;
+  if (int rc = run_eval(g, a, st, 0, true)) return rc;
   CK(cudaEventRecord(ctx.ev1, st));
   ctx.last_timed = true;
   return ASG_OK;
@@ -717,7 +726,7 @@ int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp,
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), dfvals, dalpha};
   CK(cudaEventRecord(ctx.ev0, st));
-  if (int rc = run_eval(g, a, st)) return rc;
+  if (int rc = run_eval(g, a, st, 0, true)) return rc;
   CK(cudaEventRecord(ctx.ev1, st));
   ctx.last_timed = true;
   return ASG_OK;
@@ -730,6 +739,18 @@ int32_t asg_last_kernel_ms(double *ms) {
   CK(cudaEventSynchronize(ctx.ev1));
   float f = 0.f;
   CK(cudaEventElapsedTime(&f, ctx.ev0, ctx.ev1));
+  *ms = (double)f;
+  return ASG_OK;
+}
+
+int32_t asg_last_walk_ms(double *ms) {
+  if (!ms) return set_err(ASG_EINVAL, "null pointer");
+  if (int rc = require_ctx()) return rc;
+  if (!ctx.last_timed) return set_err(ASG_ESTATE, "no timed launch yet");
+  cudaEvent_t a = ctx.walk_timed ? ctx.evw0 : ctx.ev0, b = ctx.walk_timed ? ctx.evw1 : ctx.ev1;
+  CK(cudaEventSynchronize(b));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, a, b));
   *ms = (double)f;
   return ASG_OK;
 }

@@ -13,8 +13,8 @@
 //   the COMPILED walk of the last three dimensions: the kernel is templated on the suffix budget, all
 //   levels and slot offsets are compile-time constants, so a term costs an address add, one LDS.64 and
 //   one DFMA, a pole (fixed levels of all dimensions but the last) one IMAD and one DFMA more.
-// * The hats of levels 2..5 of the last two dimensions live in per-point register tables; levels 6..8
-//   (66 of the 19 448 terms per point on the D = 10 benchmark grid) are formed on the fly.
+// * The hats of levels 2..4 of the last two dimensions live in per-point register tables; levels 5..8
+//   (286 of the 19 448 terms per point on the D = 10 benchmark grid) are formed on the fly.
 // The 1-D hat is the reference's phi (src/math.jl:345-357) evaluated on its support only, with the
 // reference's single rounding (asg_device.cuh). Out-of-domain / NaN points give exactly 0.0.
 #include <cstdlib>

@@ -68,6 +68,26 @@ def fp64_op_counts(levels):
     return instr, flops, leaves
 
 
+def fp64_op_counts_block(levels):
+    """FP64 work of the BLOCK walk (asg_kernels_block.cu) for ONE point, counted from the level vectors.
+    One record per distinct prefix (dims 0..D-4): stage DMUL (x*2^b) + DADD (int->double) + DFMA (t) + DADD (1-|t|)
+    + DMUL (prefix product) and the record's DFMA into the accumulator = 6 instr / 8 flop. Per node of dimension
+    D-3 with level > 1: DADD + DFMA + DADD (hat on the fly) + DFMA (Horner) = 4 instr / 6 flop. Per pole with
+    l_{D-2} > 1 and per subspace with l_{D-1} > 1: one DFMA. Register tables: 2 dims x 3 levels x 3 instr once per
+    point. The DFMA count equals the number of subspaces. Returns (fp64 instructions, flops, subspaces)."""
+    lv = np.unique(levels, axis=0)
+    D = lv.shape[1]
+    leaf_fma = int(np.count_nonzero(lv[:, -1] > 1))
+    poles = np.unique(lv[:, :-1], axis=0)
+    pole_fma = int(np.count_nonzero(poles[:, -1] > 1))
+    l8 = np.unique(lv[:, :-2], axis=0)
+    l8_nt = int(np.count_nonzero(l8[:, -1] > 1))
+    recs = len(np.unique(lv[:, :-3], axis=0))
+    instr = leaf_fma + pole_fma + 4 * l8_nt + 6 * recs + 18
+    flops = 2 * (leaf_fma + pole_fma) + 6 * l8_nt + 8 * recs + 2 * 3 * 4
+    return instr, flops, len(lv)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -260,7 +280,7 @@ def main():
         sampler.start()
     l0 = asg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
+    kern_ms, call_ms = [], []
     barrier()
     e0.record(stream)
     for _ in range(K):
@@ -274,8 +294,10 @@ def main():
     for _ in range(3):
         step_device()
         ms = C.c_double()
-        asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))
+        asg._capi.check(lib.asg_last_walk_ms(C.byref(ms)))     # the walk kernel alone
         kern_ms.append(ms.value)
+        asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))   # point ordering + walk
+        call_ms.append(ms.value)
     t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -334,10 +356,13 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_eval_stream<10,...>) -----------------------------------
+    # ---- roofline of the dominant kernel (k_eval_block<2,false,512>; k_eval_stream on other grids) ----
     fma_rate = C.c_double()
     asg._capi.check(lib.asg_measure_fp64_peak(C.byref(fma_rate)))
-    instr, flops, leaves = fp64_op_counts(G.levels)
+    block = bool(info.get("block")) and os.environ.get("ASG_EVAL_KERNEL", "b")[0] == "b"
+    instr, flops, leaves = (fp64_op_counts_block if block else fp64_op_counts)(G.levels)
+    kname = "k_eval_block<2,false,512>" if block else f"k_eval_stream<{D},R,false>"
+    prof_name = "r01b_final_eval_block_d10_summary.json" if block else "r01_final_eval_stream_d10_summary.json"
     k_ms = statistics.median(kern_ms)
     pts_per_launch = M
     peaks = {}
@@ -349,7 +374,7 @@ def main():
     alg_bytes = pts_per_launch * (8 * D + 8)
     roofline = {
         "bound": "fp64",  # FP64 CUDA-core pipe: the path is a sparse gather-product, not HBM- or tensor-bound
-        "kernel": f"k_eval_stream<{D},R,false>",
+        "kernel": kname,
         "achieved": flops * pts_per_launch / (k_ms * 1e-3) / 1e12,
         "peak": 2.0 * fma_rate.value / 1e12,
         "unit": "TFLOP/s",
@@ -358,6 +383,7 @@ def main():
         "fp64_pipe_slot_frac": (instr * pts_per_launch / (k_ms * 1e-3)) / fma_rate.value,
         "fp64_instr_per_point": instr, "flop_per_point": flops, "terms_per_point": leaves,
         "kernel_ms": k_ms, "points_per_launch": pts_per_launch,
+        "point_order_ms": statistics.median(call_ms) - k_ms,
         "traffic": None,
         "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
@@ -368,7 +394,7 @@ def main():
                              "note": "N*M/t with every (node, point) pair counted, SURVEY.md 8d; > 1 because "
                                      "only the one supporting node per subspace is visited"},
     }
-    prof = os.path.join(ROOT, "profiles", "r01_final_eval_stream_d10_summary.json")
+    prof = os.path.join(ROOT, "profiles", prof_name)
     if os.path.exists(prof):
         try:
             pj = json.load(open(prof))
@@ -403,7 +429,8 @@ def main():
         "config": {"workload": WORKLOAD, "nodes": int(N), "subspaces": int(info["subspaces"]),
                    "points_per_step": M_total, "points_per_gpu": M, "parallelism": f"grid replicated, points sharded x{world}",
                    "l2": "inputs larger than L2 (80 B/point * points_per_gpu >> 126 MB), no flush needed",
-                   "engine": "subspace" if info["path"] == 2 else "sweep"},
+                   "engine": ("subspace/block" if block else "subspace/stream") if info["path"] == 2 else "sweep",
+                   "point_order": "cell-key sorted inside the timed region (asg_sort.cu)" if block else "as given"},
         "products_per_s": value * N,
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -180,6 +180,9 @@ int32_t asg_measure_fp64_peak(double *fma_per_second);
 /* time (ms, CUDA events on the library stream) of the last asg_eval_device / asg_surplus_device /
  * asg_basis_dense_device kernel sequence */
 int32_t asg_last_kernel_ms(double *ms);
+/* the same for the evaluation (walk) kernel alone: equal to asg_last_kernel_ms unless the call ordered its
+ * points by cell key first (BLOCK walk on large batches, csrc/asg_sort.cu) */
+int32_t asg_last_walk_ms(double *ms);
 
 #ifdef __cplusplus
 }
