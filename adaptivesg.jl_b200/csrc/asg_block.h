@@ -18,6 +18,7 @@
 //         the pole holds the 1-D hierarchy of dimension C: level 1 at 0, level l >= 2 at
 //         off1(l) + cell  (off1 = 1, 3, 5, 9, 17, 33, 65)
 //   slot = cbase + O*size3(r) + offA(lA, r) + cA*size2(r-eA) + offB(lB, r-eA) + cB*n1(r-eA-eB) + off1(lC) + cC
+// (S = 4, 5, 6 records, see blk_max_r below, continue the same recursion upwards: dimension D-S outermost.)
 // Nodes that the grid does not hold (level caps, adapt! output) are stored as 0.0; a grid takes the
 // BLOCK layout only while that padding stays below the number of real nodes.
 //
@@ -45,19 +46,25 @@ ASG_HD constexpr int blk_bits(int l) { return l == 1 ? 0 : (l == 2 ? 1 : l - 2);
 ASG_HD constexpr uint32_t blk_n1(int r) { return r < 0 ? 0u : (r == 0 ? 1u : (1u << r) + 1u); }
 // offset of level l inside a pole: 0, 1, 3, 5, 9, ...
 ASG_HD constexpr uint32_t blk_off1(int l) { return l == 1 ? 0u : blk_n1(l - 2); }
-ASG_HD constexpr uint32_t blk_offB(int lB, int rA) {  // 2-D block of budget rA: start of level lB of dimension B
+// Compiled suffix of S dimensions and budget r (S = 1: a pole). size(S, r) doubles; level l of the suffix's
+// first dimension starts at off(S, l, r) and holds 2^b(l) sub-blocks of size(S-1, r-(l-1)).
+ASG_HD constexpr uint32_t blk_size(int S, int r);
+ASG_HD constexpr uint32_t blk_off(int S, int l, int r) {
   uint32_t s = 0;
-  for (int l = 1; l < lB; ++l) s += (1u << blk_bits(l)) * blk_n1(rA - (l - 1));
+  for (int k = 1; k < l; ++k) s += (1u << blk_bits(k)) * blk_size(S - 1, r - (k - 1));
   return s;
 }
-ASG_HD constexpr uint32_t blk_size2(int r) { return r < 0 ? 0u : blk_offB(r + 2, r); }  // 1, 5, 13, 29, 65, 145, 321, 705
-ASG_HD constexpr uint32_t blk_offA(int lA, int r) {  // chunk of budget r: start of level lA of dimension A
-  uint32_t s = 0;
-  for (int l = 1; l < lA; ++l) s += (1u << blk_bits(l)) * blk_size2(r - (l - 1));
-  return s;
-}
-ASG_HD constexpr uint32_t blk_size3(int r) { return r < 0 ? 0u : blk_offA(r + 2, r); }  // 1, 7, 25, 69, 177, 441, 1073, 2561
+ASG_HD constexpr uint32_t blk_size(int S, int r) { return r < 0 ? 0u : (S <= 1 ? blk_n1(r) : blk_off(S, r + 2, r)); }
+ASG_HD constexpr uint32_t blk_offB(int lB, int rA) { return blk_off(2, lB, rA); }  // 2-D block: start of level lB of B
+ASG_HD constexpr uint32_t blk_size2(int r) { return blk_size(2, r); }              // 1, 5, 13, 29, 65, 145, 321, 705
+ASG_HD constexpr uint32_t blk_offA(int lA, int r) { return blk_off(3, lA, r); }    // 3-D chunk: start of level lA of A
+ASG_HD constexpr uint32_t blk_size3(int r) { return blk_size(3, r); }              // 1, 7, 25, 69, 177, 441, 1073, 2561
 static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "suffix block sizes");
+// Deeper compiled suffixes for prefixes that leave little budget: half of the prefix vectors of a regular grid
+// leave r = 0 (one term), a quarter r = 1. Where a SHORTER prefix (S = 4, 5, 6 compiled dimensions) still has a
+// small budget, ONE record with a compiled S-dimensional suffix replaces all the records below it.
+constexpr int kBlkMaxS = 6;
+ASG_HD constexpr int blk_max_r(int S) { return S == 3 ? kBlkMaxBudget : (S == 4 ? 3 : ((S == 5 || S == 6) ? 2 : -1)); }
 
 // One 32-byte record per prefix level vector, in lexicographic (depth-first) order, stored pre-decoded
 // (one field per word: the kernel does no shifting or masking on its critical path). Every record but
@@ -77,7 +84,10 @@ struct __align__(16) BlockRec {
 static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words");
 constexpr uint32_t kBrS3 = 0u;    // sw = kBrS3 + r: 3-D suffix of budget r = 0..7
 constexpr uint32_t kBrS2 = 8u;    // sw = kBrS2 + r: 2-D suffix (dimension A is this record's stage or at level 1)
-constexpr uint32_t kBrNone = 16u; // stage only (no nodes under this prefix)
+constexpr uint32_t kBrS4 = 16u;   // sw = kBrS4 + r: 4-D suffix, r = 1..3   (prefix = dimensions 0..D-5)
+constexpr uint32_t kBrS5 = 20u;   // sw = kBrS5 + r: 5-D suffix, r = 1..2
+constexpr uint32_t kBrS6 = 24u;   // sw = kBrS6 + r: 6-D suffix, r = 1..2
+constexpr uint32_t kBrNone = 31u; // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
 constexpr uint32_t kBrSameIn = 1u << 9;  // same input slot and stage dimension as the previous record (siblings)
 constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2: including dimension A): depth mask

@@ -46,11 +46,12 @@ struct BlkPoint {
   uint32_t xstride;              // bytes between consecutive points / dimensions in xs (threads * 8)
 };
 
-// coordinate of dimension D-2 (which = 0) or D-1 (which = 1) of point k, from shared memory (rare levels only)
+// coordinate of dimension D-2+which (which = 0, 1: B, C at rare levels; which < 0: dimensions above A of the
+// deeper compiled suffixes) of point k, from shared memory
 template <int R>
 __device__ __forceinline__ double blk_x_rare(const BlkPoint<R> &pt, int which, int k) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)(which * R + k) * pt.xstride));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (int)pt.xstride)));
   return v;
 }
 __device__ __forceinline__ uint32_t blk_key(double v) {  // floor(v * 2^30), clamped for v == 1 (exact)
@@ -148,29 +149,37 @@ __device__ __forceinline__ void blk_suffix2(const BlkPoint<R> &pt, const uint32_
   }
 }
 
-// chunk of storage budget RS at shared byte address t3[k]: levels LA.. of dimension A
-template <int RS, int LA, int R, bool MASKED>
-__device__ __forceinline__ void blk_suffix3(const BlkPoint<R> &pt, const uint32_t (&t3)[R], int reff, double (&inner3)[R]) {
-  if constexpr (LA <= RS + 1) {
-    if (MASKED && LA - 1 > reff) return;
-    constexpr int RB = RS - (LA - 1);
-    constexpr int IMM = (int)blk_offA(LA, RS) * 8;
+// compiled suffix of S >= 3 dimensions (D-S .. D-1) of storage budget RS at shared byte address t[k] + IMM:
+// levels L.. of dimension D-S. S = 3: that dimension is A (coordinate and key in registers); S > 3: its
+// coordinate comes from shared memory (those records are few and small, see blk_max_r).
+template <int S, int RS, int L, int IMM, int R, bool MASKED>
+__device__ __forceinline__ void blk_suffixN(const BlkPoint<R> &pt, const uint32_t (&t)[R], int reff, double (&out)[R]) {
+  if constexpr (L <= RS + 1) {
+    if (MASKED && L - 1 > reff) return;
+    constexpr int RB = RS - (L - 1);
+    constexpr int IMM2 = IMM + (int)blk_off(S, L, RS) * 8;
     uint32_t t2[R];
-    double phA[R], accA[R];
+    double ph[R], sub[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      if constexpr (LA == 1) {
-        t2[k] = t3[k];
+      if constexpr (L == 1) {
+        t2[k] = t[k];
       } else {
         uint32_t cell;
-        hat_ct<(LA > 1 ? LA : 2)>(pt.xA[k], pt.qA[k], phA[k], cell);
-        t2[k] = t3[k] + cell * (blk_size2(RB) * 8u);
+        if constexpr (S == 3) {
+          hat_ct<(L > 1 ? L : 2)>(pt.xA[k], pt.qA[k], ph[k], cell);
+        } else {
+          const double x = blk_x_rare<R>(pt, 2 - S, k);  // dimension D-S is S-2 rows above dimension D-2 in xs
+          hat_ct<(L > 1 ? L : 2)>(x, blk_key(x), ph[k], cell);
+        }
+        t2[k] = t[k] + cell * (blk_size(S - 1, RB) * 8u);
       }
     }
-    blk_suffix2<RB, 1, IMM, R, MASKED>(pt, t2, reff - (LA - 1), accA);
+    if constexpr (S == 3) blk_suffix2<RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
+    else blk_suffixN<S - 1, RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
 #pragma unroll
-    for (int k = 0; k < R; ++k) inner3[k] = LA == 1 ? accA[k] : fma(phA[k], accA[k], inner3[k]);
-    blk_suffix3<RS, LA + 1, R, MASKED>(pt, t3, reff, inner3);
+    for (int k = 0; k < R; ++k) out[k] = L == 1 ? sub[k] : fma(ph[k], sub[k], out[k]);
+    blk_suffixN<S, RS, L + 1, IMM, R, MASKED>(pt, t, reff, out);
   }
 }
 
@@ -230,15 +239,15 @@ __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_
 
 // One record: the compiled suffix of the staged record. (Staging the NEXT record inside the same basic block,
 // so that ptxas interleaves the two dependency chains, was measured 5 % slower: registers.)
-template <int RS, bool S2, int R, bool MASKED>
+template <int S, int RS, int R, bool MASKED>
 __device__ __forceinline__ void blk_record(const BlkPoint<R> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
   uint32_t t[R];
 #pragma unroll
-  for (int k = 0; k < R; ++k) t[k] = st.t[k] * ((S2 ? blk_size2(RS) : blk_size3(RS)) * 8u) + st.cb;
+  for (int k = 0; k < R; ++k) t[k] = st.t[k] * (blk_size(S, RS) * 8u) + st.cb;
   const int reff = MASKED ? rem - (int)(st.sw >> kBrUsedShift) : 0;
   double v[R];
-  if constexpr (S2) blk_suffix2<RS, 1, 0, R, MASKED>(pt, t, reff, v);
-  else blk_suffix3<RS, 1, R, MASKED>(pt, t, reff, v);
+  if constexpr (S == 2) blk_suffix2<RS, 1, 0, R, MASKED>(pt, t, reff, v);
+  else blk_suffixN<S, RS, 1, 0, R, MASKED>(pt, t, reff, v);
 #pragma unroll
   for (int k = 0; k < R; ++k) acc[k] = fma(st.cur[k], v[k], acc[k]);
 }
@@ -345,19 +354,22 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
         BlkStaged<R> st;
         blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, in, st);
-#define BLK_CASE(CODE, RS, S2) \
-  case CODE: blk_record<RS, S2, R, MASKED>(pt, st, a.rem, acc); break;
+#define BLK_CASE(CODE, S, RS) \
+  case CODE: blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
         // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
         // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
         const uint32_t code = st.sw & 0xffu;
-        if (code == kBrS3 + 0) blk_record<0, false, R, MASKED>(pt, st, a.rem, acc);
-        else if (code == kBrS3 + 1) blk_record<1, false, R, MASKED>(pt, st, a.rem, acc);
-        else if (code == kBrS3 + 2) blk_record<2, false, R, MASKED>(pt, st, a.rem, acc);
+        if (code == kBrS3 + 0) blk_record<3, 0, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == kBrS3 + 1) blk_record<3, 1, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == kBrS3 + 2) blk_record<3, 2, R, MASKED>(pt, st, a.rem, acc);
         else switch (code) {
-          BLK_CASE(kBrS3 + 3, 3, false)
-          BLK_CASE(kBrS3 + 4, 4, false) BLK_CASE(kBrS3 + 5, 5, false) BLK_CASE(kBrS3 + 6, 6, false) BLK_CASE(kBrS3 + 7, 7, false)
-          BLK_CASE(kBrS2 + 0, 0, true) BLK_CASE(kBrS2 + 1, 1, true) BLK_CASE(kBrS2 + 2, 2, true) BLK_CASE(kBrS2 + 3, 3, true)
-          BLK_CASE(kBrS2 + 4, 4, true) BLK_CASE(kBrS2 + 5, 5, true) BLK_CASE(kBrS2 + 6, 6, true) BLK_CASE(kBrS2 + 7, 7, true)
+          BLK_CASE(kBrS3 + 3, 3, 3) BLK_CASE(kBrS3 + 4, 3, 4) BLK_CASE(kBrS3 + 5, 3, 5) BLK_CASE(kBrS3 + 6, 3, 6)
+          BLK_CASE(kBrS3 + 7, 3, 7)
+          BLK_CASE(kBrS2 + 0, 2, 0) BLK_CASE(kBrS2 + 1, 2, 1) BLK_CASE(kBrS2 + 2, 2, 2) BLK_CASE(kBrS2 + 3, 2, 3)
+          BLK_CASE(kBrS2 + 4, 2, 4) BLK_CASE(kBrS2 + 5, 2, 5) BLK_CASE(kBrS2 + 6, 2, 6) BLK_CASE(kBrS2 + 7, 2, 7)
+          BLK_CASE(kBrS4 + 1, 4, 1) BLK_CASE(kBrS4 + 2, 4, 2) BLK_CASE(kBrS4 + 3, 4, 3)
+          BLK_CASE(kBrS5 + 1, 5, 1) BLK_CASE(kBrS5 + 2, 5, 2)
+          BLK_CASE(kBrS6 + 1, 6, 1) BLK_CASE(kBrS6 + 2, 6, 2)
           default: break;  // kBrNone: a stage-only record
         }
 #undef BLK_CASE

@@ -2,6 +2,7 @@
 // and a host model of the walk the kernel performs over it (used as the packer's self-check).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -11,19 +12,21 @@ namespace asg {
 
 namespace {
 
-struct PrefixInfo {
-  int r = -1;           // suffix budget: max sum(l-1) over dimensions A, B, C of the nodes under this prefix
-  int pb = 0;           // position bits of the prefix
-  int used = 0;         // sum(l-1) of the prefix
-  int nt = 0;           // non-trivial dimensions (level > 1)
-  int k0 = 0;           // last non-trivial dimension
-  bool parent_of = false;  // some other prefix restarts from this one
-  bool split = false;   // S2 records (one per level of A)
-  uint32_t cbase = 0;   // S3: first slot; S2: see cbaseA
+using Key = std::vector<uint8_t>;  // levels of the prefix dimensions 0..D-4 (always full length)
+
+struct Rec {             // one record before S2 splitting
+  int depth = 0;         // data-driven prefix: dimensions 0..depth-1; compiled suffix: S = D - depth dimensions
+  int S = 3;
+  int r = -1;            // budget of the compiled suffix: max sum(l-1) over its dimensions; -1: stage only
+  int pb = 0;            // position bits of the prefix
+  int used = 0;          // sum(l-1) of the prefix
+  int nt = 0;            // non-trivial prefix dimensions (level > 1)
+  int k0 = 0;            // last non-trivial prefix dimension
+  bool parent_of = false;  // some other record restarts from this one
+  bool split = false;    // S = 3 only: S2 records, one per level of A
+  uint32_t cbase = 0;
   uint32_t cbaseA[kBlkMaxBudget + 1] = {0};  // S2: first slot of level lA = 1..r+1
 };
-
-using Key = std::vector<uint8_t>;
 
 Key parent_of(const Key &p) {
   Key q = p;
@@ -44,6 +47,37 @@ inline uint32_t cell_host(double x, int l) {
   return std::min(c, (1u << b) - 1u);
 }
 
+int max_compiled_dims() {  // experiment knob: ASG_BLOCK_MAXS=3 keeps one record per prefix level vector
+  static const int v = [] {
+    const char *e = getenv("ASG_BLOCK_MAXS");
+    const int s = e ? atoi(e) : kBlkMaxS;
+    return std::min(std::max(s, 3), kBlkMaxS);
+  }();
+  return v;
+}
+
+// compiled suffix of S dimensions (D-S .. D-1), storage budget rs, evaluated up to budget reff, Horner form
+double eval_suffix_host(int D, int S, int rs, int reff, const double *blk, const double *x01) {
+  if (S == 1) {  // pole
+    const double xC = x01[D - 1];
+    double inner = blk[0];
+    for (int lC = 2; lC <= reff + 1; ++lC) {
+      const uint32_t cC = cell_host(xC, lC);
+      inner = std::fma(blk[blk_off1(lC) + cC], hat_host(xC, lC, cC), inner);
+    }
+    return inner;
+  }
+  const double x = x01[D - S];
+  double out = 0.0;
+  for (int l = 1; l <= reff + 1; ++l) {
+    const int rb = rs - (l - 1);
+    const uint32_t c = cell_host(x, l);
+    const double sub = eval_suffix_host(D, S - 1, rb, reff - (l - 1), blk + blk_off(S, l, rs) + (size_t)c * blk_size(S - 1, rb), x01);
+    out = l == 1 ? sub : std::fma(hat_host(x, l, c), sub, out);
+  }
+  return out;
+}
+
 }  // namespace
 
 int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm, const double *coefs,
@@ -55,28 +89,78 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
   if (D < 4) return no("D < 4");
   if (D - 3 > 15) return no("D > 18");
   if (N <= 0) return no("empty grid");
-  const int K = D - 3;  // prefix dimensions 0..K-1; A = K, B = K+1, C = K+2
+  const int K = D - 3;  // longest prefix: dimensions 0..K-1; A = K, B = K+1, C = K+2
+  const uint64_t cap = (uint64_t)kBlkTileCoefs - 2;  // a tile window is aligned down / up to even slots
 
-  // 1. prefix level vectors and their suffix budgets
-  std::map<Key, PrefixInfo> pre;
+  // 1. full-length prefix level vectors and the budgets of their 3-D suffixes
+  std::map<Key, int> pre;  // -> max sum(l-1) over dimensions A, B, C
   {
     Key cur;
-    PrefixInfo *pi = nullptr;
+    int *pr = nullptr;
     for (int64_t k = 0; k < N; ++k) {
       const uint8_t *L = lv + (size_t)perm[k] * D;
-      if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
+      if (!pr || std::memcmp(cur.data(), L, (size_t)K) != 0) {
         cur.assign(L, L + K);
-        pi = &pre[cur];
+        pr = &pre.emplace(cur, -1).first->second;
       }
       const int eS = (L[K] - 1) + (L[K + 1] - 1) + (L[K + 2] - 1);
       if (eS > kBlkMaxBudget) return no("suffix budget > 7");
-      pi->r = std::max(pi->r, eS);
+      *pr = std::max(*pr, eS);
     }
   }
-  // 2. closure under "reset the last non-trivial dimension": the records a walk restarts from must exist
+  // 2. records. A group of prefix vectors that share their first d components and leaves a small budget
+  //    below them becomes ONE record with a compiled suffix of S = D - d dimensions (shallowest d first);
+  //    every other prefix vector is a record of its own with the 3-D suffix.
+  std::map<Key, Rec> recs;         // keyed by the prefix padded with ones: lexicographic = depth-first order
+  std::map<Key, Key> cover;        // full prefix vector -> key of the record that holds its nodes
+  {
+    std::vector<const Key *> keys;
+    std::vector<int> rr;
+    for (auto &kv : pre) { keys.push_back(&kv.first); rr.push_back(kv.second); }
+    std::vector<char> done(keys.size(), 0);
+    const int maxS = max_compiled_dims();
+    for (int d = std::max(0, D - maxS); d < K; ++d) {
+      const int S = D - d;
+      size_t g0 = 0;
+      while (g0 < keys.size()) {
+        size_t g1 = g0 + 1;
+        while (g1 < keys.size() && std::memcmp(keys[g1]->data(), keys[g0]->data(), (size_t)d) == 0) ++g1;
+        if (!done[g0]) {  // groups nest: either every member is free or the whole group is already held
+          int rsub = 0, pb = 0;
+          for (size_t m = g0; m < g1; ++m) {
+            int e = rr[m];
+            for (int j = d; j < K; ++j) e += (*keys[m])[(size_t)j] - 1;
+            rsub = std::max(rsub, e);
+          }
+          for (int j = 0; j < d; ++j) pb += blk_bits((*keys[g0])[(size_t)j]);
+          if (rsub >= 1 && rsub <= blk_max_r(S) && pb <= 24 && (((uint64_t)blk_size(S, rsub)) << pb) <= cap) {
+            Key key(keys[g0]->begin(), keys[g0]->begin() + d);
+            key.resize((size_t)K, 1);
+            Rec R;
+            R.depth = d;
+            R.S = S;
+            R.r = rsub;
+            recs[key] = R;
+            for (size_t m = g0; m < g1; ++m) { done[m] = 1; cover[*keys[m]] = key; }
+          }
+        }
+        g0 = g1;
+      }
+    }
+    for (size_t m = 0; m < keys.size(); ++m)
+      if (!done[m]) {
+        Rec R;
+        R.depth = K;
+        R.S = 3;
+        R.r = rr[m];
+        recs[*keys[m]] = R;
+        cover[*keys[m]] = *keys[m];
+      }
+  }
+  // 3. closure under "reset the last non-trivial dimension": the records a walk restarts from must exist
   {
     std::vector<Key> todo;
-    for (auto &kv : pre) todo.push_back(kv.first);
+    for (auto &kv : recs) todo.push_back(kv.first);
     while (!todo.empty()) {
       Key p = todo.back();
       todo.pop_back();
@@ -84,25 +168,23 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       for (uint8_t l : p) triv = triv && l == 1;
       if (triv) continue;
       Key q = parent_of(p);
-      auto it = pre.find(q);
-      if (it == pre.end()) {
-        pre[q] = PrefixInfo();
+      auto it = recs.find(q);
+      if (it == recs.end()) {
+        Rec R;  // stage-only record
+        R.depth = K;
+        it = recs.emplace(q, R).first;
         todo.push_back(q);
-        it = pre.find(q);
       }
       it->second.parent_of = true;
     }
-    if (pre.find(Key((size_t)K, 1)) == pre.end()) pre[Key((size_t)K, 1)] = PrefixInfo();
+    if (recs.find(Key((size_t)K, 1)) == recs.end()) { Rec R; R.depth = K; recs[Key((size_t)K, 1)] = R; }
   }
-  // 3. geometry, storage
+  // 4. geometry, storage
   uint64_t total = 0;
   int max_slot = 0;
-  const uint64_t cap = (uint64_t)kBlkTileCoefs - 2;  // a tile window is aligned down / up to even slots
-  for (auto &kv : pre) {
+  for (auto &kv : recs) {
     const Key &p = kv.first;
-    PrefixInfo &I = kv.second;
-    I.pb = I.used = I.nt = 0;
-    I.k0 = 0;
+    Rec &I = kv.second;
     for (int d = 0; d < K; ++d) {
       const int l = p[(size_t)d];
       if (l > 1) { I.nt++; I.k0 = d; }
@@ -111,11 +193,11 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
     }
     if (I.pb > 24) return no("prefix position needs more than 24 bits");
     if (I.r >= 0) {
-      const uint64_t s3 = ((uint64_t)blk_size3(I.r)) << I.pb;
-      if (s3 <= cap) {
+      const uint64_t sz = ((uint64_t)blk_size(I.S, I.r)) << I.pb;
+      if (sz <= cap) {
         I.cbase = (uint32_t)total;
-        total += s3;
-      } else {
+        total += sz;
+      } else {  // only S = 3 records can be too large (deeper suffixes were admitted by size)
         I.split = true;
         for (int lA = 1; lA <= I.r + 1; ++lA) {
           const uint64_t s2 = ((uint64_t)blk_size2(I.r - (lA - 1))) << (I.pb + blk_bits(lA));
@@ -140,30 +222,36 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
     for (int64_t n = 0; n < N; ++n) synth[(size_t)n] = std::sin(1.0 + 0.37 * (double)n) + 0.25;
     coefs = synth.data();
   }
-  // 4. node slots
+  // 5. node slots
   {
     Key cur;
-    const PrefixInfo *pi = nullptr;
+    const Rec *pi = nullptr;
     for (int64_t k = 0; k < N; ++k) {
       const int64_t n = perm[k];
       const uint8_t *L = lv + (size_t)n * D;
       const uint32_t *C = cells + (size_t)n * D;
       if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
         cur.assign(L, L + K);
-        pi = &pre[cur];
+        pi = &recs[cover[cur]];
       }
       uint64_t O = 0;
-      for (int d = 0; d < K; ++d) O = (O << blk_bits(L[d])) | C[d];
-      const int lA = L[K], lB = L[K + 1], lC = L[K + 2];
-      const int rA = pi->r - (lA - 1), rB = rA - (lB - 1);
-      const uint64_t in2 = (uint64_t)blk_offB(lB, rA) + (uint64_t)C[K + 1] * blk_n1(rB) + blk_off1(lC) + C[K + 2];
+      for (int d = 0; d < pi->depth; ++d) O = (O << blk_bits(L[d])) | C[d];
       uint64_t slot;
+      int rr = pi->r;
       if (!pi->split) {
-        slot = pi->cbase + O * blk_size3(pi->r) + blk_offA(lA, pi->r) + (uint64_t)C[K] * blk_size2(rA) + in2;
+        slot = pi->cbase + O * blk_size(pi->S, pi->r);
+        for (int j = pi->S; j >= 3; --j) {  // compiled dimensions above the 2-D block, outermost first
+          const int l = L[D - j];
+          slot += blk_off(j, l, rr) + (uint64_t)C[D - j] * blk_size(j - 1, rr - (l - 1));
+          rr -= l - 1;
+        }
       } else {
-        const uint64_t O2 = (O << blk_bits(lA)) | C[K];
-        slot = pi->cbaseA[lA - 1] + O2 * blk_size2(rA) + in2;
+        const int lA = L[K];
+        rr -= lA - 1;
+        slot = pi->cbaseA[lA - 1] + ((O << blk_bits(lA)) | C[K]) * blk_size2(rr);
       }
+      const int lB = L[K + 1], lC = L[K + 2];
+      slot += (uint64_t)blk_offB(lB, rr) + (uint64_t)C[K + 1] * blk_n1(rr - (lB - 1)) + blk_off1(lC) + C[K + 2];
       if (slot >= total || out.bslot_of_node[(size_t)n] != -1) {  // duplicates were rejected before: packer bug
         err = "internal error: block slot out of range or assigned twice";
         return ASG_ESTATE;
@@ -172,7 +260,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       out.bcoef[(size_t)slot] = coefs ? coefs[n] : 0.0;
     }
   }
-  // 5. records in lexicographic order + the slot span each one reads
+  // 6. records in lexicographic order + the slot span each one reads
   std::vector<uint32_t> lo, hi;
   auto stage_of = [](BlockRec &q, int slot, int k0, int l, bool save, int used) {
     q.slot = (uint32_t)slot;
@@ -185,9 +273,9 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
   };
   Key prev_parent;
   int prev_k0 = -1;
-  for (auto &kv : pre) {
+  for (auto &kv : recs) {
     const Key &p = kv.first;
-    const PrefixInfo &I = kv.second;
+    const Rec &I = kv.second;
     BlockRec q{};
     const int l0 = I.nt ? p[(size_t)I.k0] : 1;
     stage_of(q, I.nt ? I.nt - 1 : 0, I.k0, l0, I.parent_of && I.nt, I.used);
@@ -200,11 +288,11 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       out.brec.push_back(q);
       lo.push_back(0); hi.push_back(0);
     } else if (!I.split) {
-      q.sw |= kBrS3 + (uint32_t)I.r;
+      q.sw |= (I.S == 3 ? kBrS3 : (I.S == 4 ? kBrS4 : (I.S == 5 ? kBrS5 : kBrS6))) + (uint32_t)I.r;
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
-      hi.push_back(I.cbase + (blk_size3(I.r) << I.pb));
+      hi.push_back(I.cbase + (blk_size(I.S, I.r) << I.pb));
     } else {
       for (int lA = 1; lA <= I.r + 1; ++lA) {
         BlockRec s = q;
@@ -222,7 +310,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       prev_k0 = -1;  // the next prefix record follows S2 records of another dimension
     }
   }
-  // 6. tiles: consecutive records whose spans fit one coefficient buffer
+  // 7. tiles: consecutive records whose spans fit one coefficient buffer
   {
     size_t j = 0;
     const size_t nrec = out.brec.size();
@@ -259,7 +347,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
     }
   }
   out.blk_ok = true;
-  // 7. self-check: the walk over the records must reproduce the direct sum over the nodes
+  // 8. self-check: the walk over the records must reproduce the direct sum over the nodes
   if (selfcheck) {
     uint64_t s = 0x9E3779B97F4A7C15ull;
     auto rnd = [&]() {
@@ -299,25 +387,22 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
 }
 
 // The walk of asg_kernels_block.cu, one point, plain loops: records in order, one stage per record from
-// the saved slot, then the regular suffix of budget min(r, rem - used) with the layout of asg_block.h.
+// the saved slot, then the compiled suffix of budget min(r, rem - used) with the layout of asg_block.h.
 double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) {
-  const int K = D - 3;
   double P[kBlkMaxSlots + 2];
   uint64_t O[kBlkMaxSlots + 2];
   P[0] = 1.0;
   O[0] = 0;
   double acc = 0.0;
-  const double xA = x01[K], xB = x01[K + 1], xC = x01[K + 2];
   double Pin = 1.0, xin = 0.0;
-  uint64_t Oin = 0;
   for (const BlockRec &q : pk.brec) {
     const int used = (int)(q.sw >> kBrUsedShift);
     if (used > rem) continue;
     if (!(q.sw & kBrSameIn)) {  // siblings keep the input of the previous record in registers
       Pin = P[q.slot];
-      Oin = O[q.slot];
       xin = x01[q.k0];
     }
+    const uint64_t Oin = O[q.slot];
     double s;
     {
       const uint64_t bits = (uint64_t)q.s_hi << 32;
@@ -330,30 +415,11 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
     if (q.sw & kBrSave) { P[q.slot + 1] = cur; O[q.slot + 1] = cO; }
     const uint32_t code = q.sw & 0xffu;
     if (code >= kBrNone) continue;
-    const bool s2 = code >= kBrS2;
-    const int rs = (int)(code & 7u);
+    const int S = code >= kBrS6 ? 6 : (code >= kBrS5 ? 5 : (code >= kBrS4 ? 4 : (code >= kBrS2 ? 2 : 3)));
+    const int rs = (int)(code & (S >= 4 ? 3u : 7u));
     const int reff = std::min(rs, rem - used);
-    const double *chunk = pk.bcoef.data() + q.cbase + cO * (s2 ? blk_size2(rs) : blk_size3(rs));
-    double inner3 = 0.0;
-    for (int lA = 1; lA <= (s2 ? 1 : reff + 1); ++lA) {
-      const int rA = rs - (lA - 1), reffA = reff - (lA - 1);
-      const uint32_t cA = cell_host(xA, lA);
-      const double *blk2 = s2 ? chunk : chunk + blk_offA(lA, rs) + (size_t)cA * blk_size2(rA);
-      double accA = 0.0;
-      for (int lB = 1; lB <= reffA + 1; ++lB) {
-        const int rB = rA - (lB - 1), reffB = reffA - (lB - 1);
-        const uint32_t cB = cell_host(xB, lB);
-        const double *pole = blk2 + blk_offB(lB, rA) + (size_t)cB * blk_n1(rB);
-        double inner = pole[0];
-        for (int lC = 2; lC <= reffB + 1; ++lC) {
-          const uint32_t cC = cell_host(xC, lC);
-          inner = std::fma(pole[blk_off1(lC) + cC], hat_host(xC, lC, cC), inner);
-        }
-        accA = lB == 1 ? inner : std::fma(hat_host(xB, lB, cB), inner, accA);
-      }
-      inner3 = lA == 1 ? accA : std::fma(hat_host(xA, lA, cA), accA, inner3);
-    }
-    acc = std::fma(cur, inner3, acc);
+    const double *chunk = pk.bcoef.data() + q.cbase + cO * blk_size(S, rs);
+    acc = std::fma(cur, eval_suffix_host(D, S, rs, reff, chunk, x01), acc);
   }
   return acc;
 }
