@@ -275,6 +275,8 @@ int repack(asg_grid *g) {
   I.block = g->blk_ok ? 1 : 0;
   I.block_slots = g->blk_ok ? (int64_t)pk.bcoef.size() - 2 : 0;
   I.block_records = g->blk_ok ? (int64_t)pk.brec.size() : 0;
+  I.block_tiles = g->blk_ok ? (int64_t)pk.btiles.size() : 0;
+  I.block_stack = g->blk_ok ? pk.blk_slots : 0;
   if (g->blk_ok) I.device_bytes += (int64_t)(g->d_bcoef.bytes() + g->d_brec.bytes() + g->d_btiles.bytes());
   return ASG_OK;
 }
@@ -1043,6 +1045,8 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->block = (pk.canonical && pk.blk_ok) ? 1 : 0;
   info->block_slots = info->block ? (int64_t)pk.bcoef.size() - 2 : 0;
   info->block_records = info->block ? (int64_t)pk.brec.size() : 0;
+  info->block_tiles = info->block ? (int64_t)pk.btiles.size() : 0;
+  info->block_stack = info->block ? pk.blk_slots : 0;
   if (!pk.canonical) t_err = pk.why;
   else if (!pk.blk_ok) t_err = "no BLOCK layout: " + pk.blk_why;
   return ASG_OK;

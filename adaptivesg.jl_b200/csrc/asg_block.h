@@ -63,8 +63,20 @@ static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "
 // Deeper compiled suffixes for prefixes that leave little budget: half of the prefix vectors of a regular grid
 // leave r = 0 (one term), a quarter r = 1. Where a SHORTER prefix (S = 4, 5, 6 compiled dimensions) still has a
 // small budget, ONE record with a compiled S-dimensional suffix replaces all the records below it.
-constexpr int kBlkMaxS = 6;
-ASG_HD constexpr int blk_max_r(int S) { return S == 3 ? kBlkMaxBudget : (S == 4 ? 3 : ((S == 5 || S == 6) ? 2 : -1)); }
+#ifndef ASG_BLK_R4
+#define ASG_BLK_R4 4  // largest budget compiled for a 4-D suffix (70 terms)
+#define ASG_BLK_R5 3  // 5-D (56 terms)
+#define ASG_BLK_R6 3  // 6-D (84 terms)
+#define ASG_BLK_R7 2  // 7-D (36 terms)
+#endif
+#ifndef ASG_BLK_R8
+#define ASG_BLK_R8 0
+#endif
+constexpr int kBlkMaxS = ASG_BLK_R8 > 0 ? 8 : 7;
+ASG_HD constexpr int blk_max_r(int S) {
+  return S == 3 ? kBlkMaxBudget
+                : (S == 4 ? ASG_BLK_R4 : (S == 5 ? ASG_BLK_R5 : (S == 6 ? ASG_BLK_R6 : (S == 7 ? ASG_BLK_R7 : (S == 8 ? ASG_BLK_R8 : -1)))));
+}
 
 // One 32-byte record per prefix level vector, in lexicographic (depth-first) order, stored pre-decoded
 // (one field per word: the kernel does no shifting or masking on its critical path). Every record but
@@ -73,7 +85,7 @@ ASG_HD constexpr int blk_max_r(int S) { return S == 3 ? kBlkMaxBudget : (S == 4 
 // non-trivial dimensions before k0).
 struct __align__(16) BlockRec {
   uint32_t cbase;  // first coefficient slot of the record (chunk 0)
-  uint32_t sw;     // bits 0..7: kBrS3 + r | kBrS2 + r | kBrNone (compiled suffix to run); 8..15: flags; 16..31: used
+  uint32_t sw;     // bits 0..7: blk_code(S, r) | kBrNone (compiled suffix to run); 8..15: flags; 16..31: used
   uint32_t slot;   // stack slot to restart from
   uint32_t k0;     // stage dimension
   uint32_t b;      // stage: cell bits of the level
@@ -82,12 +94,10 @@ struct __align__(16) BlockRec {
   uint32_t odd;    // stage: 1 if level > 2 (index = 2*cell + 1)
 };
 static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words");
-constexpr uint32_t kBrS3 = 0u;    // sw = kBrS3 + r: 3-D suffix of budget r = 0..7
-constexpr uint32_t kBrS2 = 8u;    // sw = kBrS2 + r: 2-D suffix (dimension A is this record's stage or at level 1)
-constexpr uint32_t kBrS4 = 16u;   // sw = kBrS4 + r: 4-D suffix, r = 1..3   (prefix = dimensions 0..D-5)
-constexpr uint32_t kBrS5 = 20u;   // sw = kBrS5 + r: 5-D suffix, r = 1..2
-constexpr uint32_t kBrS6 = 24u;   // sw = kBrS6 + r: 6-D suffix, r = 1..2
-constexpr uint32_t kBrNone = 31u; // stage only (no nodes under this prefix)
+// suffix code = 8 * S + r: S = 3 the 3-D suffix (r = 0..7); S = 2 the 2-D suffix of a split record (dimension A is
+// the record's stage or at level 1); S = 4..7 deeper suffixes with r = 1..blk_max_r(S)
+ASG_HD constexpr uint32_t blk_code(int S, int r) { return (uint32_t)(8 * S + r); }
+constexpr uint32_t kBrNone = 255u;  // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
 constexpr uint32_t kBrSameIn = 1u << 9;  // same input slot and stage dimension as the previous record (siblings)
 constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2: including dimension A): depth mask

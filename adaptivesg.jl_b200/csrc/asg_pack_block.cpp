@@ -288,7 +288,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       out.brec.push_back(q);
       lo.push_back(0); hi.push_back(0);
     } else if (!I.split) {
-      q.sw |= (I.S == 3 ? kBrS3 : (I.S == 4 ? kBrS4 : (I.S == 5 ? kBrS5 : kBrS6))) + (uint32_t)I.r;
+      q.sw |= blk_code(I.S, I.r);
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
@@ -301,7 +301,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
           stage_of(s, I.nt, K, lA, false, I.used + lA - 1);
           if (lA > 2) s.sw |= kBrSameIn;
         }
-        s.sw |= kBrS2 + (uint32_t)rA;
+        s.sw |= blk_code(2, rA);
         s.cbase = I.cbaseA[lA - 1];
         out.brec.push_back(s);
         lo.push_back(s.cbase);
@@ -414,9 +414,8 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
     const uint64_t cO = (Oin << q.b) | cell;
     if (q.sw & kBrSave) { P[q.slot + 1] = cur; O[q.slot + 1] = cO; }
     const uint32_t code = q.sw & 0xffu;
-    if (code >= kBrNone) continue;
-    const int S = code >= kBrS6 ? 6 : (code >= kBrS5 ? 5 : (code >= kBrS4 ? 4 : (code >= kBrS2 ? 2 : 3)));
-    const int rs = (int)(code & (S >= 4 ? 3u : 7u));
+    if (code == kBrNone) continue;
+    const int S = (int)(code >> 3), rs = (int)(code & 7u);
     const int reff = std::min(rs, rem - used);
     const double *chunk = pk.bcoef.data() + q.cbase + cO * blk_size(S, rs);
     acc = std::fma(cur, eval_suffix_host(D, S, rs, reff, chunk, x01), acc);

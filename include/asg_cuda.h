@@ -74,6 +74,8 @@ typedef struct asg_grid_info_t {
   int64_t block;           /* 1: BLOCK layout present (compiled walk of the last three dimensions)  */
   int64_t block_slots;     /* its coefficient slots incl. zero padding                              */
   int64_t block_records;   /* its prefix records                                                    */
+  int64_t block_tiles;     /* shared-memory tiles the walk streams per batch of points              */
+  int64_t block_stack;     /* saved prefix products per point the walk keeps in shared memory       */
 } asg_grid_info_t;
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -25,7 +25,7 @@ def _pack_info(asg, levels, indices):
 def test_block_layout_regular_grids(asg):
     """asg_pack_info runs the packer's self-check (host model of the kernel's walk against the direct sum
     over the nodes, with and without a depth mask) for every grid of at most 50 000 nodes."""
-    for D, depth, ml, nrec in [(4, 6, 6, 6), (5, 5, 5, 9), (6, 7, (6, 7, 8, 9, 10, 11), 52), (10, 5, 5, 109),
+    for D, depth, ml, nrec in [(4, 6, 6, 6), (5, 5, 5, 5), (6, 7, (6, 7, 8, 9, 10, 11), 37), (10, 5, 5, 56),
                                (7, 4, (2, 3, 4, 4, 2, 3, 4), None), (12, 3, 3, None)]:
         G = asg.SparseGridInterpolant(D)
         asg.rsg(G, depth, ml)
@@ -37,12 +37,13 @@ def test_block_layout_regular_grids(asg):
             assert info["block_records"] == nrec          # prefix vectors, minus those merged into 4..6-D suffixes
         else:
             assert len(G) <= info["block_slots"] <= 2 * len(G) + 4096
-    # the benchmark grid: C(14, 7) = 3432 prefix vectors in 1430 records (small budgets take 4..6-D suffixes), no padding
+    # the benchmark grid: C(14, 7) = 3432 prefix vectors in 1003 records (small budgets take 4..7-D suffixes), no padding
     os.environ["ASG_PACK_SELFCHECK"] = "1"
     G = asg.SparseGridInterpolant(10)
     asg.rsg(G, 8, 8)
     rc, info, msg = _pack_info(asg, G.levels, G.indices)
-    assert rc == 0 and info["block"] == 1 and info["block_slots"] == 652065 and info["block_records"] == 1430, msg
+    assert rc == 0 and info["block"] == 1 and info["block_slots"] == 652065 and info["block_records"] == 1003, msg
+    assert info["block_stack"] == 5 and info["block_tiles"] == 253
     # outside the layout's limits: D < 4, suffix levels > 8
     for D, depth in [(3, 5), (4, 10)]:
         G = asg.SparseGridInterpolant(D)
