@@ -68,23 +68,24 @@ def fp64_op_counts(levels):
     return instr, flops, leaves
 
 
-def fp64_op_counts_block(levels):
-    """FP64 work of the BLOCK walk (asg_kernels_block.cu) for ONE point, counted from the level vectors.
-    One record per distinct prefix (dims 0..D-4): stage DMUL (x*2^b) + DADD (int->double) + DFMA (t) + DADD (1-|t|)
-    + DMUL (prefix product) and the record's DFMA into the accumulator = 6 instr / 8 flop. Per node of dimension
-    D-3 with level > 1: DADD + DFMA + DADD (hat on the fly) + DFMA (Horner) = 4 instr / 6 flop. Per pole with
-    l_{D-2} > 1 and per subspace with l_{D-1} > 1: one DFMA. Register tables: 2 dims x 3 levels x 3 instr once per
-    point. The DFMA count equals the number of subspaces. Returns (fp64 instructions, flops, subspaces)."""
+def fp64_op_counts_block(levels, records):
+    """FP64 work of the BLOCK walk (asg_kernels_block.cu) for ONE point, counted from the level vectors and the
+    number of records the packer formed. Per record: stage DMUL (x*2^b) + DADD (int->double) + DFMA (t) + DADD (1-|t|)
+    + DMUL (prefix product) and the record's DFMA into the accumulator = 6 instr / 8 flop. Every other trie node of
+    dimensions 0..D-3 with level > 1 is compiled: DADD + DFMA + DADD (hat on the fly) + DFMA (Horner) = 4 instr /
+    6 flop (plus DMUL x*2^b where the cell key is not in a register: dimensions above D-3). Per pole with l_{D-2} > 1
+    and per subspace with l_{D-1} > 1: one DFMA. Register tables: 2 dims x 3 levels x 3 instr once per point.
+    Returns (fp64 instructions, flops, subspaces)."""
     lv = np.unique(levels, axis=0)
     D = lv.shape[1]
     leaf_fma = int(np.count_nonzero(lv[:, -1] > 1))
     poles = np.unique(lv[:, :-1], axis=0)
     pole_fma = int(np.count_nonzero(poles[:, -1] > 1))
-    l8 = np.unique(lv[:, :-2], axis=0)
-    l8_nt = int(np.count_nonzero(l8[:, -1] > 1))
-    recs = len(np.unique(lv[:, :-3], axis=0))
-    instr = leaf_fma + pole_fma + 4 * l8_nt + 6 * recs + 18
-    flops = 2 * (leaf_fma + pole_fma) + 6 * l8_nt + 8 * recs + 2 * 3 * 4
+    nt_A = int(np.count_nonzero(np.unique(lv[:, :-2], axis=0)[:, -1] > 1))   # nodes of dimension D-3 with level > 1
+    nt_pre = sum(int(np.count_nonzero(np.unique(lv[:, :k], axis=0)[:, -1] > 1)) for k in range(1, D - 2))
+    compiled_pre = nt_pre - (records - 1)          # prefix nodes that are not a record's stage (deeper suffixes)
+    instr = leaf_fma + pole_fma + 4 * nt_A + 5 * compiled_pre + 6 * records + 18
+    flops = 2 * (leaf_fma + pole_fma) + 6 * nt_A + 7 * compiled_pre + 8 * records + 2 * 3 * 4
     return instr, flops, len(lv)
 
 
@@ -360,7 +361,7 @@ def main():
     fma_rate = C.c_double()
     asg._capi.check(lib.asg_measure_fp64_peak(C.byref(fma_rate)))
     block = bool(info.get("block")) and os.environ.get("ASG_EVAL_KERNEL", "b")[0] == "b"
-    instr, flops, leaves = (fp64_op_counts_block if block else fp64_op_counts)(G.levels)
+    instr, flops, leaves = fp64_op_counts_block(G.levels, int(info["block_records"])) if block else fp64_op_counts(G.levels)
     kname = "k_eval_block<2,false,512>" if block else f"k_eval_stream<{D},R,false>"
     prof_name = "r01b_final_eval_block_d10_summary.json" if block else "r01_final_eval_stream_d10_summary.json"
     k_ms = statistics.median(kern_ms)
