@@ -363,7 +363,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
         BlkStaged<R> st;
         blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, in, st);
 #define BLK_CASE(S, RS) \
-  case blk_code(S, RS): if constexpr (RS <= blk_max_r(S)) blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
+  case blk_code(S, RS): if constexpr (S <= 3 || RS <= blk_max_r(S)) blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
         // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
         // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
         const uint32_t code = st.sw & 0xffu;

@@ -108,6 +108,14 @@ def _grids(oracle):
         OG.coefs = rng.standard_normal(len(OG.levels)) * 2.0 ** (-OG.depths.astype(float) / 2)
         OG.fvals = np.zeros(len(OG.levels))
         out.append(OG)
+    # 3-D chunks larger than a shared-memory tile: split into S2 records (level of dimension D-3 as the stage)
+    OG = oracle.OracleGrid(4)
+    OG.rsg(9, 9)
+    keep = np.sum(OG.levels[:, 1:] - 1, axis=1) <= 7
+    OG.levels, OG.indices, OG.depths = OG.levels[keep], OG.indices[keep], OG.depths[keep]
+    OG.coefs = rng.standard_normal(len(OG.levels))
+    OG.fvals = np.zeros(len(OG.levels))
+    out.append(OG)
     return out
 
 
@@ -119,6 +127,8 @@ def test_block_walk_parity(asg, oracle):
         G = _mirror(asg, OG)
         info = G.info()
         assert info["block"] == 1, (D, len(OG.levels))
+        if D == 4 and len(OG.levels) == 15489:
+            assert info["block_records"] == 16            # 9 prefix levels, the level-2 one split along dimension D-3
         X = np.vstack([OG.lb + (OG.ub - OG.lb) * rng.random((3000, D)), _edge_points(D, OG.lb, OG.ub, rng)])
         want, sc = OG.evaluate(X, return_abssum=True)
         L = int(rng.integers(1, int(OG.depths.max()) + 1))
