@@ -204,3 +204,30 @@ def test_block_walk_train_cfg4(asg, oracle):
     assert G.info()["block"] == 1
     assert np.array_equal(G.levels, OG.levels) and np.array_equal(G.indices, OG.indices)
     assert np.max(np.abs(G.coefs - OG.coefs)) < 1e-13
+
+
+@pytest.mark.gpu
+def test_block_walk_adapt_cfg4(asg):
+    """adapt! on BASELINE configs[3] (D = 6, depth 13, tol 3e-3): the grids it grows are irregular (zero padding,
+    stage-only parent records, split records); every level's candidate surpluses come from the BLOCK walk while the
+    layout applies. The node count is the one SURVEY.md section 8 derives (19 929, converged at depth 12) and the
+    three engines agree on the final grid."""
+    def f(X):
+        return np.sum(np.sin(2 * np.pi * X), axis=1)
+    G = asg.SparseGridInterpolant(6)
+    asg.train(G, f, 7, tuple(range(6, 12)), vectorized=True)
+    assert len(G) == 15089 and G.info()["block"] == 1
+    log = []
+    asg.adapt(G, f, 13, tol=3e-3, verbose=False, vectorized=True, log=log)
+    assert len(G) == 19929, log
+    rng = np.random.default_rng(4)
+    X = np.vstack([rng.random((20000, 6)), rng.integers(0, 4097, size=(20000, 6)) / 4096.0])
+    G.set_path("sweep")
+    want = G.evaluate(X)
+    for path in ("stream", "block"):
+        try:
+            G.set_path(path)
+        except asg.AsgError:
+            assert path == "block"       # the final grid may need more padding than the layout accepts
+            continue
+        assert np.max(np.abs(G.evaluate(X) - want)) < 5e-14, path
