@@ -13,12 +13,12 @@ Layout: ``csrc/`` CUDA kernels + C ABI (-> ``lib/libasg_cuda.so``), ``_capi.py``
 from . import _capi
 from ._capi import AsgError, InvalidNodeError, LIB_PATH, init, launch_count
 from .interpolant import (SparseGridInterpolant, adapt, allindices_of_level, basis, child, coefficients,
-                          dehierarchization_matrix, deserialize, hierarchization_matrix, hierarchize, isbig2add, isvalid,
+                          dehierarchization_matrix, deserialize, extrapolate, hierarchization_matrix, hierarchize, isbig2add, isvalid,
                           maxlevels, nodedepth, rsg, serialize, stack, train)
 
 __all__ = [
     "SparseGridInterpolant", "rsg", "train", "adapt", "coefficients", "basis", "dehierarchization_matrix",
     "hierarchization_matrix", "serialize", "deserialize", "maxlevels", "stack", "nodedepth", "isvalid",
-    "allindices_of_level", "child", "isbig2add", "hierarchize", "AsgError", "InvalidNodeError", "init", "launch_count",
+    "allindices_of_level", "child", "isbig2add", "hierarchize", "extrapolate", "AsgError", "InvalidNodeError", "init", "launch_count",
     "LIB_PATH",
 ]

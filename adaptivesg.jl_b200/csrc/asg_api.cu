@@ -117,6 +117,12 @@ struct asg_grid {
   DevBuf<long long> s_i64a, s_i64b;
   DevBuf<double> s_tmp, s_tmp2;
   DevBuf<int> s_flag;
+  // adapt! candidate generation (asg_kernels_adapt.cu): the unique children of the last asg_children call
+  DevBuf<long long> c_PL, c_PI, c_CL, c_CI, c_OL, c_OI;
+  DevBuf<unsigned char> c_valid;
+  DevBuf<int> c_table;
+  DevBuf<unsigned int> c_flags, c_sums;
+  int64_t ch_n = -1, ch_generation = -1;
   // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
   DevBuf<uint32_t> s_key[2], s_key2[2], s_idx[2], s_perm[2];
   DevBuf<unsigned char> s_sorttmp[2];
@@ -543,6 +549,8 @@ int32_t asg_grid_destroy(asg_grid *g) {
         g->s_key[s].release(); g->s_key2[s].release(); g->s_idx[s].release(); g->s_perm[s].release(); g->s_sorttmp[s].release();
         if (g->sort_ev[s]) cudaEventDestroy(g->sort_ev[s]);
       }
+      g->c_PL.release(); g->c_PI.release(); g->c_CL.release(); g->c_CI.release(); g->c_OL.release(); g->c_OI.release();
+      g->c_valid.release(); g->c_table.release(); g->c_flags.release(); g->c_sums.release();
       g->s_i64a.release(); g->s_i64b.release(); g->s_tmp.release(); g->s_tmp2.release(); g->s_flag.release();
     }
   }
@@ -886,6 +894,102 @@ int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const doub
     // alpha is now on the host too: keep the host mirror, the finite flag and the device slots in step
     return scatter_coefs_locked(g, n, idx, 0, alpha, g->s_out[0].p);
   }
+  return ASG_OK;
+}
+
+// ---- adapt! candidate generation ----------------------------------------------------------------
+int32_t asg_children(asg_grid *g, int64_t depth, int64_t *n_parents, int64_t *n_candidates, int64_t *n_unique) {
+  if (!g || !n_unique) return set_err(ASG_EINVAL, "null argument");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
+  const int D = g->D;
+  std::vector<long long> PL, PI;
+  for (int64_t n = 0; n < g->N; ++n) {  // parents = nodes of that depth (src/train.jl:316-318), in node order
+    int64_t dsum = 0;
+    for (int d = 0; d < D; ++d) dsum += g->levels[(size_t)n * D + d];
+    if (dsum - D + 1 != depth) continue;
+    for (int d = 0; d < D; ++d) {
+      const int64_t l = g->levels[(size_t)n * D + d], i = g->indices[(size_t)n * D + d];
+      if (l < 1 || (l == 2 && i != 0 && i != 2))  // child() throws on these, src/math.jl:919, 949
+        return set_err(ASG_EINVALID_NODE, "invalid level-index pair among the parents");
+      PL.push_back(l);
+      PI.push_back(i);
+    }
+  }
+  const int64_t n_p = (int64_t)PL.size() / D, n_cand = n_p * 2 * D;
+  if (n_parents) *n_parents = n_p;
+  if (n_candidates) *n_candidates = n_cand;
+  *n_unique = 0;
+  g->ch_n = 0;
+  g->ch_generation = g->info.generation;
+  if (n_cand == 0) return ASG_OK;
+  if (n_cand >= ((int64_t)1 << 30)) return set_err(ASG_EUNSUPPORTED, "more than 2^30 candidates in one level");
+  int64_t tsize = 1024;
+  while (tsize < 2 * n_cand) tsize <<= 1;
+  const int64_t nblk = (n_cand + 1023) / 1024;
+  if (int rc = g->c_PL.reserve((size_t)n_p * D)) return rc;
+  if (int rc = g->c_PI.reserve((size_t)n_p * D)) return rc;
+  if (int rc = g->c_CL.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = g->c_CI.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = g->c_OL.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = g->c_OI.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = g->c_valid.reserve((size_t)n_cand)) return rc;
+  if (int rc = g->c_table.reserve((size_t)tsize)) return rc;
+  if (int rc = g->c_flags.reserve((size_t)n_cand)) return rc;
+  if (int rc = g->c_sums.reserve((size_t)nblk + 1)) return rc;
+  cudaStream_t st = ctx.stream;
+  CK(cudaMemcpyAsync(g->c_PL.p, PL.data(), PL.size() * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(g->c_PI.p, PI.data(), PI.size() * 8, cudaMemcpyHostToDevice, st));
+  int64_t l = 0;
+  unsigned int *total = g->c_sums.p + nblk;
+  CK(launch_children(D, n_p, g->c_PL.p, g->c_PI.p, g->c_CL.p, g->c_CI.p, g->c_valid.p, g->c_table.p, tsize, g->c_flags.p,
+                     g->c_sums.p, total, g->c_OL.p, g->c_OI.p, st, &l));
+  bump(l);
+  unsigned int nu = 0;
+  CK(cudaMemcpyAsync(&nu, total, sizeof nu, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  g->ch_n = (int64_t)nu;
+  *n_unique = g->ch_n;
+  return ASG_OK;
+}
+
+int32_t asg_children_fetch(asg_grid *g, int64_t n, int64_t *levels, int64_t *indices, int64_t sn, int64_t sd, double *X,
+                           int64_t sp, int64_t sdim) {
+  if (!g || (n > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "null argument");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (g->ch_n < 0 || g->ch_generation != g->info.generation)
+    return set_err(ASG_ESTATE, "asg_children has not been called on this state of the grid");
+  if (n != g->ch_n) return set_err(ASG_EINVAL, "n differs from the count asg_children returned");
+  if (n == 0) return ASG_OK;
+  const int D = g->D;
+  cudaStream_t st = ctx.stream;
+  std::vector<long long> L((size_t)n * D), I((size_t)n * D);
+  CK(cudaMemcpyAsync(L.data(), g->c_OL.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(I.data(), g->c_OI.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
+  if (X) {  // coordinates of the children: the bit-exact get_x of the evaluation path (mul + add, never fused)
+    if (int rc = g->s_tmp.reserve((size_t)n * D)) return rc;
+    if (int rc = g->s_flag.reserve(1)) return rc;
+    CK(cudaMemsetAsync(g->s_flag.p, 0, sizeof(int), st));
+    DeviceGrid dg = g->dg;
+    dg.D = D;
+    for (int d = 0; d < D; ++d) {
+      dg.lb[d] = g->lb[d];
+      volatile double w = g->ub[d] - g->lb[d];
+      dg.width[d] = w;
+    }
+    int64_t l = 0;
+    CK(launch_nodes_x(D, nullptr, dg, g->c_OL.p, g->c_OI.p, n, g->s_tmp.p, D, 1, g->s_flag.p, st, &l));
+    bump(l);
+    if (int rc = copy_out_matrix(g->s_tmp.p, n, D, X, sp, sdim, st)) return rc;
+  }
+  CK(cudaStreamSynchronize(st));
+  for (int64_t k = 0; k < n; ++k)
+    for (int d = 0; d < D; ++d) {
+      levels[k * sn + d * sd] = L[(size_t)k * D + d];
+      indices[k * sn + d * sd] = I[(size_t)k * D + d];
+    }
   return ASG_OK;
 }
 

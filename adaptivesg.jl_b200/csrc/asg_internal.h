@@ -208,6 +208,12 @@ cudaError_t launch_basis_sweep(const DeviceGrid &g, const BasisArgs &a, cudaStre
 cudaError_t launch_nodes_x(int D, const double *lb_dev_or_null, const DeviceGrid &g, const long long *lev,
                            const long long *idx, int64_t n, double *Xout, int64_t sp, int64_t sd, int *bad,
                            cudaStream_t st, int64_t *launches);
+// adapt! candidate generation (asg_kernels_adapt.cu): unique valid children of n_p parent rows, in the reference's
+// visiting order; *total (device) receives their number
+cudaError_t launch_children(int D, int64_t n_p, const long long *PL, const long long *PI, long long *CL, long long *CI,
+                            unsigned char *valid, int *table, int64_t table_size, unsigned int *flags,
+                            unsigned int *sums, unsigned int *total, long long *OL, long long *OI, cudaStream_t st,
+                            int64_t *launches);
 cudaError_t launch_scatter_f64(double *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,
                                int64_t *launches);
 cudaError_t launch_scatter_hash(HashEnt *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,

@@ -210,6 +210,22 @@ class SparseGridInterpolant:
                                        -1 if max_depth is None else int(max_depth), _vp(out)))
         return out
 
+    def children(self, depth: int):
+        """Unique valid children of all nodes of ``depth``, generated and de-duplicated on the device
+        (src/train.jl:337-398, asg_children): ``(levels, indices, X, n_candidates)`` with ``X`` their coordinates;
+        rows in the reference's visiting order (for j, for parent, left then right), first occurrence kept."""
+        lib = _capi.load()
+        h = self._ensure()
+        n_p, n_c, n_u = C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.asg_children(h, int(depth), C.byref(n_p), C.byref(n_c), C.byref(n_u)))
+        n = n_u.value
+        Lv = np.empty((n, self._D), dtype=np.int64)
+        Ix = np.empty((n, self._D), dtype=np.int64)
+        X = np.empty((n, self._D), dtype=np.float64)
+        if n:
+            check(lib.asg_children_fetch(h, n, _ptr(Lv, i64p), _ptr(Ix, i64p), self._D, 1, _ptr(X, f64p), self._D, 1))
+        return Lv, Ix, X, n_c.value
+
     def nodes_x(self, levels=None, indices=None) -> np.ndarray:
         """get_x rows (src/math.jl:490-497), computed on the device. Defaults to all grid nodes."""
         if levels is None:
@@ -280,6 +296,26 @@ def _children(l, i, right: bool):
     return l + 1, inew
 
 
+def _candidates_host(PL, PI):
+    """all valid children of the parent rows, repeats included, in the reference's visiting order
+    (src/train.jl:337-398: for j, for parent, left then right)"""
+    D = PL.shape[1]
+    cl, ci = [], []
+    for j in range(D):
+        ll, li = _children(PL[:, j], PI[:, j], False)
+        rl, ri = _children(PL[:, j], PI[:, j], True)
+        L2 = np.repeat(PL, 2, axis=0)
+        I2 = np.repeat(PI, 2, axis=0)
+        L2[0::2, j], I2[0::2, j] = ll, li
+        L2[1::2, j], I2[1::2, j] = rl, ri
+        ok = _valid_rows(L2, I2)
+        cl.append(L2[ok])
+        ci.append(I2[ok])
+    CL = np.concatenate(cl, axis=0) if cl else np.empty((0, D), np.int64)
+    CI = np.concatenate(ci, axis=0) if ci else np.empty((0, D), np.int64)
+    return CL, CI
+
+
 def isbig2add(alpha, fx, rtol, atol, use_rtol):
     """src/math.jl:257-274, vectorised; isapprox(fx, 0, atol = rtol) is |fx| <= rtol."""
     alpha, fx = np.asarray(alpha), np.asarray(fx)
@@ -306,6 +342,50 @@ def maxlevels(G: SparseGridInterpolant) -> np.ndarray:
     if len(G.levels) == 0:
         return np.zeros(G.ndims, dtype=np.int64)
     return np.asarray(G.levels).max(axis=0)
+
+
+def extrapolate(G: SparseGridInterpolant, X, dims: int = 1) -> np.ndarray:
+    """Batched linear extrapolation of ``G`` to points (partially) outside the domain: the documented intent of
+    ``_extrapolate`` (src/class.jl:695-737), which the reference's own call site never reaches (src/class.jl:752-757
+    tests ``x in G`` the wrong way round and calls an undefined name). One batched evaluation at the clamped points
+    plus one per dimension for the points outside in that dimension: neighbour one ghost
+    mesh step ``1 / 2^(maxlevel_j - 1)`` (src/math.jl:888-890) towards the interior, one-sided slope
+    ``(G(xbnd) - G(xnbr)) / h``, ``value += slope * overshoot``. Two readings of the documented intent ("1st order
+    Taylor expansion"): lengths are unit-cube lengths (the reference rescales unit-cube points a second time, SURVEY
+    defect B4) and slopes are taken against the value at the boundary point (the reference's loop uses the running
+    value, src/class.jl:731, a Taylor expansion only when one coordinate is outside). With one coordinate outside on
+    ``[0,1]^D`` this is the reference's arithmetic. Points inside the domain get ``G(x)``; an affine function is
+    extrapolated exactly."""
+    X = np.asarray(X, dtype=np.float64)
+    if dims == 2:
+        X = X.T
+    X = np.atleast_2d(X)
+    D = G.ndims
+    assert X.shape[1] == D, "x must have the same dimension as the grid."
+    lb, ub = np.asarray(G.lb, dtype=np.float64), np.asarray(G.ub, dtype=np.float64)
+    w = ub - lb
+    with np.errstate(invalid="ignore"):
+        x01 = 0.0 + (1.0 * (X - lb)) / w                        # scale(), src/math.jl:308
+        xb01 = np.minimum(np.maximum(x01, 0.0), 1.0)           # clamp.(x01, 0.0, 1.0), NaN stays NaN
+
+        def to_x(u):  # unit cube -> domain; the faces map to lb / ub exactly so that the kernel sees 0.0 / 1.0
+            return np.where(u >= 1.0, ub, np.where(u <= 0.0, lb, lb + w * u))
+
+        f0 = G.evaluate(to_x(xb01))
+        fval = f0.copy()
+        maxl = maxlevels(G)
+        for j in range(D):
+            outside = np.flatnonzero(~((x01[:, j] >= 0.0) & (x01[:, j] <= 1.0)))
+            if len(outside) == 0:
+                continue
+            h = 1.0 / float(1 << (int(maxl[j]) - 1))            # ghost_distance
+            right = x01[outside, j] > 1.0
+            xn = xb01[outside].copy()
+            xn[:, j] -= np.where(right, h, -h)
+            fn = G.evaluate(to_x(xn))
+            slope = np.where(right, f0[outside] - fn, fn - f0[outside]) / h
+            fval[outside] += slope * (x01[outside, j] - xb01[outside, j])
+    return fval
 
 
 def coefficients(G: SparseGridInterpolant) -> np.ndarray:
@@ -508,10 +588,14 @@ def train(G: SparseGridInterpolant, f, maxdepth: int, maxlevels, verbose: bool =
 
 
 def adapt(G: SparseGridInterpolant, f2fit, maxdepth: int, verbose: bool = True, tol: float = 1e-3,
-          toltype: str = "absolute", parallel: bool = False, vectorized: bool = False, log: list | None = None):
+          toltype: str = "absolute", parallel: bool = False, vectorized: bool = False, log: list | None = None,
+          device_candidates: bool = True):
     """``adapt!`` (src/train.jl:235-463). Child generation, validity, acceptance and dedupe stay on
     the host; all candidates of one level go through ONE surplus call against the whole current grid
-    (the grid is not mutated inside a level, src/train.jl:434-438).  ``parallel`` is accepted and
+    (the grid is not mutated inside a level, src/train.jl:434-438). With ``device_candidates`` (default) the
+    children, their validity test and the removal of repeats run on the device (``asg_children``):
+    every unique child is evaluated once - the reference calls ``f`` and ``G`` at each repeat and lets a Dict drop
+    them afterwards, same node set; ``device_candidates=False`` keeps that order of work on the host.  ``parallel`` is accepted and
     ignored: batching removes the threaded region.  New rows are appended in first-insertion order of
     the reference's visiting order (for j, for parent, left then right); the reference's own row order
     is Julia ``Dict`` iteration order, so compare node SETS."""
@@ -542,23 +626,14 @@ def adapt(G: SparseGridInterpolant, f2fit, maxdepth: int, verbose: bool = True, 
         parents = np.flatnonzero(G.depths == lnow)
         if verbose:
             print(f"level {lnow}/{maxdepth}, #parents: {len(parents)}, ", end="")
-        PL, PI = G.levels[parents], G.indices[parents]
-        cl, ci = [], []
-        for j in range(D):
-            ll, li = _children(PL[:, j], PI[:, j], False)
-            rl, ri = _children(PL[:, j], PI[:, j], True)
-            L2 = np.repeat(PL, 2, axis=0)
-            I2 = np.repeat(PI, 2, axis=0)
-            L2[0::2, j], I2[0::2, j] = ll, li
-            L2[1::2, j], I2[1::2, j] = rl, ri
-            ok = _valid_rows(L2, I2)
-            cl.append(L2[ok])
-            ci.append(I2[ok])
-        CL = np.concatenate(cl, axis=0) if cl else np.empty((0, D), np.int64)
-        CI = np.concatenate(ci, axis=0) if ci else np.empty((0, D), np.int64)
+        if device_candidates:
+            # children, validity and the removal of repeats on the device; every unique child is evaluated once
+            CL, CI, X, _ = G.children(lnow)
+        else:
+            CL, CI = _candidates_host(G.levels[parents], G.indices[parents])
+            X = G.nodes_x(CL, CI) if len(CL) else None
         n_added = 0
         if len(CL):
-            X = G.nodes_x(CL, CI)
             fv = _apply_f(f2fit, X, vectorized)
             al = G.surplus(X, fv)  # whole current grid
             big = isbig2add(al, fv, rtol, atol, toltype == "relative")

@@ -13,7 +13,7 @@ module AdaptiveSGCUDA
 using SparseArrays, Printf
 
 export SparseGridInterpolant, rsg!, train!, adapt!, coefficients, basis, dehierarchization_matrix,
-       hierarchization_matrix, hierarchize!, serialize, deserialize, maxlevels, sync!, nodedepth, isvalid,
+       hierarchization_matrix, hierarchize!, extrapolate, serialize, deserialize, maxlevels, sync!, nodedepth, isvalid,
        allindices_of_level, child, scale, get_x
 
 const LIB = get(ENV, "ASG_CUDA_LIB", "libasg_cuda")
@@ -162,6 +162,35 @@ function evaluate(G::SparseGridInterpolant{D}, X::AbstractMatrix{Float64}; dims:
     return out
 end
 (G::SparseGridInterpolant)(X::AbstractMatrix) = evaluate(G, convert(Matrix{Float64}, X))   # additive: batched rows
+
+"""
+    extrapolate(G, X)
+
+Batched linear extrapolation of `G` to the rows of `X` (documented intent of `_extrapolate`, src/class.jl:695-737,
+which the reference's call site never reaches): one batched evaluation at the clamped points plus one per dimension
+for the points outside in that dimension. Unit-cube lengths; slopes against the value at the boundary point.
+"""
+function extrapolate(G::SparseGridInterpolant{D}, X::AbstractMatrix{Float64}) where {D}
+    w = G.ub .- G.lb
+    x01 = (X .- G.lb') ./ w'
+    xb01 = clamp.(x01, 0.0, 1.0)
+    to_x(u) = ifelse.(u .>= 1.0, G.ub', ifelse.(u .<= 0.0, G.lb', G.lb' .+ w' .* u))   # faces map to lb / ub exactly
+    f0 = evaluate(G, to_x(xb01))
+    fval = copy(f0)
+    maxl = maxlevels(G)
+    for j in 1:D
+        out = findall(.!((x01[:, j] .>= 0.0) .& (x01[:, j] .<= 1.0)))
+        isempty(out) && continue
+        h = 1.0 / (1 << (maxl[j] - 1))                          # ghost_distance, src/math.jl:888-890
+        right = x01[out, j] .> 1.0
+        xn = xb01[out, :]
+        xn[:, j] .-= ifelse.(right, h, -h)
+        fn = evaluate(G, to_x(xn))
+        slope = ifelse.(right, f0[out] .- fn, fn .- f0[out]) ./ h
+        fval[out] .+= slope .* (x01[out, j] .- xb01[out, j])
+    end
+    return fval
+end
 
 function (G::SparseGridInterpolant{D})(x::AbstractVector; safe::Bool = true, extrapolate::Bool = false) where {D}
     safe && @assert length(x) == D "Input point must match the dimension of the grid."

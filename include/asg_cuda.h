@@ -151,6 +151,17 @@ int32_t asg_nodes_x(asg_grid *g, int64_t first, int64_t n, double *Xout, int64_t
 int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                        int64_t sd, double *Xout, int64_t sp, int64_t sdim);
 
+/* ---- adapt! candidate generation (src/train.jl:337-398; child: src/math.jl:907-959; isvalid: 418-448) --------
+ * asg_children builds, on the device, the valid children of every node of depth `depth` in the reference's visiting
+ * order (for j in 1:D, for parent in node order, left then right) and removes the repeats (a child is reached from
+ * up to D parents; the first one generated stays - the reference's `!haskey` rule). The reference evaluates f and G
+ * at every repeat before its Dict drops them; generating the unique set first gives the same nodes with up to D
+ * times fewer calls of f. n_candidates = 2 * D * n_parents. asg_children_fetch copies the n_unique rows (strides in
+ * elements, as everywhere) and, if X != NULL, their coordinates (get_x, domain units). */
+int32_t asg_children(asg_grid *g, int64_t depth, int64_t *n_parents, int64_t *n_candidates, int64_t *n_unique);
+int32_t asg_children_fetch(asg_grid *g, int64_t n, int64_t *levels, int64_t *indices, int64_t sn, int64_t sd, double *X,
+                           int64_t sp, int64_t sdim);
+
 /* ---- basis rows: basis(x,G) / basis(Xs,G) / basis(G) / dehierarchization_matrix
  *      (src/class.jl:434-454, 483-503, 521-538, 555-567; documented intent) ----- */
 /* pass 1: row_nnz[m] = number of stored entries of row m. Entry (m,n) = prod_d phi(...) is stored

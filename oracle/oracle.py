@@ -247,6 +247,36 @@ class OracleGrid:
             return float(self.evaluate(x[None, :])[0])
         return self.evaluate(x)
 
+    # -- src/class.jl:695-737 (documented intent: the reference's call site never reaches it, defect B3) --------
+    def extrapolate(self, x) -> float:
+        """First-order Taylor expansion at the nearest boundary point, one point, scalar loop as in the reference:
+        f0 = G(xbnd); for every dimension j outside [0,1]: neighbour one ghost mesh step (src/math.jl:888-890,
+        finest level of that dimension) towards the interior, one-sided slope (f0 - f(nbr)) / h, fval += slope *
+        overshoot. Two deliberate readings of the documented intent ("1st order Taylor expansion"): lengths are
+        unit-cube lengths (the reference rescales unit-cube points a second time, defect B4), and every slope is
+        taken against f0 (the reference's loop uses the running fval, src/class.jl:731, which is a Taylor expansion
+        only when a single coordinate is outside). With one coordinate outside on [0,1]^D this is the reference's
+        arithmetic verbatim."""
+        x = np.asarray(x, dtype=np.float64)
+        w = self.ub - self.lb
+        x01 = 0.0 + (1.0 * (x - self.lb)) / w                  # scale(), src/math.jl:308
+        xb01 = np.minimum(np.maximum(x01, 0.0), 1.0)           # clamp.(x01, 0.0, 1.0)   (NaN stays NaN)
+        to_x = lambda u: np.where(u >= 1.0, self.ub, np.where(u <= 0.0, self.lb, self.lb + w * u))
+        f0 = fval = float(self.evaluate(to_x(xb01)[None, :])[0])
+        maxl = self.levels.max(axis=0)
+        for j in range(self.D):
+            if 0.0 <= x01[j] <= 1.0:
+                continue
+            dx_out = x01[j] - xb01[j]
+            h = 1.0 / power2(int(maxl[j]) - 1)                 # ghost_distance
+            right = x01[j] > 1.0
+            xn = xb01.copy()
+            xn[j] -= h if right else -h
+            fn = float(self.evaluate(to_x(xn)[None, :])[0])
+            slope = ((f0 - fn) if right else (fn - f0)) / h
+            fval += slope * dx_out
+        return fval
+
     # -- src/class.jl:434-538 (documented intent) ----------------------------------------------
     def basis(self, X=None, dropzeros: bool = True, atol: float = 1e-16) -> np.ndarray:
         """Dense M x N matrix; entries the reference would drop are exactly 0.0."""

@@ -546,3 +546,52 @@ def test_fuzz_irregular_grids(asg, oracle):
             assert_close(yb[:3000], wb, sb, f"fuzz {trial} D={D} large batch")
             assert_close(G.evaluate(Xb, max_depth=L)[:3000], OG.evaluate(Xb[:3000], max_depth=L), sb, "large batch masked")
     assert len(kinds) >= 3          # regular, irregular dense, irregular hashed were all exercised
+
+
+def test_extrapolate_batched(asg, oracle, cfg1, cfg_nonunit):
+    """batched linear extrapolation (1 + D batched evaluations) against the scalar oracle
+    restatement of src/class.jl:695-737 (documented intent); affine functions are extrapolated exactly."""
+    rng = np.random.default_rng(21)
+    for OG in (cfg1, cfg_nonunit):
+        G = _mirror(asg, OG)
+        D = OG.D
+        u = rng.random((400, D)) * 1.6 - 0.3                     # about half the coordinates outside [0,1]
+        u[:50] = rng.random((50, D))                             # inside: plain evaluation
+        u[50:60, 0] = 1.0                                        # on a face: not outside
+        X = OG.lb + (OG.ub - OG.lb) * u
+        got = asg.extrapolate(G, X)
+        want = np.array([OG.extrapolate(x) for x in X])
+        assert np.max(np.abs(got - want)) < 1e-11 * max(1.0, np.max(np.abs(want)))
+        assert np.array_equal(got[:50], G.evaluate(X[:50]))
+    aff = lambda x: float(1.0 + 2.0 * x[0] - x[1] + 0.5 * x[2])
+    G = asg.SparseGridInterpolant(3)
+    asg.train(G, aff, 4, 4)
+    X = rng.random((200, 3)) * 3.0 - 1.0
+    assert np.max(np.abs(asg.extrapolate(G, X) - (1.0 + 2.0 * X[:, 0] - X[:, 1] + 0.5 * X[:, 2]))) < 1e-12
+
+
+def test_children_on_device(asg, oracle, cfg1, cfg2, cfg_nonunit):
+    """adapt!'s candidate generation on the device (asg_children) against the host
+    restatement of src/train.jl:337-398 -- the same rows, each once, in the reference's visiting order, with
+    bit-exact coordinates; level-2 boundary nodes have a child on one side only (src/math.jl:931-959)."""
+    from _asg_b200_pkg import interpolant as ip
+    for OG in (cfg1, cfg2, cfg_nonunit):
+        G = _mirror(asg, OG)
+        for depth in sorted(set(int(d) for d in OG.depths)):
+            parents = np.flatnonzero(OG.depths == depth)
+            CLh, CIh = ip._candidates_host(OG.levels[parents], OG.indices[parents])
+            key = np.concatenate([CLh, CIh], axis=1)
+            _, first = np.unique(key, axis=0, return_index=True)
+            first.sort()
+            Lv, Ix, X, n_cand = G.children(depth)
+            assert n_cand == 2 * OG.D * len(parents)
+            assert np.array_equal(Lv, CLh[first]) and np.array_equal(Ix, CIh[first]), (OG.D, depth)
+            assert np.array_equal(X, OG.stack(Lv, Ix))
+    # both orders of work give the same grid
+    f = lambda X: -1.0 / (0.1 + np.sum(X, axis=1))
+    Ga, Gb = asg.SparseGridInterpolant(2), asg.SparseGridInterpolant(2)
+    for G, dev in ((Ga, True), (Gb, False)):
+        asg.train(G, f, 4, (3, 8), vectorized=True)
+        asg.adapt(G, f, 12, tol=1e-4, verbose=False, vectorized=True, device_candidates=dev)
+    assert np.array_equal(Ga.levels, Gb.levels) and np.array_equal(Ga.indices, Gb.indices)
+    assert np.array_equal(Ga.coefs, Gb.coefs)
