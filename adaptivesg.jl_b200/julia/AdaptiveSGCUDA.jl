@@ -329,6 +329,22 @@ function train!(G::SparseGridInterpolant{D}, f::Function, maxdepth::Int, maxleve
     return nothing
 end
 
+"""
+    children(G, depth) -> (levels, indices, X)
+
+Unique valid children of all nodes of `depth` (src/train.jl:337-398), generated on the device, with coordinates.
+"""
+function children(G::SparseGridInterpolant{D}, depth::Int) where {D}
+    h = ensure!(G)
+    np_, nc, nu = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0)
+    check(ccall((:asg_children, LIB), Int32, (Ptr{Cvoid}, Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}), h, depth, np_, nc, nu))
+    n = nu[]
+    L = Matrix{Int}(undef, n, D); I = Matrix{Int}(undef, n, D); X = Matrix{Float64}(undef, n, D)
+    n > 0 && GC.@preserve L I X check(ccall((:asg_children_fetch, LIB), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ptr{Float64}, Int64, Int64), h, n, L, I, 1, n, X, 1, n))
+    return L, I, X
+end
+
 function adapt!(G::SparseGridInterpolant{D}, f2fit::Function, maxdepth::Int; verbose::Bool = true, tol::Float64 = 1e-3,
                 toltype::Symbol = :absolute, parallel::Bool = false) where {D}
     @assert length(G) > 0 "The grid structure in G is empty."
@@ -347,19 +363,15 @@ function adapt!(G::SparseGridInterpolant{D}, f2fit::Function, maxdepth::Int; ver
     while lnow < maxdepth
         parents = findall(G.depths .== lnow)
         verbose && @printf("level %d/%d, #parents: %d, ", lnow, maxdepth, length(parents))
-        candL = Vector{Int}[]; candI = Vector{Int}[]
-        for j in 1:D, p in parents, side in (:left, :right)        # the reference's visiting order
-            L, I = child(G.levels[p, :], G.indices[p, :], j; side = side)
-            isvalid(L, I) && (push!(candL, L); push!(candI, I))
-        end
+        # children, validity test and removal of repeats on the device (asg_children): every unique child is
+        # evaluated once; rows in the reference's visiting order (for j, for parent, left then right)
+        CL, CI, X = children(G, lnow)
         new = Dict{NTuple{2,Vector{Int}},NTuple{2,Float64}}(); order = NTuple{2,Vector{Int}}[]
-        if !isempty(candL)
-            CL = permutedims(reduce(hcat, candL)); CI = permutedims(reduce(hcat, candI))
-            X = get_x(G, CL, CI)
+        if size(CL, 1) > 0
             fv = Float64[f2fit(X[k, :]) for k in 1:size(X, 1)]
             al = surplus(G, X, fv)                                    # ONE kernel call for the whole level
             for k in eachindex(fv)
-                key = (candL[k], candI[k])
+                key = (CL[k, :], CI[k, :])
                 if big(al[k], fv[k]) && !haskey(new, key); new[key] = (fv[k], al[k]); push!(order, key); end
             end
         end
