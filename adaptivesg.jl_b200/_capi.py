@@ -90,6 +90,8 @@ SIGNATURES = {
                                C.c_int64, vp],
     "asg_pack_info": [C.c_int32, C.c_int64, i64p, i64p, C.c_int64, C.c_int64, C.POINTER(GridInfo)],
     "asg_measure_fp64_peak": [f64p],
+    "asg_rsg_count": [C.c_int32, C.c_int64, i64p, i64p],
+    "asg_rsg_fill": [C.c_int32, C.c_int64, i64p, C.c_int64, i64p, i64p, C.c_int64, C.c_int64],
     "asg_children": [vp, C.c_int64, i64p, i64p, i64p],
     "asg_children_fetch": [vp, C.c_int64, i64p, i64p, C.c_int64, C.c_int64, f64p, C.c_int64, C.c_int64],
     "asg_last_kernel_ms": [f64p],

@@ -1156,6 +1156,21 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   return ASG_OK;
 }
 
+int32_t asg_rsg_count(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N) {
+  if (D <= 0 || D > kMaxDim || !maxlevels || !N) return set_err(ASG_EINVAL, "bad argument");
+  std::string err;
+  const int rc = rsg_count(D, maxdepth, maxlevels, N, err);
+  return rc == ASG_OK ? ASG_OK : set_err(rc, err);
+}
+
+int32_t asg_rsg_fill(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t N, int64_t *levels, int64_t *indices,
+                     int64_t sn, int64_t sd) {
+  if (D <= 0 || D > kMaxDim || !maxlevels || N < 0 || (N > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "bad argument");
+  std::string err;
+  const int rc = rsg_fill(D, maxdepth, maxlevels, N, levels, indices, sn, sd, err);
+  return rc == ASG_OK ? ASG_OK : set_err(rc, err);
+}
+
 int32_t asg_measure_fp64_peak(double *fma_per_second) {
   if (!fma_per_second) return set_err(ASG_EINVAL, "null pointer");
   if (int rc = require_ctx()) return rc;

@@ -167,6 +167,11 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
 // host model of the BLOCK walk of asg_kernels_block.cu for one unit-cube point (packer self-check, tests)
 double block_walk_host(int D, const PackResult &pk, const double *x01, int rem);
 
+// rsg! node enumeration on the host (asg_rsg.cpp, src/train.jl:40-78)
+int rsg_count(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N, std::string &err);
+int rsg_fill(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t N, int64_t *levels, int64_t *indices, int64_t sn,
+             int64_t sd, std::string &err);
+
 // ---- kernel launchers (asg_kernels_*.cu) -------------------------------------------------------
 struct EvalArgs {
   const double *X;   // device

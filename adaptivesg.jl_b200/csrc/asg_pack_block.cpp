@@ -86,7 +86,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
   out.blk_why.clear();
   out.bcoef.clear(); out.brec.clear(); out.btiles.clear(); out.bslot_of_node.clear();
   auto no = [&](const char *w) { out.blk_why = w; return ASG_OK; };
-  if (D < 4) return no("D < 4");
+  if (D < 3) return no("D < 3");
   if (D - 3 > 15) return no("D > 18");
   if (N <= 0) return no("empty grid");
   const int K = D - 3;  // longest prefix: dimensions 0..K-1; A = K, B = K+1, C = K+2

@@ -503,24 +503,6 @@ def deserialize(dat: dict) -> SparseGridInterpolant:
 # -------------------------------------------------------------------------------------------------
 # training (src/train.jl)
 # -------------------------------------------------------------------------------------------------
-def _level_vectors(D: int, budget: int, maxlevels) -> np.ndarray:
-    """Admissible level vectors of rsg! in Iterators.product order (dimension 1 fastest),
-    src/train.jl:56-57, enumerated with pruning instead of scanning the full product."""
-    out = []
-    ks = [1] * D
-
-    def rec(d: int, remaining: int):  # choose k_d for d = D-1 .. 0; `remaining` = budget left for dims <= d
-        if d < 0:
-            out.append(tuple(ks))
-            return
-        for k in range(1, min(int(maxlevels[d]), remaining - d) + 1):  # dims below d need >= 1 each
-            ks[d] = k
-            rec(d - 1, remaining - k)
-
-    rec(D - 1, budget)
-    return np.array(out, dtype=np.int64).reshape(-1, D)
-
-
 def rsg(G: SparseGridInterpolant, maxdepth: int, maxlevels) -> None:
     """``rsg!`` (src/train.jl:40-78): fill G with the regular sparse grid node set, zero fvals/coefs."""
     D = G.ndims
@@ -531,17 +513,15 @@ def rsg(G: SparseGridInterpolant, maxdepth: int, maxlevels) -> None:
         raise ValueError("maxlevels must be >= 1")
     if maxdepth < 2:
         raise ValueError("maxdepth must be >= 2")
-    lvs = _level_vectors(D, maxdepth + D - 1, ml)
-    Ls, Is = [], []
-    for ks in lvs:
-        per_dim = [allindices_of_level(int(k)) for k in ks]
-        # Iterators.product: first dimension fastest
-        mesh = np.meshgrid(*per_dim, indexing="ij")
-        idx = np.stack([m.reshape(-1, order="F") for m in mesh], axis=1)
-        Is.append(idx)
-        Ls.append(np.broadcast_to(ks, idx.shape))
-    G.levels = np.ascontiguousarray(np.concatenate(Ls, axis=0), dtype=np.int64)
-    G.indices = np.ascontiguousarray(np.concatenate(Is, axis=0), dtype=np.int64)
+    # the enumeration itself is host C++ in the library (csrc/asg_rsg.cpp): 652 065 x 10 nodes in ~20 ms
+    lib = _capi.load()
+    ml = np.ascontiguousarray(ml)
+    n = C.c_int64()
+    check(lib.asg_rsg_count(D, int(maxdepth), _ptr(ml, i64p), C.byref(n)))
+    Lv = np.empty((n.value, D), dtype=np.int64)
+    Ix = np.empty((n.value, D), dtype=np.int64)
+    check(lib.asg_rsg_fill(D, int(maxdepth), _ptr(ml, i64p), n.value, _ptr(Lv, i64p), _ptr(Ix, i64p), D, 1))
+    G.levels, G.indices = Lv, Ix
     G.depths = G.levels.sum(axis=1) - D + 1
     G.fvals = np.zeros(len(G.levels))
     G.coefs = np.zeros(len(G.levels))

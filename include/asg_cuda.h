@@ -151,6 +151,13 @@ int32_t asg_nodes_x(asg_grid *g, int64_t first, int64_t n, double *Xout, int64_t
 int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                        int64_t sd, double *Xout, int64_t sp, int64_t sdim);
 
+/* ---- rsg! node enumeration (src/train.jl:40-78), host code, no device needed: the regular sparse grid node set
+ * {l : l_d <= maxlevels_d, sum(l_d - 1) <= maxdepth - 1} in the reference's order (level vectors and index tuples in
+ * Iterators.product order, dimension 1 fastest). Call _count, allocate N x D, call _fill (strides in elements). */
+int32_t asg_rsg_count(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N);
+int32_t asg_rsg_fill(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t N, int64_t *levels, int64_t *indices,
+                     int64_t sn, int64_t sd);
+
 /* ---- adapt! candidate generation (src/train.jl:337-398; child: src/math.jl:907-959; isvalid: 418-448) --------
  * asg_children builds, on the device, the valid children of every node of depth `depth` in the reference's visiting
  * order (for j in 1:D, for parent in node order, left then right) and removes the repeats (a child is reached from

@@ -44,8 +44,13 @@ def test_block_layout_regular_grids(asg):
     rc, info, msg = _pack_info(asg, G.levels, G.indices)
     assert rc == 0 and info["block"] == 1 and info["block_slots"] == 652065 and info["block_records"] == 1003, msg
     assert info["block_stack"] == 5 and info["block_tiles"] == 253
-    # outside the layout's limits: D < 4, suffix levels > 8
-    for D, depth in [(3, 5), (4, 10)]:
+    # D = 3: no prefix at all, one record
+    G = asg.SparseGridInterpolant(3)
+    asg.rsg(G, 7, 5)
+    rc, info, msg = _pack_info(asg, G.levels, G.indices)
+    assert rc == 0 and info["block"] == 1 and info["block_records"] == 1 and info["block_slots"] == 1073, msg  # caps: padding
+    # outside the layout's limits: D < 3, suffix levels > 8
+    for D, depth in [(2, 5), (4, 10)]:
         G = asg.SparseGridInterpolant(D)
         asg.rsg(G, depth, depth)
         rc, info, msg = _pack_info(asg, G.levels, G.indices)
@@ -94,7 +99,7 @@ def _edge_points(D, lb, ub, rng):
 def _grids(oracle):
     rng = np.random.default_rng(99)
     out = []
-    for D, depth, ml, keepfrac, unit in [(4, 7, 7, 1.0, True), (10, 5, 5, 1.0, True), (6, 6, (4, 5, 6, 3, 6, 6), 1.0, False),
+    for D, depth, ml, keepfrac, unit in [(3, 8, 8, 1.0, False), (3, 7, (5, 6, 4), 0.8, True), (4, 7, 7, 1.0, True), (10, 5, 5, 1.0, True), (6, 6, (4, 5, 6, 3, 6, 6), 1.0, False),
                                          (5, 6, 6, 0.9, False), (7, 4, 4, 0.7, True), (4, 8, 8, 1.0, False),
                                          (12, 3, 3, 1.0, True)]:
         lb = np.zeros(D) if unit else -rng.random(D)
@@ -170,7 +175,7 @@ def test_block_walk_large_sorted_batch(asg, oracle):
     """>= 2^20 points: two points per thread and the cell-key ordering of the points (asg_sort.cu). The
     per-point arithmetic does not depend on the batch, so the results equal those of a small batch bit for bit."""
     rng = np.random.default_rng(11)
-    OG = _grids(oracle)[1]                                   # D = 10, depth 5
+    OG = [g for g in _grids(oracle) if g.D == 10][0]         # D = 10, depth 5
     G = _mirror(asg, OG)
     G.set_path("block")
     M = (1 << 20) + 12345
