@@ -90,6 +90,8 @@ SIGNATURES = {
                                C.c_int64, vp],
     "asg_pack_info": [C.c_int32, C.c_int64, i64p, i64p, C.c_int64, C.c_int64, C.POINTER(GridInfo)],
     "asg_measure_fp64_peak": [f64p],
+    "asg_grid_export": [vp, vp, C.c_int64, i64p],
+    "asg_grid_import": [vp, vp, C.c_int64],
     "asg_rsg_count": [C.c_int32, C.c_int64, i64p, i64p],
     "asg_rsg_fill": [C.c_int32, C.c_int64, i64p, C.c_int64, i64p, i64p, C.c_int64, C.c_int64],
     "asg_children": [vp, C.c_int64, i64p, i64p, i64p],
@@ -142,6 +144,11 @@ def init(device: int | None = None) -> int:
     check(load().asg_init(int(device)))
     _init_device = int(device)
     return _init_device
+
+
+def device_ready() -> bool:
+    """True once asg_init has succeeded in this process."""
+    return _init_device is not None
 
 
 def launch_count() -> int:

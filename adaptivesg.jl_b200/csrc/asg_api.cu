@@ -123,6 +123,8 @@ struct asg_grid {
   DevBuf<int> c_table;
   DevBuf<unsigned int> c_flags, c_sums;
   int64_t ch_n = -1, ch_generation = -1;
+  std::vector<unsigned char> blob;  // asg_grid_export: between the size query and the copy
+  int64_t blob_generation = -1;
   // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
   DevBuf<uint32_t> s_key[2], s_key2[2], s_idx[2], s_perm[2];
   DevBuf<unsigned char> s_sorttmp[2];
@@ -241,11 +243,19 @@ int device_upload(asg_grid *g, const PackResult &pk) {
   return ASG_OK;
 }
 
+int install_pack(asg_grid *g, PackResult &pk);
+
 int repack(asg_grid *g) {
   PackResult pk;
   std::string err;
   int rc = pack_grid(g->D, g->N, g->levels.data(), g->indices.data(), g->coefs.data(), pk, err);
   if (rc != ASG_OK) return set_err(rc, err);
+  return install_pack(g, pk);
+}
+
+// make a packed grid (fresh from pack_grid, or read from a blob) the state of the handle: device upload, slot maps, info
+int install_pack(asg_grid *g, PackResult &pk) {
+  int rc;
   g->canonical = pk.canonical;
   g->regular = pk.regular;
   g->rp = pk.rp;
@@ -1154,6 +1164,45 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   if (!pk.canonical) t_err = pk.why;
   else if (!pk.blk_ok) t_err = "no BLOCK layout: " + pk.blk_why;
   return ASG_OK;
+}
+
+// ---- device-format persistence -------------------------------------------------
+int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes) {
+  if (!g || !bytes) return set_err(ASG_EINVAL, "null argument");
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
+  if (g->blob_generation != g->info.generation || g->blob.empty()) {
+    PackResult pk;
+    std::string err;
+    int rc = pack_grid(g->D, g->N, g->levels.data(), g->indices.data(), g->coefs.data(), pk, err);
+    if (rc != ASG_OK) return set_err(rc, err);
+    pack_serialize(g->D, g->lb, g->ub, g->levels, g->indices, g->coefs, pk, g->blob);
+    g->blob_generation = g->info.generation;
+  }
+  *bytes = (int64_t)g->blob.size();
+  if (!buf) return ASG_OK;  // size query
+  if (capacity < *bytes) return set_err(ASG_EINVAL, "buffer too small for the packed grid");
+  std::memcpy(buf, g->blob.data(), g->blob.size());
+  std::vector<unsigned char>().swap(g->blob);  // the blob can be large: do not keep a second copy around
+  return ASG_OK;
+}
+
+int32_t asg_grid_import(asg_grid *g, const void *buf, int64_t bytes) {
+  if (!g || !buf || bytes <= 0) return set_err(ASG_EINVAL, "null argument");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  PackResult pk;
+  std::vector<int64_t> L, I;
+  std::vector<double> c;
+  std::string err;
+  int rc = pack_deserialize((const unsigned char *)buf, (size_t)bytes, g->D, g->lb, g->ub, L, I, c, pk, err);
+  if (rc != ASG_OK) return set_err(rc, err);
+  g->uploaded = false;
+  g->levels.swap(L);
+  g->indices.swap(I);
+  g->coefs.swap(c);
+  g->N = (int64_t)g->coefs.size();
+  return install_pack(g, pk);
 }
 
 int32_t asg_rsg_count(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N) {

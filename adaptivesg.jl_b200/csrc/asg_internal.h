@@ -167,6 +167,14 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
 // host model of the BLOCK walk of asg_kernels_block.cu for one unit-cube point (packer self-check, tests)
 double block_walk_host(int D, const PackResult &pk, const double *x01, int rem);
 
+// device-format persistence (asg_persist.cpp): node arrays + every packed layout as one blob
+void pack_serialize(int D, const double *lb, const double *ub, const std::vector<int64_t> &levels,
+                    const std::vector<int64_t> &indices, const std::vector<double> &coefs, const PackResult &pk,
+                    std::vector<unsigned char> &out);
+int pack_deserialize(const unsigned char *buf, size_t bytes, int D, const double *lb, const double *ub,
+                     std::vector<int64_t> &levels, std::vector<int64_t> &indices, std::vector<double> &coefs, PackResult &pk,
+                     std::string &err);
+
 // rsg! node enumeration on the host (asg_rsg.cpp, src/train.jl:40-78)
 int rsg_count(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N, std::string &err);
 int rsg_fill(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t N, int64_t *levels, int64_t *indices, int64_t sn,

@@ -425,7 +425,11 @@ bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_
 
 template <int R, bool MASKED, int NT>
 static void blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(k_eval_block<R, MASKED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // one instantiation serves every grid: raise its dynamic shared-memory limit ONCE to the device maximum (setting
+  // it per launch to the launch's own size races between host threads that evaluate different grids)
+  static const cudaError_t once =
+      cudaFuncSetAttribute(k_eval_block<R, MASKED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  (void)once;
   k_eval_block<R, MASKED, NT><<<blocks, NT, smem, st>>>(g, a);
 }
 template <int NT>

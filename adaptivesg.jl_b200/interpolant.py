@@ -116,6 +116,12 @@ class SparseGridInterpolant:
             self.sync()
         return h
 
+    def info_raw(self) -> dict:
+        """asg_grid_info without syncing the host arrays first"""
+        gi = _capi.GridInfo()
+        check(_capi.load().asg_grid_info(self._grid(), C.byref(gi)))
+        return gi.as_dict()
+
     def info(self) -> dict:
         gi = _capi.GridInfo()
         check(_capi.load().asg_grid_info(self._ensure(), C.byref(gi)))
@@ -482,9 +488,21 @@ def hierarchize(G: SparseGridInterpolant, fvals=None) -> np.ndarray:
 # -------------------------------------------------------------------------------------------------
 # I/O (src/io.jl:9-72): same keys, arrays aliased not copied
 # -------------------------------------------------------------------------------------------------
-def serialize(G: SparseGridInterpolant) -> dict:
-    return {"D": G.ndims, "lb": list(G.lb), "ub": list(G.ub), "levels": G.levels, "indices": G.indices,
-            "depths": G.depths, "fvals": G.fvals, "coefs": G.coefs}
+def serialize(G: SparseGridInterpolant, packed: bool = False) -> dict:
+    """``serialize`` (src/io.jl:30-38): the Dict of the reference, arrays aliased. ``packed=True`` adds the key
+    ``"packed"``: the device-format blob of the uploaded grid (``asg_grid_export``), which lets
+    ``deserialize`` skip validation, sorting and packing."""
+    dat = {"D": G.ndims, "lb": list(G.lb), "ub": list(G.ub), "levels": G.levels, "indices": G.indices,
+           "depths": G.depths, "fvals": G.fvals, "coefs": G.coefs}
+    if packed:
+        lib = _capi.load()
+        h = G._ensure()
+        n = C.c_int64()
+        check(lib.asg_grid_export(h, None, 0, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        check(lib.asg_grid_export(h, buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+        dat["packed"] = buf
+    return dat
 
 
 def deserialize(dat: dict) -> SparseGridInterpolant:
@@ -497,6 +515,16 @@ def deserialize(dat: dict) -> SparseGridInterpolant:
     G.depths = dat["depths"]
     G.fvals = dat["fvals"]
     G.coefs = dat["coefs"]
+    if dat.get("packed") is not None:
+        # device-format blob: straight to the upload; a blob of another build (other layout constants) is ignored
+        buf = np.ascontiguousarray(dat["packed"], dtype=np.uint8)
+        rc = _capi.load().asg_grid_import(G._grid(), buf.ctypes.data_as(C.c_void_p), buf.size)
+        if rc == 0:
+            info = G.info_raw()
+            assert info["N"] == len(G.levels), "packed blob does not belong to these node arrays"
+            object.__setattr__(G, "_dirty", False)
+        elif rc != _capi.ASG_EUNSUPPORTED:
+            check(rc)
     return G
 
 

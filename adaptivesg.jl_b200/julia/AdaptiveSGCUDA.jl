@@ -266,12 +266,29 @@ end
 # ---------------------------------------------------------------------------------------------
 # I/O (src/io.jl:9-72): same Dict schema; deserialize leaves the mirror unsynced
 # ---------------------------------------------------------------------------------------------
-serialize(G::SparseGridInterpolant{D}) where {D} = Dict{Symbol,Any}(:D => D, :lb => collect(G.lb), :ub => collect(G.ub),
-    :levels => G.levels, :indices => G.indices, :depths => G.depths, :fvals => G.fvals, :coefs => G.coefs)
+# `packed = true` adds :packed, the device-format blob of the uploaded grid (asg_grid_export): deserialize then skips
+# validation, sorting and packing (asg_grid_import); a blob of a build with other layout constants is ignored.
+function serialize(G::SparseGridInterpolant{D}; packed::Bool = false) where {D}
+    dat = Dict{Symbol,Any}(:D => D, :lb => collect(G.lb), :ub => collect(G.ub),
+        :levels => G.levels, :indices => G.indices, :depths => G.depths, :fvals => G.fvals, :coefs => G.coefs)
+    if packed
+        h = ensure!(G); n = Ref{Int64}(0)
+        check(ccall((:asg_grid_export, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{Int64}), h, C_NULL, 0, n))
+        buf = Vector{UInt8}(undef, n[])
+        GC.@preserve buf check(ccall((:asg_grid_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64, Ref{Int64}), h, buf, n[], n))
+        dat[:packed] = buf
+    end
+    return dat
+end
 function deserialize(dat::AbstractDict)
     for k in (:lb, :ub, :levels, :indices, :depths, :fvals, :coefs); @assert haskey(dat, k) "Serialized data must contain $k."; end
     G = SparseGridInterpolant(dat[:D], lb = dat[:lb], ub = dat[:ub])
     G.levels = dat[:levels]; G.indices = dat[:indices]; G.depths = dat[:depths]; G.fvals = dat[:fvals]; G.coefs = dat[:coefs]
+    if haskey(dat, :packed)
+        buf = dat[:packed]::Vector{UInt8}
+        rc = GC.@preserve buf ccall((:asg_grid_import, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64), G.handle, buf, length(buf))
+        rc == 0 ? setfield!(G, :synced, true) : (rc == -6 || check(rc))      # -6 = ASG_EUNSUPPORTED: repack on first use
+    end
     return G
 end
 

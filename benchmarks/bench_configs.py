@@ -98,6 +98,21 @@ def main():
     print(json.dumps({"config": "cfg3-train", "nodes": len(G), "rsg_s": t_rsg, "train_total_s": t_train,
                       "interpolation_err_at_nodes": err, "pairs": 8.8e10}), flush=True)
 
+    # ---- device-format persistence of the trained cfg3 grid -----------------------------------
+    t0 = time.perf_counter()
+    G.sync()
+    t_upload = time.perf_counter() - t0                     # validate + sort + pack + upload
+    t0 = time.perf_counter()
+    dat = asg.serialize(G, packed=True)
+    t_export = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    H = asg.deserialize(dat)
+    t_import = time.perf_counter() - t0                     # checksum + upload
+    same = bool(np.array_equal(G.evaluate(Xn), H.evaluate(Xn)))
+    print(json.dumps({"config": "cfg3-persist", "nodes": len(G), "upload_s": t_upload, "export_s": t_export,
+                      "import_s": t_import, "blob_bytes": int(dat["packed"].size), "identical_results": same}), flush=True)
+    del H, dat
+
     # ---- cfg5 -------------------------------------------------------------------------------------
     G = asg.SparseGridInterpolant(4)
     asg.rsg(G, 10, 10)

@@ -151,6 +151,15 @@ int32_t asg_nodes_x(asg_grid *g, int64_t first, int64_t n, double *Xout, int64_t
 int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                        int64_t sd, double *Xout, int64_t sp, int64_t sdim);
 
+/* ---- device-format persistence (interchange format stays the Dict of src/io.jl:30-38) ------------
+ * asg_grid_export writes the node arrays and every packed layout of the uploaded grid (current coefficients) as one
+ * blob: call with buf = NULL for the size, then with a buffer. asg_grid_import makes a blob the state of the handle
+ * like asg_grid_upload does, without validating, sorting or packing again; the handle must have the blob's D and
+ * domain. ASG_EUNSUPPORTED: written by a build with other layout constants (fall back to asg_grid_upload);
+ * ASG_EINVAL: not a blob / checksum mismatch / other dimension or domain. */
+int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes);
+int32_t asg_grid_import(asg_grid *g, const void *buf, int64_t bytes);
+
 /* ---- rsg! node enumeration (src/train.jl:40-78), host code, no device needed: the regular sparse grid node set
  * {l : l_d <= maxlevels_d, sum(l_d - 1) <= maxdepth - 1} in the reference's order (level vectors and index tuples in
  * Iterators.product order, dimension 1 fastest). Call _count, allocate N x D, call _fill (strides in elements). */

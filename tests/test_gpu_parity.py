@@ -595,3 +595,45 @@ def test_children_on_device(asg, oracle, cfg1, cfg2, cfg_nonunit):
         asg.adapt(G, f, 12, tol=1e-4, verbose=False, vectorized=True, device_candidates=dev)
     assert np.array_equal(Ga.levels, Gb.levels) and np.array_equal(Ga.indices, Gb.indices)
     assert np.array_equal(Ga.coefs, Gb.coefs)
+
+
+def test_packed_persistence(asg, oracle, cfg2, cfg_d10):
+    """serialize(G, packed=True) carries the device-format blob; deserialize uploads it
+    without packing again and evaluates bit-identically; corrupted / foreign blobs are rejected."""
+    import ctypes as C
+    rng = np.random.default_rng(8)
+    for OG in (cfg2, cfg_d10):
+        G = _mirror(asg, OG)
+        X = OG.lb + (OG.ub - OG.lb) * rng.random((5000, OG.D))
+        y = G.evaluate(X)
+        dat = asg.serialize(G, packed=True)
+        assert dat["levels"] is G.levels and dat["packed"].dtype == np.uint8 and dat["packed"].size > 16 * len(OG.levels)
+        H = asg.deserialize(dat)
+        assert H._dirty is False                               # no re-upload from the host arrays
+        i0, i1 = G.info(), H.info()
+        for k in ("N", "canonical", "subspaces", "coef_slots", "hash_slots", "block", "block_slots", "block_records", "regular"):
+            assert i0[k] == i1[k], k
+        for path in ("auto", "sweep"):
+            G.set_path(path); H.set_path(path)
+            assert np.array_equal(G.evaluate(X), H.evaluate(X))
+        assert np.array_equal(y, H.set_path("auto").evaluate(X))
+        G.set_path("auto")
+        B0, B1 = asg.basis(X[:50], G), asg.basis(X[:50], H)
+        assert (B0 != B1).nnz == 0
+        # coefficient updates after an import reach every layout
+        idx = np.arange(0, len(OG.levels), 7, dtype=np.int64)
+        vals = rng.standard_normal(len(idx))
+        for T in (G, H):
+            T.coefs[idx] = vals
+            asg._capi.check(asg._capi.load().asg_grid_scatter_coefs(T._ensure(), len(idx), idx.ctypes.data_as(asg._capi.i64p),
+                                                                      vals.ctypes.data_as(asg._capi.f64p)))
+        assert np.array_equal(G.evaluate(X), H.evaluate(X))
+        # corrupted blob / wrong handle
+        bad = dat["packed"].copy()
+        bad[len(bad) // 2] ^= 0x40
+        lib = asg._capi.load()
+        assert lib.asg_grid_import(H._grid(), bad.ctypes.data_as(C.c_void_p), bad.size) == asg._capi.ASG_EINVAL
+        assert "checksum" in lib.asg_last_error().decode()
+        other = asg.SparseGridInterpolant(OG.D, lb=OG.lb - 1.0, ub=OG.ub)
+        assert lib.asg_grid_import(other._grid(), dat["packed"].ctypes.data_as(C.c_void_p), dat["packed"].size) == asg._capi.ASG_EINVAL
+        assert np.array_equal(G.evaluate(X), H.evaluate(X))    # the failed imports left H untouched
