@@ -56,13 +56,15 @@ int max_compiled_dims() {  // experiment knob: ASG_BLOCK_MAXS=3 keeps one record
   return v;
 }
 
-// compiled suffix of S dimensions (D-S .. D-1), storage budget rs, evaluated up to budget reff, Horner form
+// compiled suffix of S dimensions (D-S .. D-1), storage budget rs, evaluated up to budget reff, Horner form.
+// Every read must stay inside the block of size(S, rs) doubles it belongs to: NaN (a failed self-check) otherwise.
 double eval_suffix_host(int D, int S, int rs, int reff, const double *blk, const double *x01) {
   if (S == 1) {  // pole
     const double xC = x01[D - 1];
     double inner = blk[0];
     for (int lC = 2; lC <= reff + 1; ++lC) {
       const uint32_t cC = cell_host(xC, lC);
+      if (blk_off1(lC) + cC >= blk_n1(rs)) return std::nan("");
       inner = std::fma(blk[blk_off1(lC) + cC], hat_host(xC, lC, cC), inner);
     }
     return inner;
@@ -72,6 +74,7 @@ double eval_suffix_host(int D, int S, int rs, int reff, const double *blk, const
   for (int l = 1; l <= reff + 1; ++l) {
     const int rb = rs - (l - 1);
     const uint32_t c = cell_host(x, l);
+    if (blk_off(S, l, rs) + ((size_t)c + 1) * blk_size(S - 1, rb) > blk_size(S, rs)) return std::nan("");
     const double sub = eval_suffix_host(D, S - 1, rb, reff - (l - 1), blk + blk_off(S, l, rs) + (size_t)c * blk_size(S - 1, rb), x01);
     out = l == 1 ? sub : std::fma(hat_host(x, l, c), sub, out);
   }
@@ -417,6 +420,7 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
     if (code == kBrNone) continue;
     const int S = (int)(code >> 3), rs = (int)(code & 7u);
     const int reff = std::min(rs, rem - used);
+    if ((uint64_t)q.cbase + (cO + 1) * blk_size(S, rs) > pk.bcoef.size()) return std::nan("");  // chunk outside the storage
     const double *chunk = pk.bcoef.data() + q.cbase + cO * blk_size(S, rs);
     acc = std::fma(cur, eval_suffix_host(D, S, rs, reff, chunk, x01), acc);
   }
