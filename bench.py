@@ -89,6 +89,24 @@ def fp64_op_counts_block(levels, records):
     return instr, flops, len(lv)
 
 
+def pin_to_gpu_numa_node(index):
+    """Multi-rank runs: bind this process (and the pinned host buffers it allocates afterwards) to the CPU cores
+    NVML reports as local to its GPU, so that the eight ranks' H2D streams do not all cross the socket link."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -232,6 +250,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     asg.init(local_rank)
@@ -429,6 +448,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "nodes": int(N), "subspaces": int(info["subspaces"]),
                    "points_per_step": M_total, "points_per_gpu": M, "parallelism": f"grid replicated, points sharded x{world}",
+                   "host_cores_bound_to_gpu_numa_node": numa,
                    "l2": "inputs larger than L2 (80 B/point * points_per_gpu >> 126 MB), no flush needed",
                    "engine": ("subspace/block" if block else "subspace/stream") if info["path"] == 2 else "sweep",
                    "point_order": "cell-key sorted inside the timed region (asg_sort.cu)" if block else "as given"},
