@@ -236,3 +236,16 @@ def test_block_walk_adapt_cfg4(asg):
             assert path == "block"       # the final grid may need more padding than the layout accepts
             continue
         assert np.max(np.abs(G.evaluate(X) - want)) < 5e-14, path
+
+
+@pytest.mark.gpu
+def test_engines_differential_fuzz():
+    """benchmarks/fuzz_paths.py: 80 random grids (D = 1..12, caps, node subsets, non-unit domains, adapt!-grown), every
+    engine against the sweep engine, unmasked and depth-masked, batches of 257 .. 2^20 points"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "fuzz_paths.py"), "80", "12345"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all grids agree" in r.stdout
