@@ -237,6 +237,7 @@ int device_upload(asg_grid *g, const PackResult &pk) {
       dg.n_brec = (uint32_t)pk.brec.size();
       dg.n_btiles = (uint32_t)pk.btiles.size();
       dg.blk_slots = pk.blk_slots;
+      dg.blk_tile_coefs = pk.blk_tile_coefs;
     }
   }
   CK(cudaStreamSynchronize(st));

@@ -37,7 +37,11 @@
 namespace asg {
 
 constexpr int kBlkMaxBudget = 7;     // suffix budget r <= 7  <=>  suffix levels <= 8 (register tables)
-constexpr int kBlkTileCoefs = 3072;  // doubles per shared-memory coefficient tile (24 KB)
+// doubles per shared-memory coefficient tile: the packer takes the largest candidate whose walk (two buffers of it,
+// the records, the coordinates and the prefix stack of 1024 points) still fits the 227 KB of an SM
+constexpr int kBlkTileCandidates[] = {6144, 4608, 3072, 2048, 1024};
+constexpr int kBlkTileCoefsMax = 6144;
+constexpr int kBlkThreadsWalk = 512;  // threads of the walk's CTA (two points each at full size)
 constexpr int kBlkTileRecs = 128;    // records per tile (4 KB)
 constexpr int kBlkMaxSlots = 8;      // saved prefix products: slots 0..7 (slot s = s non-trivial prefix dims)
 
@@ -64,8 +68,8 @@ static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "
 // leave r = 0 (one term), a quarter r = 1. Where a SHORTER prefix (S = 4, 5, 6 compiled dimensions) still has a
 // small budget, ONE record with a compiled S-dimensional suffix replaces all the records below it.
 #ifndef ASG_BLK_R4
-#define ASG_BLK_R4 4  // largest budget compiled for a 4-D suffix (70 terms)
-#define ASG_BLK_R5 3  // 5-D (56 terms)
+#define ASG_BLK_R4 5  // largest budget compiled for a 4-D suffix (126 terms)
+#define ASG_BLK_R5 4  // 5-D (126 terms)
 #define ASG_BLK_R6 3  // 6-D (84 terms)
 #define ASG_BLK_R7 2  // 7-D (36 terms)
 #endif

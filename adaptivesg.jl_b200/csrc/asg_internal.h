@@ -103,6 +103,7 @@ struct DeviceGrid {
   const BlockTile *btiles;
   uint32_t n_brec, n_btiles;
   int blk_slots;                    // saved prefix slots the walk needs (<= kBlkMaxSlots)
+  int blk_tile_coefs;               // doubles per coefficient tile buffer (chosen by the packer)
   // sweep engine (caller's node order)
   int64_t N;
   const SweepDim *sw;       // [N][D]
@@ -148,6 +149,7 @@ struct PackResult {
   std::vector<BlockTile> btiles;
   std::vector<int64_t> bslot_of_node;
   int blk_slots = 0;
+  int blk_tile_coefs = 0;             // coefficient tile size the tiles were cut for
   // sweep engine
   std::vector<SweepDim> sw;
   std::vector<uint64_t> sw_low;
@@ -207,6 +209,8 @@ cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStr
 cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 bool block_kernel_fits(const DeviceGrid &g);  // shared memory of the BLOCK walk fits an SM for this grid
+// shared memory (bytes) of the BLOCK walk: R points per thread, `threads` threads, D dimensions, stack slots, tile size
+size_t block_smem_bytes(int D, int slots, int tile_coefs, int R, int threads);
 // bit-interleaved cell-key ordering of the query points (asg_sort.cu): perm_out[j] = j-th point in key order
 size_t sort_points_temp_bytes(int64_t M);
 cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t sp, int64_t sd, uint32_t *keys,

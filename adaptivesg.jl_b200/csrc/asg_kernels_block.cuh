@@ -1,0 +1,415 @@
+// asg_kernels_block.cuh -- BLOCK walk of the subspace engine (sm_100a): the main evaluation kernel for
+// grids that are (nearly) regular in their last three dimensions (asg_block.h).
+//
+//   G(x) = sum_n c_n prod_d phi(x01_d; l_nd, i_nd)                       (src/class.jl:629-643)
+//
+// * One thread owns R = 2 query points, a CTA of 512 threads owns 1024 points and walks the whole record
+//   stream for them; one CTA per SM, grid-stride over the points.
+// * Records (16 B, one per prefix level vector) and the coefficient blocks they reference are streamed
+//   from L2 into shared memory by 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completed on
+//   mbarriers, double buffered.
+// * A record applies ONE data-driven stage (the level of its last non-trivial prefix dimension) to the
+//   prefix product / position saved by its parent record (a small stack in shared memory), then runs
+//   the COMPILED walk of the last three dimensions: the kernel is templated on the suffix budget, all
+//   levels and slot offsets are compile-time constants, so a term costs an address add, one LDS.64 and
+//   one DFMA, a pole (fixed levels of all dimensions but the last) one IMAD and one DFMA more.
+// * The hats of levels 2..4 of the last two dimensions live in per-point register tables; levels 5..8
+//   (286 of the 19 448 terms per point on the D = 10 benchmark grid) are formed on the fly.
+// The 1-D hat is the reference's phi (src/math.jl:345-357) evaluated on its support only, with the
+// reference's single rounding (asg_device.cuh). Out-of-domain / NaN points give exactly 0.0.
+#pragma once
+#include <cstdlib>
+
+#include "asg_device.cuh"
+
+namespace asg {
+
+constexpr int kBlkThreads = 512;  // default CTA size (384 threads x 168 registers was measured 6 % slower)
+constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulated in registers
+
+struct __align__(16) BlkSmem {
+  BlockRec rec[2][kBlkTileRecs];
+  unsigned long long bar[2];
+  // followed by  double coef[2][tile_coefs]  (the two coefficient tile buffers; size chosen by the packer),
+  //              double xs[D][R][threads]  (unit-cube coordinates of every dimension),
+  //              double Ps[slots][R][threads], uint32_t Os[slots][R][threads]  (saved prefixes)
+};
+
+template <int R>
+struct BlkPoint {
+  double phC[R][kBlkTab + 1];    // last dimension: hat of level l
+  uint32_t wC8[R][kBlkTab + 1];  // last dimension: (off1(l) + cell_l) * 8
+  double phB[R][kBlkTab + 1];    // dimension D-2: hat of level l
+  uint32_t cB[R][kBlkTab + 1];   // dimension D-2: cell of level l
+  double xA[R];                  // unit-cube coordinate of dimension D-3 (its hats are formed on the fly)
+  uint32_t qA[R];                // and its 30-bit cell key
+  uint32_t xsBC;                 // shared byte address of this thread's coordinate of dimension D-2 (point 0)
+  uint32_t xstride;              // bytes between consecutive points / dimensions in xs (threads * 8)
+};
+
+// coordinate of dimension D-2+which (which = 0, 1: B, C at rare levels; which < 0: dimensions above A of the
+// deeper compiled suffixes) of point k, from shared memory
+template <int R>
+__device__ __forceinline__ double blk_x_rare(const BlkPoint<R> &pt, int which, int k) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (int)pt.xstride)));
+  return v;
+}
+__device__ __forceinline__ uint32_t blk_key(double v) {  // floor(v * 2^30), clamped for v == 1 (exact)
+  return v < 1.0 ? (uint32_t)(v * 1073741824.0) : ((1u << kKeyBits) - 1u);
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <int IMM>
+__device__ __forceinline__ double lds_f64_imm(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+
+// hat and cell of the supporting node of compile-time level L >= 2
+template <int L>
+__device__ __forceinline__ void hat_ct(double x, uint32_t q, double &ph, uint32_t &cell) {
+  constexpr int b = blk_bits(L);
+  cell = q >> (kKeyBits - b);
+  const uint32_t i = (cell << 1) + (L > 2 ? 1u : 0u);
+  const double t = fma(x, (double)(1u << (L - 1)), -u32_to_f64(i));  // x*2^(l-1) - i, one rounding (math.jl:347)
+  ph = 1.0 - fabs(t);
+}
+
+// the same from the coordinate alone (dimensions whose key is not kept in a register)
+template <int L>
+__device__ __forceinline__ void hat_ct_x(double x, double &ph, uint32_t &cell) {
+  constexpr int b = blk_bits(L);
+  cell = min((uint32_t)(x * (double)(1u << b)), (1u << b) - 1u);  // floor(x*2^b), clamped for x == 1 (exact)
+  const uint32_t i = (cell << 1) + (L > 2 ? 1u : 0u);
+  const double t = fma(x, (double)(1u << (L - 1)), -u32_to_f64(i));
+  ph = 1.0 - fabs(t);
+}
+
+template <int L, int R>
+__device__ __forceinline__ void get_C(const BlkPoint<R> &pt, int k, double &ph, uint32_t &w8) {
+  if constexpr (L <= kBlkTab) {
+    ph = pt.phC[k][L];
+    w8 = pt.wC8[k][L];
+  } else {
+    uint32_t cell;
+    hat_ct_x<L>(blk_x_rare<R>(pt, 1, k), ph, cell);
+    w8 = (blk_off1(L) + cell) * 8u;
+  }
+}
+template <int L, int R>
+__device__ __forceinline__ void get_B(const BlkPoint<R> &pt, int k, double &ph, uint32_t &cell) {
+  if constexpr (L <= kBlkTab) {
+    ph = pt.phB[k][L];
+    cell = pt.cB[k][L];
+  } else {
+    hat_ct_x<L>(blk_x_rare<R>(pt, 0, k), ph, cell);
+  }
+}
+
+// ---- compiled suffix walk ---------------------------------------------------------------------------
+// pole: levels 1..RP+1 of the last dimension at shared byte address tp[k] + IMM
+template <int RP, int LC, int IMM, int R, bool MASKED>
+__device__ __forceinline__ void blk_pole(const BlkPoint<R> &pt, const uint32_t (&tp)[R], int reff, double (&inner)[R]) {
+  if constexpr (LC <= RP + 1) {
+    if (MASKED && LC - 1 > reff) return;
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      double ph;
+      uint32_t w8;
+      get_C<LC, R>(pt, k, ph, w8);
+      const double c = lds_f64_imm<IMM>(tp[k] + w8);
+      inner[k] = fma(c, ph, inner[k]);
+    }
+    blk_pole<RP, LC + 1, IMM, R, MASKED>(pt, tp, reff, inner);
+  }
+}
+
+// 2-D block of storage budget RB at shared byte address t2[k] + IMM: levels LB.. of dimension B (Horner form:
+// one DFMA per pole, none for level 1)
+template <int RB, int LB, int IMM, int R, bool MASKED>
+__device__ __forceinline__ void blk_suffix2(const BlkPoint<R> &pt, const uint32_t (&t2)[R], int reff, double (&accA)[R]) {
+  if constexpr (LB <= RB + 1) {
+    if (MASKED && LB - 1 > reff) return;
+    constexpr int RP = RB - (LB - 1);
+    constexpr int IMM2 = IMM + (int)blk_offB(LB, RB) * 8;
+    uint32_t tp[R];
+    double phB[R], inner[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if constexpr (LB == 1) {
+        tp[k] = t2[k];
+      } else {
+        uint32_t cell;
+        get_B<(LB > 1 ? LB : 2), R>(pt, k, phB[k], cell);
+        tp[k] = t2[k] + cell * (blk_n1(RP) * 8u);
+      }
+      inner[k] = lds_f64_imm<IMM2>(tp[k]);  // level 1 of the last dimension: phi = 1, cell = 0
+    }
+    blk_pole<RP, 2, IMM2, R, MASKED>(pt, tp, reff - (LB - 1), inner);
+#pragma unroll
+    for (int k = 0; k < R; ++k) accA[k] = LB == 1 ? inner[k] : fma(phB[k], inner[k], accA[k]);
+    blk_suffix2<RB, LB + 1, IMM, R, MASKED>(pt, t2, reff, accA);
+  }
+}
+
+// compiled suffix of S >= 3 dimensions (D-S .. D-1) of storage budget RS at shared byte address t[k] + IMM:
+// levels L.. of dimension D-S. S = 3: that dimension is A (coordinate and key in registers); S > 3: its
+// coordinate comes from shared memory (those records are few and small, see blk_max_r).
+template <int S, int RS, int L, int IMM, int R, bool MASKED>
+__device__ __forceinline__ void blk_suffixN(const BlkPoint<R> &pt, const uint32_t (&t)[R], int reff, double (&out)[R]) {
+  if constexpr (L <= RS + 1) {
+    if (MASKED && L - 1 > reff) return;
+    constexpr int RB = RS - (L - 1);
+    constexpr int IMM2 = IMM + (int)blk_off(S, L, RS) * 8;
+    uint32_t t2[R];
+    double ph[R], sub[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      if constexpr (L == 1) {
+        t2[k] = t[k];
+      } else {
+        uint32_t cell;
+        if constexpr (S == 3) {
+          hat_ct<(L > 1 ? L : 2)>(pt.xA[k], pt.qA[k], ph[k], cell);
+        } else {
+          // dimension D-S is S-2 rows above dimension D-2 in xs
+          hat_ct_x<(L > 1 ? L : 2)>(blk_x_rare<R>(pt, 2 - S, k), ph[k], cell);
+        }
+        t2[k] = t[k] + cell * (blk_size(S - 1, RB) * 8u);
+      }
+    }
+    if constexpr (S == 3) blk_suffix2<RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
+    else blk_suffixN<S - 1, RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
+#pragma unroll
+    for (int k = 0; k < R; ++k) out[k] = L == 1 ? sub[k] : fma(ph[k], sub[k], out[k]);
+    blk_suffixN<S, RS, L + 1, IMM, R, MASKED>(pt, t, reff, out);
+  }
+}
+
+// ---- the data-driven stage of a record ---------------------------------------------------------------
+template <int R>
+struct BlkStaged {     // a record after its stage: everything its compiled suffix needs
+  double cur[R];       // prefix product over dimensions 0..D-4 (S2: and A)
+  uint32_t t[R];       // cO * chunk bytes is formed by the suffix; here: prefix position
+  uint32_t sw;         // suffix code (blk_code(S, r), kBrNone), flags, used
+  uint32_t cb;         // shared byte address of the record's chunk 0
+};
+template <int R>
+struct BlkRegs {       // input of the current run of sibling records, kept in registers
+  double Pin[R], xin[R];
+};
+
+// Fetch the record at shared address rbase and apply its stage: hat of the level-l node of dimension k0
+// that supports the point, on top of the prefix saved by the parent record (stack slot ra.z).
+template <int R, bool MASKED, int NT>
+__device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_t os_t, uint32_t xs_t, uint32_t tbias,
+                                          int rem, BlkRegs<R> &in, BlkStaged<R> &out) {
+  uint4 ra, rb;  // {cbase, sw, slot, k0} {b, s_hi, lim, odd}
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(rbase));
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(rbase));
+  const uint32_t pa = ps_t + ra.z * (R * NT * 8u), oa = os_t + ra.z * (R * NT * 4u);
+  uint32_t Oin[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Oin[k]) : "r"(oa + k * (NT * 4u)));
+  if (!(ra.y & kBrSameIn)) {  // siblings (same parent, same stage dimension) keep these inputs in registers
+    const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      in.Pin[k] = lds_f64(pa + k * (NT * 8u));
+      in.xin[k] = lds_f64(xa + k * (NT * 8u));
+    }
+  }
+  const double s = __hiloint2double((int)rb.y, 0);                            // 2^(l-1), or 0 for the root record
+  const double s2b = __hiloint2double((int)((rb.x << 20) + 0x3ff00000u), 0);  // 2^b
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const uint32_t cell = min((uint32_t)(in.xin[k] * s2b), rb.z);  // floor(x*2^b), clamped for x == 1 (exact)
+    const double tt = fma(in.xin[k], s, -u32_to_f64((cell << 1) + rb.w));  // x*2^(l-1) - i, one rounding (math.jl:347)
+    out.cur[k] = in.Pin[k] * (1.0 - fabs(tt));
+    out.t[k] = (Oin[k] << rb.x) | cell;
+  }
+  if (ra.y & kBrSave) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(pa + (R + k) * (NT * 8u)), "d"(out.cur[k]));
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(oa + (R + k) * (NT * 4u)), "r"(out.t[k]));
+    }
+  }
+  out.sw = ra.y;
+  if (MASKED && (int)(ra.y >> kBrUsedShift) > rem) out.sw = (ra.y & ~0xffu) | kBrNone;  // depth mask: lies deeper
+  out.cb = ra.x * 8u + tbias;
+}
+
+// One record: the compiled suffix of the staged record. (Staging the NEXT record inside the same basic block,
+// so that ptxas interleaves the two dependency chains, was measured 5 % slower: registers.)
+template <int S, int RS, int R, bool MASKED>
+__device__ __forceinline__ void blk_record(const BlkPoint<R> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
+  uint32_t t[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) t[k] = st.t[k] * (blk_size(S, RS) * 8u) + st.cb;
+  const int reff = MASKED ? rem - (int)(st.sw >> kBrUsedShift) : 0;
+  double v[R];
+  if constexpr (S == 2) blk_suffix2<RS, 1, 0, R, MASKED>(pt, t, reff, v);
+  else blk_suffixN<S, RS, 1, 0, R, MASKED>(pt, t, reff, v);
+#pragma unroll
+  for (int k = 0; k < R; ++k) acc[k] = fma(st.cur[k], v[k], acc[k]);
+}
+
+// producer side (one thread): start the copies of tile t into buffer `buf`
+__device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm, uint32_t t, int buf) {
+  const BlockTile tl = g.btiles[t];
+  const uint32_t rbytes = (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
+  const uint32_t cbytes = (tl.c1 - tl.c0) * 8u;
+  // the buffer was last read through the generic proxy: order those reads before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(&sm.bar[buf], rbytes + cbytes);
+  tma_load_1d(sm.rec[buf], g.brec + tl.r0, rbytes, &sm.bar[buf]);
+  if (cbytes)
+    tma_load_1d(reinterpret_cast<double *>(&sm + 1) + (size_t)buf * g.blk_tile_coefs, g.bcoef + tl.c0, cbytes, &sm.bar[buf]);
+}
+
+// registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
+template <int R, bool MASKED, int NT>
+__global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid g, const EvalArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  BlkSmem &sm = *reinterpret_cast<BlkSmem *>(smem_raw);
+  const int D = g.D;
+  const int K = D - 3;
+  double *coefbuf = reinterpret_cast<double *>(smem_raw + sizeof(BlkSmem));
+  double *xs = coefbuf + 2 * (size_t)g.blk_tile_coefs;
+  double *Ps = xs + (size_t)D * R * NT;
+  uint32_t *Os = reinterpret_cast<uint32_t *>(Ps + (size_t)g.blk_slots * R * NT);
+  const uint32_t tid = threadIdx.x;
+  // shared byte addresses of this thread's column in xs / Ps / Os
+  uint32_t xs_t = smem_u32(xs) + tid * 8u;
+  uint32_t ps_t = smem_u32(Ps) + tid * 8u;
+  uint32_t os_t = smem_u32(Os) + tid * 4u;
+  const int64_t tile_pts = (int64_t)NT * R;
+  const int64_t stride = (int64_t)gridDim.x * tile_pts;
+  const uint32_t ntiles = g.n_btiles;
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {  // slot 0: the empty prefix (never overwritten)
+    Ps[k * NT + tid] = 1.0;
+    Os[k * NT + tid] = 0u;
+  }
+  __syncthreads();
+  uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
+
+  for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
+    BlkPoint<R> pt;
+    pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
+    pt.xstride = NT * 8u;
+    uint32_t inside = 0u;  // bit k: point k lies in the domain
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t j = base + (int64_t)k * NT + tid;
+      const int64_t jj = j < a.M ? j : a.M - 1;  // tail lanes redo the last point, never store
+      const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
+      bool in = true;
+      for (int d = 0; d < D; ++d) {
+        const double xd = a.X[mm * a.sp + d * a.sd];
+        const double u = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));  // scale(), src/math.jl:308
+        in = in && (u >= 0.0) && (u <= 1.0);                                             // NaN fails both
+        xs[(d * R + k) * NT + tid] = u;
+      }
+      if (in) inside |= 1u << k;
+      else  // walked at the centre of the cube; the result is replaced by the exact 0.0
+        for (int d = 0; d < D; ++d) xs[(d * R + k) * NT + tid] = 0.5;
+      const double uA = xs[(K * R + k) * NT + tid], uB = xs[((K + 1) * R + k) * NT + tid], uC = xs[((K + 2) * R + k) * NT + tid];
+      const uint32_t qB = blk_key(uB), qC = blk_key(uC);
+      pt.xA[k] = uA;
+      pt.qA[k] = blk_key(uA);
+#pragma unroll
+      for (int l = 2; l <= kBlkTab; ++l) {
+        uint32_t cell;
+        hat_cell(uC, qC, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phC[k][l], cell);
+        pt.wC8[k][l] = (blk_off1(l) + cell) * 8u;
+        hat_cell(uB, qB, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phB[k][l], pt.cB[k][l]);
+        pin_f64(pt.phC[k][l]); pin_u32(pt.wC8[k][l]);
+        pin_f64(pt.phB[k][l]); pin_u32(pt.cB[k][l]);
+      }
+    }
+    if (tid == 0) {
+      blk_issue_tile(g, sm, 0, 0);
+      if (ntiles > 1) blk_issue_tile(g, sm, 1, 1);
+    }
+    double acc[R];
+    BlkRegs<R> in;
+#pragma unroll
+    for (int k = 0; k < R; ++k) { acc[k] = 0.0; in.Pin[k] = 1.0; in.xin[k] = 0.5; }
+
+    for (uint32_t t = 0; t < ntiles; ++t) {
+      const int buf = (int)(t & 1u);
+      const BlockTile tl = g.btiles[t];
+      mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
+      phases ^= 1u << buf;
+      uint32_t rbase = smem_u32(sm.rec[buf]);
+      uint32_t tbias = smem_u32(coefbuf + (size_t)buf * g.blk_tile_coefs) - tl.c0 * 8u;  // shared byte address of coefficient slot 0
+      pin_u32(rbase);
+      pin_u32(tbias);
+      pin_u32(xs_t);  // keep the three column addresses in registers: ptxas would re-derive them per record
+      pin_u32(ps_t);
+      pin_u32(os_t);
+      const uint32_t rend = rbase + (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
+      for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
+        BlkStaged<R> st;
+        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, in, st);
+#define BLK_CASE(S, RS) \
+  case blk_code(S, RS): if constexpr (S <= 3 || RS <= blk_max_r(S)) blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
+        // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
+        // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
+        const uint32_t code = st.sw & 0xffu;
+        if (code == blk_code(3, 0)) blk_record<3, 0, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == blk_code(3, 1)) blk_record<3, 1, R, MASKED>(pt, st, a.rem, acc);
+        else if (code == blk_code(3, 2)) blk_record<3, 2, R, MASKED>(pt, st, a.rem, acc);
+        else switch (code) {
+          BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
+          BLK_CASE(2, 0) BLK_CASE(2, 1) BLK_CASE(2, 2) BLK_CASE(2, 3) BLK_CASE(2, 4) BLK_CASE(2, 5) BLK_CASE(2, 6) BLK_CASE(2, 7)
+          BLK_CASE(4, 1) BLK_CASE(4, 2) BLK_CASE(4, 3) BLK_CASE(4, 4) BLK_CASE(4, 5)
+          BLK_CASE(5, 1) BLK_CASE(5, 2) BLK_CASE(5, 3) BLK_CASE(5, 4)
+          BLK_CASE(6, 1) BLK_CASE(6, 2) BLK_CASE(6, 3) BLK_CASE(6, 4)
+          BLK_CASE(7, 1) BLK_CASE(7, 2) BLK_CASE(7, 3)
+          BLK_CASE(8, 1) BLK_CASE(8, 2)
+          default: break;  // kBrNone: a stage-only record
+        }
+#undef BLK_CASE
+      }
+      __syncthreads();  // every warp is done with buffer `buf`
+      if (tid == 0 && t + 2 < ntiles) blk_issue_tile(g, sm, t + 2, buf);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int64_t j = base + (int64_t)k * NT + tid;
+      if (j < a.M) {
+        const int64_t mm = a.perm ? (int64_t)a.perm[j] : j;
+        const double v = ((inside >> k) & 1u) ? acc[k] : 0.0;
+        a.out[mm] = a.fvals ? (a.fvals[mm] - v) : v;
+      }
+    }
+  }
+}
+
+// One launch function per (points per thread, masked) variant; each is instantiated in its own translation unit
+// (asg_kernels_block_r{1,2}{,m}.cu) so that the four large kernels compile in parallel.
+template <int R, bool MASKED, int NT>
+void blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
+  // one instantiation serves every grid: raise its dynamic shared-memory limit ONCE to the device maximum (setting
+  // it per launch to the launch's own size races between host threads that evaluate different grids)
+  static const cudaError_t once =
+      cudaFuncSetAttribute(k_eval_block<R, MASKED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  (void)once;
+  k_eval_block<R, MASKED, NT><<<blocks, NT, smem, st>>>(g, a);
+}
+
+}  // namespace asg

@@ -1,0 +1,6 @@
+// asg_kernels_block_r1.cu -- the BLOCK walk with 1 point per thread, unmasked (see asg_kernels_block.cuh)
+#include "asg_kernels_block.cuh"
+
+namespace asg {
+template void blk_launch<1, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+}  // namespace asg

@@ -1,0 +1,6 @@
+// asg_kernels_block_r1m.cu -- the BLOCK walk with 1 point per thread, depth-masked (see asg_kernels_block.cuh)
+#include "asg_kernels_block.cuh"
+
+namespace asg {
+template void blk_launch<1, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+}  // namespace asg

@@ -1,0 +1,6 @@
+// asg_kernels_block_r2m.cu -- the BLOCK walk with 2 points per thread, depth-masked (see asg_kernels_block.cuh)
+#include "asg_kernels_block.cuh"
+
+namespace asg {
+template void blk_launch<2, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+}  // namespace asg

@@ -47,6 +47,25 @@ inline uint32_t cell_host(double x, int l) {
   return std::min(c, (1u << b) - 1u);
 }
 
+// the layout functions of asg_block.h are recursive (made for compile-time use): tabulate them once for the host
+struct BlkTables {
+  uint32_t size[kBlkMaxS + 1][kBlkMaxBudget + 1];
+  uint32_t off[kBlkMaxS + 1][kBlkMaxBudget + 3][kBlkMaxBudget + 1];
+  BlkTables() {
+    for (int S = 1; S <= kBlkMaxS; ++S)
+      for (int r = 0; r <= kBlkMaxBudget; ++r) {
+        size[S][r] = blk_size(S, r);
+        for (int l = 1; l <= kBlkMaxBudget + 2; ++l) off[S][l][r] = S >= 2 ? blk_off(S, l, r) : 0u;
+      }
+  }
+};
+const BlkTables &tabs() {
+  static const BlkTables t;
+  return t;
+}
+inline uint32_t t_size(int S, int r) { return r < 0 ? 0u : tabs().size[S][r]; }
+inline uint32_t t_off(int S, int l, int r) { return tabs().off[S][l][r]; }
+
 int max_compiled_dims() {  // experiment knob: ASG_BLOCK_MAXS=3 keeps one record per prefix level vector
   static const int v = [] {
     const char *e = getenv("ASG_BLOCK_MAXS");
@@ -74,8 +93,8 @@ double eval_suffix_host(int D, int S, int rs, int reff, const double *blk, const
   for (int l = 1; l <= reff + 1; ++l) {
     const int rb = rs - (l - 1);
     const uint32_t c = cell_host(x, l);
-    if (blk_off(S, l, rs) + ((size_t)c + 1) * blk_size(S - 1, rb) > blk_size(S, rs)) return std::nan("");
-    const double sub = eval_suffix_host(D, S - 1, rb, reff - (l - 1), blk + blk_off(S, l, rs) + (size_t)c * blk_size(S - 1, rb), x01);
+    if (t_off(S, l, rs) + ((size_t)c + 1) * t_size(S - 1, rb) > t_size(S, rs)) return std::nan("");
+    const double sub = eval_suffix_host(D, S - 1, rb, reff - (l - 1), blk + t_off(S, l, rs) + (size_t)c * t_size(S - 1, rb), x01);
     out = l == 1 ? sub : std::fma(hat_host(x, l, c), sub, out);
   }
   return out;
@@ -83,9 +102,39 @@ double eval_suffix_host(int D, int S, int rs, int reff, const double *blk, const
 
 }  // namespace
 
+static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm,
+                            const double *coefs, bool selfcheck, int tile_coefs, PackResult &out, std::string &err);
+
+// Try the tile sizes from the largest down: a larger tile lets more prefixes take a deep compiled suffix (fewer
+// records, a shallower stack), but two buffers of it must fit the SM next to the per-point state of the walk.
 int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm, const double *coefs,
                 bool selfcheck, PackResult &out, std::string &err) {
+  static const int forced = [] { const char *e = getenv("ASG_BLOCK_TILE"); return e ? atoi(e) : 0; }();  // experiment knob
+  std::string first_why;
+  for (int tc : kBlkTileCandidates) {
+    if (forced && tc != forced) continue;
+    const int rc = pack_blocks_tile(D, N, lv, cells, perm, coefs, selfcheck, tc, out, err);
+    if (rc != ASG_OK) return rc;
+    if (!out.blk_ok) {  // limits that do not depend on the tile size end the search
+      if (first_why.empty()) first_why = out.blk_why;
+      if (out.blk_why.find("tile") == std::string::npos && out.blk_why.find("padding") == std::string::npos) return ASG_OK;
+      continue;
+    }
+    if (block_smem_bytes(D, out.blk_slots, tc, 2, kBlkThreadsWalk) <= 227u * 1024u) return ASG_OK;
+    if (tc == kBlkTileCandidates[sizeof(kBlkTileCandidates) / sizeof(int) - 1] &&
+        block_smem_bytes(D, out.blk_slots, tc, 1, kBlkThreadsWalk) <= 227u * 1024u)
+      return ASG_OK;  // smallest tile, one point per thread
+    out.blk_ok = false;
+    out.blk_why = "the walk's shared memory does not fit an SM";
+  }
+  if (!out.blk_ok && !first_why.empty() && out.blk_why.empty()) out.blk_why = first_why;
+  return ASG_OK;
+}
+
+static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm,
+                            const double *coefs, bool selfcheck, int tile_coefs, PackResult &out, std::string &err) {
   out.blk_ok = false;
+  out.blk_tile_coefs = tile_coefs;
   out.blk_why.clear();
   out.bcoef.clear(); out.brec.clear(); out.btiles.clear(); out.bslot_of_node.clear();
   auto no = [&](const char *w) { out.blk_why = w; return ASG_OK; };
@@ -93,7 +142,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
   if (D - 3 > 15) return no("D > 18");
   if (N <= 0) return no("empty grid");
   const int K = D - 3;  // longest prefix: dimensions 0..K-1; A = K, B = K+1, C = K+2
-  const uint64_t cap = (uint64_t)kBlkTileCoefs - 2;  // a tile window is aligned down / up to even slots
+  const uint64_t cap = (uint64_t)tile_coefs - 2;  // a tile window is aligned down / up to even slots
 
   // 1. full-length prefix level vectors and the budgets of their 3-D suffixes
   std::map<Key, int> pre;  // -> max sum(l-1) over dimensions A, B, C
@@ -136,7 +185,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
             rsub = std::max(rsub, e);
           }
           for (int j = 0; j < d; ++j) pb += blk_bits((*keys[g0])[(size_t)j]);
-          if (rsub >= 1 && rsub <= blk_max_r(S) && pb <= 24 && (((uint64_t)blk_size(S, rsub)) << pb) <= cap) {
+          if (rsub >= 1 && rsub <= blk_max_r(S) && pb <= 24 && (((uint64_t)t_size(S, rsub)) << pb) <= cap) {
             Key key(keys[g0]->begin(), keys[g0]->begin() + d);
             key.resize((size_t)K, 1);
             Rec R;
@@ -196,14 +245,14 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
     }
     if (I.pb > 24) return no("prefix position needs more than 24 bits");
     if (I.r >= 0) {
-      const uint64_t sz = ((uint64_t)blk_size(I.S, I.r)) << I.pb;
+      const uint64_t sz = ((uint64_t)t_size(I.S, I.r)) << I.pb;
       if (sz <= cap) {
         I.cbase = (uint32_t)total;
         total += sz;
       } else {  // only S = 3 records can be too large (deeper suffixes were admitted by size)
         I.split = true;
         for (int lA = 1; lA <= I.r + 1; ++lA) {
-          const uint64_t s2 = ((uint64_t)blk_size2(I.r - (lA - 1))) << (I.pb + blk_bits(lA));
+          const uint64_t s2 = ((uint64_t)t_size(2, I.r - (lA - 1))) << (I.pb + blk_bits(lA));
           if (s2 > cap) return no("a suffix block exceeds the shared-memory tile");
           I.cbaseA[lA - 1] = (uint32_t)total;
           total += s2;
@@ -242,19 +291,19 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       uint64_t slot;
       int rr = pi->r;
       if (!pi->split) {
-        slot = pi->cbase + O * blk_size(pi->S, pi->r);
+        slot = pi->cbase + O * t_size(pi->S, pi->r);
         for (int j = pi->S; j >= 3; --j) {  // compiled dimensions above the 2-D block, outermost first
           const int l = L[D - j];
-          slot += blk_off(j, l, rr) + (uint64_t)C[D - j] * blk_size(j - 1, rr - (l - 1));
+          slot += t_off(j, l, rr) + (uint64_t)C[D - j] * t_size(j - 1, rr - (l - 1));
           rr -= l - 1;
         }
       } else {
         const int lA = L[K];
         rr -= lA - 1;
-        slot = pi->cbaseA[lA - 1] + ((O << blk_bits(lA)) | C[K]) * blk_size2(rr);
+        slot = pi->cbaseA[lA - 1] + ((O << blk_bits(lA)) | C[K]) * t_size(2, rr);
       }
       const int lB = L[K + 1], lC = L[K + 2];
-      slot += (uint64_t)blk_offB(lB, rr) + (uint64_t)C[K + 1] * blk_n1(rr - (lB - 1)) + blk_off1(lC) + C[K + 2];
+      slot += (uint64_t)t_off(2, lB, rr) + (uint64_t)C[K + 1] * blk_n1(rr - (lB - 1)) + blk_off1(lC) + C[K + 2];
       if (slot >= total || out.bslot_of_node[(size_t)n] != -1) {  // duplicates were rejected before: packer bug
         err = "internal error: block slot out of range or assigned twice";
         return ASG_ESTATE;
@@ -295,7 +344,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
-      hi.push_back(I.cbase + (blk_size(I.S, I.r) << I.pb));
+      hi.push_back(I.cbase + (t_size(I.S, I.r) << I.pb));
     } else {
       for (int lA = 1; lA <= I.r + 1; ++lA) {
         BlockRec s = q;
@@ -308,7 +357,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
         s.cbase = I.cbaseA[lA - 1];
         out.brec.push_back(s);
         lo.push_back(s.cbase);
-        hi.push_back(s.cbase + (blk_size2(rA) << (I.pb + blk_bits(lA))));
+        hi.push_back(s.cbase + (t_size(2, rA) << (I.pb + blk_bits(lA))));
       }
       prev_k0 = -1;  // the next prefix record follows S2 records of another dimension
     }
@@ -327,7 +376,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
             t.c0 = a; t.c1 = b; have = true;
           } else {
             const uint32_t na = std::min(t.c0, a), nb = std::max(t.c1, b);
-            if (nb - na > (uint32_t)kBlkTileCoefs) break;
+            if (nb - na > (uint32_t)tile_coefs) break;
             t.c0 = na; t.c1 = nb;
           }
         }
@@ -337,7 +386,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
       out.btiles.push_back(t);
     }
     for (const BlockTile &t : out.btiles) {
-      if (t.c1 - t.c0 > (uint32_t)kBlkTileCoefs || t.r1 - t.r0 > (uint32_t)kBlkTileRecs || (t.c0 & 1u) || (t.c1 & 1u) ||
+      if (t.c1 - t.c0 > (uint32_t)tile_coefs || t.r1 - t.r0 > (uint32_t)kBlkTileRecs || (t.c0 & 1u) || (t.c1 & 1u) ||
           (uint64_t)t.c1 > out.bcoef.size()) {
         err = "internal error: block tile out of bounds";
         return ASG_ESTATE;
@@ -420,8 +469,8 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
     if (code == kBrNone) continue;
     const int S = (int)(code >> 3), rs = (int)(code & 7u);
     const int reff = std::min(rs, rem - used);
-    if ((uint64_t)q.cbase + (cO + 1) * blk_size(S, rs) > pk.bcoef.size()) return std::nan("");  // chunk outside the storage
-    const double *chunk = pk.bcoef.data() + q.cbase + cO * blk_size(S, rs);
+    if ((uint64_t)q.cbase + (cO + 1) * t_size(S, rs) > pk.bcoef.size()) return std::nan("");  // chunk outside the storage
+    const double *chunk = pk.bcoef.data() + q.cbase + cO * t_size(S, rs);
     acc = std::fma(cur, eval_suffix_host(D, S, rs, reff, chunk, x01), acc);
   }
   return acc;
