@@ -103,7 +103,6 @@ static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words"
 ASG_HD constexpr uint32_t blk_code(int S, int r) { return (uint32_t)(8 * S + r); }
 constexpr uint32_t kBrNone = 255u;  // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
-constexpr uint32_t kBrSameIn = 1u << 9;  // same input slot and stage dimension as the previous record (siblings)
 constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2: including dimension A): depth mask
 
 struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)

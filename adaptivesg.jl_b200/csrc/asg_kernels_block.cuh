@@ -44,7 +44,6 @@ struct BlkPoint {
   double xA[R];                  // unit-cube coordinate of dimension D-3 (its hats are formed on the fly)
   uint32_t qA[R];                // and its 30-bit cell key
   uint32_t xsBC;                 // shared byte address of this thread's coordinate of dimension D-2 (point 0)
-  uint32_t xstride;              // bytes between consecutive points / dimensions in xs (threads * 8)
 };
 
 // coordinate of dimension D-2+which (which = 0, 1: B, C at rare levels; which < 0: dimensions above A of the
@@ -52,7 +51,7 @@ struct BlkPoint {
 template <int R>
 __device__ __forceinline__ double blk_x_rare(const BlkPoint<R> &pt, int which, int k) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (int)pt.xstride)));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (kBlkThreads * 8))));
   return v;
 }
 __device__ __forceinline__ uint32_t blk_key(double v) {  // floor(v * 2^30), clamped for v == 1 (exact)
@@ -200,16 +199,12 @@ struct BlkStaged {     // a record after its stage: everything its compiled suff
   uint32_t sw;         // suffix code (blk_code(S, r), kBrNone), flags, used
   uint32_t cb;         // shared byte address of the record's chunk 0
 };
-template <int R>
-struct BlkRegs {       // input of the current run of sibling records, kept in registers
-  double Pin[R], xin[R];
-};
 
 // Fetch the record at shared address rbase and apply its stage: hat of the level-l node of dimension k0
 // that supports the point, on top of the prefix saved by the parent record (stack slot ra.z).
 template <int R, bool MASKED, int NT>
 __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_t os_t, uint32_t xs_t, uint32_t tbias,
-                                          int rem, BlkRegs<R> &in, BlkStaged<R> &out) {
+                                          int rem, BlkStaged<R> &out) {
   uint4 ra, rb;  // {cbase, sw, slot, k0} {b, s_hi, lim, odd}
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(rbase));
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(rbase));
@@ -217,21 +212,22 @@ __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_
   uint32_t Oin[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Oin[k]) : "r"(oa + k * (NT * 4u)));
-  if (!(ra.y & kBrSameIn)) {  // siblings (same parent, same stage dimension) keep these inputs in registers
-    const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
+  // (keeping the inputs of sibling records -- same parent, same stage dimension -- in registers instead of
+  // re-loading them was measured 4 % SLOWER: the eight registers are worth more to the compiled suffix)
+  const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
+  double Pin[R], xin[R];
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      in.Pin[k] = lds_f64(pa + k * (NT * 8u));
-      in.xin[k] = lds_f64(xa + k * (NT * 8u));
-    }
+  for (int k = 0; k < R; ++k) {
+    Pin[k] = lds_f64(pa + k * (NT * 8u));
+    xin[k] = lds_f64(xa + k * (NT * 8u));
   }
   const double s = __hiloint2double((int)rb.y, 0);                            // 2^(l-1), or 0 for the root record
   const double s2b = __hiloint2double((int)((rb.x << 20) + 0x3ff00000u), 0);  // 2^b
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const uint32_t cell = min((uint32_t)(in.xin[k] * s2b), rb.z);  // floor(x*2^b), clamped for x == 1 (exact)
-    const double tt = fma(in.xin[k], s, -u32_to_f64((cell << 1) + rb.w));  // x*2^(l-1) - i, one rounding (math.jl:347)
-    out.cur[k] = in.Pin[k] * (1.0 - fabs(tt));
+    const uint32_t cell = min((uint32_t)(xin[k] * s2b), rb.z);  // floor(x*2^b), clamped for x == 1 (exact)
+    const double tt = fma(xin[k], s, -u32_to_f64((cell << 1) + rb.w));  // x*2^(l-1) - i, one rounding (math.jl:347)
+    out.cur[k] = Pin[k] * (1.0 - fabs(tt));
     out.t[k] = (Oin[k] << rb.x) | cell;
   }
   if (ra.y & kBrSave) {
@@ -309,7 +305,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
     BlkPoint<R> pt;
     pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
-    pt.xstride = NT * 8u;
+    static_assert(NT == kBlkThreads, "blk_x_rare assumes the default CTA size");
     uint32_t inside = 0u;  // bit k: point k lies in the domain
 #pragma unroll
     for (int k = 0; k < R; ++k) {
@@ -345,9 +341,8 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       if (ntiles > 1) blk_issue_tile(g, sm, 1, 1);
     }
     double acc[R];
-    BlkRegs<R> in;
 #pragma unroll
-    for (int k = 0; k < R; ++k) { acc[k] = 0.0; in.Pin[k] = 1.0; in.xin[k] = 0.5; }
+    for (int k = 0; k < R; ++k) acc[k] = 0.0;
 
     for (uint32_t t = 0; t < ntiles; ++t) {
       const int buf = (int)(t & 1u);
@@ -364,7 +359,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       const uint32_t rend = rbase + (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
       for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
         BlkStaged<R> st;
-        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, in, st);
+        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, st);
 #define BLK_CASE(S, RS) \
   case blk_code(S, RS): if constexpr (S <= 3 || RS <= blk_max_r(S)) blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
         // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:

@@ -323,18 +323,12 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     q.odd = l > 2 ? 1u : 0u;
     q.sw = (save ? kBrSave : 0u) | ((uint32_t)used << kBrUsedShift);
   };
-  Key prev_parent;
-  int prev_k0 = -1;
   for (auto &kv : recs) {
     const Key &p = kv.first;
     const Rec &I = kv.second;
     BlockRec q{};
     const int l0 = I.nt ? p[(size_t)I.k0] : 1;
     stage_of(q, I.nt ? I.nt - 1 : 0, I.k0, l0, I.parent_of && I.nt, I.used);
-    const Key par = parent_of(p);
-    if (I.nt && prev_k0 == I.k0 && par == prev_parent) q.sw |= kBrSameIn;  // sibling of the previous record
-    prev_parent = par;
-    prev_k0 = I.nt ? I.k0 : -1;
     if (I.r < 0) {
       q.sw |= kBrNone;
       out.brec.push_back(q);
@@ -351,7 +345,6 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
         const int rA = I.r - (lA - 1);
         if (lA > 1) {  // stage = level lA of dimension A, restart from the prefix product this prefix saved
           stage_of(s, I.nt, K, lA, false, I.used + lA - 1);
-          if (lA > 2) s.sw |= kBrSameIn;
         }
         s.sw |= blk_code(2, rA);
         s.cbase = I.cbaseA[lA - 1];
@@ -359,7 +352,6 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
         lo.push_back(s.cbase);
         hi.push_back(s.cbase + (t_size(2, rA) << (I.pb + blk_bits(lA))));
       }
-      prev_k0 = -1;  // the next prefix record follows S2 records of another dimension
     }
   }
   // 7. tiles: consecutive records whose spans fit one coefficient buffer
@@ -446,14 +438,10 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
   P[0] = 1.0;
   O[0] = 0;
   double acc = 0.0;
-  double Pin = 1.0, xin = 0.0;
   for (const BlockRec &q : pk.brec) {
     const int used = (int)(q.sw >> kBrUsedShift);
     if (used > rem) continue;
-    if (!(q.sw & kBrSameIn)) {  // siblings keep the input of the previous record in registers
-      Pin = P[q.slot];
-      xin = x01[q.k0];
-    }
+    const double Pin = P[q.slot], xin = x01[q.k0];
     const uint64_t Oin = O[q.slot];
     double s;
     {
