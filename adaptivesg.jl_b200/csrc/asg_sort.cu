@@ -58,7 +58,7 @@ cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t
   // out-of-domain keys are 0xffffffff: sort on all 32 bits when any plane is cut so that they stay last
   e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t *)keys, keys_alt, (const uint32_t *)idx, perm_out,
                                       (int)M, 0, 32, st);
-  if (launches) *launches += 4;  // histogram + onesweep passes of the library sort
+  // (the histogram / onesweep passes of the library sort are not counted as launches of this library's kernels)
   (void)end_bit;
   return e;
 }
