@@ -402,9 +402,12 @@ int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, in
 int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
               int64_t max_depth, double *out) {
   const int D = g->D;
-  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 22);  // 4 Mi points per pipeline slot
+  // chunk sizes ramp up 1 Mi, 2 Mi, 4 Mi, 8 Mi, 8 Mi, ...: the first copy (the only one no kernel hides) is short,
+  // the later chunks are large enough for the cell-key ordering of the BLOCK walk to bite
+  const int64_t first = std::min<int64_t>(M, (int64_t)1 << 20);
+  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 23);  // buffer size per pipeline slot
   std::vector<double> repack_buf;
-  const int nslot = M > chunk ? 2 : 1;
+  const int nslot = M > first ? 2 : 1;
   for (int s = 0; s < nslot; ++s) {
     if (int rc = g->s_X[s].reserve((size_t)chunk * D)) return rc;
     if (int rc = g->s_out[s].reserve((size_t)chunk)) return rc;
@@ -412,8 +415,10 @@ int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim,
       if (int rc = g->s_f[s].reserve((size_t)chunk)) return rc;
   }
   int slot = 0;
-  for (int64_t m0 = 0; m0 < M; m0 += chunk, slot ^= (nslot - 1)) {
-    const int64_t cnt = std::min(chunk, M - m0);
+  int64_t next = first;
+  for (int64_t m0 = 0, cnt = 0; m0 < M; m0 += cnt, slot ^= (nslot - 1)) {
+    cnt = std::min(next, M - m0);
+    next = std::min(2 * next, chunk);
     cudaStream_t st = ctx.pipe[slot];
     EvalArgs a{};
     if (int rc = stage_points(X, m0, cnt, D, sp, sdim, g->s_X[slot].p, a.sp, a.sd, st, repack_buf)) return rc;
