@@ -1076,6 +1076,58 @@ int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int6
   return ASG_OK;
 }
 
+int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                           int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals) {
+  if (int rc = check_eval_args(g, X, M, row_ptr)) return rc;
+  if (!colptr) return set_err(ASG_EINVAL, "null colptr");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  const int64_t N = g->N;
+  if (M == 0) {
+    for (int64_t c = 0; c <= N; ++c) colptr[c] = 0;
+    return ASG_OK;
+  }
+  const int64_t nnz = row_ptr[M];
+  if (nnz < 0 || nnz >= ((int64_t)1 << 31) || (nnz > 0 && (!rowidx || !vals))) return set_err(ASG_EINVAL, "bad CSC buffers");
+  cudaStream_t st = ctx.stream;
+  BasisArgs a{};
+  if (int rc = upload_points(g, X, M, sp, sdim, a.sp, a.sd, st)) return rc;
+  if (int rc = g->s_i64a.reserve((size_t)M + 1)) return rc;
+  if (int rc = g->s_i64b.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
+  if (int rc = g->s_tmp.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
+  CK(cudaMemcpyAsync(g->s_i64a.p, row_ptr, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, st));
+  a.X = g->s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 1;
+  a.row_ptr = g->s_i64a.p; a.colidx = g->s_i64b.p; a.vals = g->s_tmp.p;
+  CK(run_basis(g, a, st));
+  // CSR -> CSC: stable sort of the entries by column (rows stay ascending inside a column); scratch shared with the
+  // point ordering of the BLOCK walk (slot 1 holds the outputs)
+  const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
+  const size_t tb = csc_temp_bytes(std::max<int64_t>(nnz, 1));
+  if (int rc = g->s_key[0].reserve(n1)) return rc;
+  if (int rc = g->s_key2[0].reserve(n1)) return rc;
+  if (int rc = g->s_idx[0].reserve(n1)) return rc;
+  if (int rc = g->s_perm[0].reserve(n1)) return rc;
+  if (int rc = g->s_key[1].reserve(n1)) return rc;
+  if (int rc = g->s_sorttmp[0].reserve(tb)) return rc;
+  DevBuf<long long> &d_colptr = g->c_PL, &d_rowidx = g->c_PI;  // adapt! scratch, free between calls
+  if (int rc = d_colptr.reserve((size_t)N + 1)) return rc;
+  if (int rc = d_rowidx.reserve(n1)) return rc;
+  if (int rc = g->s_tmp2.reserve(n1)) return rc;
+  if (g->sort_ev[0]) CK(cudaStreamWaitEvent(st, g->sort_ev[0], 0));
+  int64_t l = 0;
+  CK(csr_to_csc(g->s_i64a.p, g->s_i64b.p, g->s_tmp.p, M, N, nnz, g->s_key[0].p, g->s_key2[0].p, g->s_idx[0].p,
+                g->s_perm[0].p, g->s_key[1].p, g->s_sorttmp[0].p, tb, d_colptr.p, d_rowidx.p, g->s_tmp2.p, st, &l));
+  bump(l);
+  CK(cudaMemcpyAsync(colptr, d_colptr.p, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (nnz) {
+    CK(cudaMemcpyAsync(rowidx, d_rowidx.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vals, g->s_tmp2.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  g->ch_n = -1;  // the adapt! scratch was reused
+  return ASG_OK;
+}
+
 int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, double atol,
                                int32_t dropzeros, double *dout, int64_t ldm, int64_t ldn, void *stream) {
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;

@@ -216,6 +216,12 @@ size_t sort_points_temp_bytes(int64_t M);
 cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t sp, int64_t sd, uint32_t *keys,
                         uint32_t *keys_alt, uint32_t *idx, uint32_t *perm_out, void *temp, size_t temp_bytes,
                         cudaStream_t st, int64_t *launches);
+// CSR -> CSC of a basis matrix on the device (asg_sort.cu)
+size_t csc_temp_bytes(int64_t nnz);
+cudaError_t csr_to_csc(const long long *row_ptr, const long long *colidx, const double *vals, int64_t M, int64_t N,
+                       int64_t nnz, uint32_t *keys, uint32_t *keys_alt, uint32_t *ent, uint32_t *perm, uint32_t *rows,
+                       void *temp, size_t temp_bytes, long long *colptr, long long *rowidx, double *vout, cudaStream_t st,
+                       int64_t *launches);
 cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);

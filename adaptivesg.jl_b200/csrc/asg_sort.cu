@@ -64,3 +64,70 @@ cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t
 }
 
 }  // namespace asg
+
+// ---- CSR -> CSC on the device (basis matrices: SparseMatrixCSC is what the reference returns, src/class.jl:483-503) ----
+namespace asg {
+
+__global__ void k_csr_expand(const long long *row_ptr, int64_t M, const long long *colidx, uint32_t *keys, uint32_t *ent,
+                             uint32_t *rows) {
+  // one warp per row: entry e of row m gets key = its column, payload = e, and remembers m
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t m = warp; m < M; m += nwarps)
+    for (long long e = row_ptr[m] + lane; e < row_ptr[m + 1]; e += 32) {
+      keys[e] = (uint32_t)colidx[e];
+      ent[e] = (uint32_t)e;
+      rows[e] = (uint32_t)m;
+    }
+}
+__global__ void k_csc_gather(int64_t nnz, const uint32_t *perm, const uint32_t *rows, const double *vals, long long *rowidx,
+                             double *vout) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t e = perm[k];
+    rowidx[k] = rows[e];
+    vout[k] = vals[e];
+  }
+}
+__global__ void k_csc_colptr(int64_t nnz, int64_t N, const uint32_t *sorted_cols, long long *colptr) {
+  // colptr[c] = first position whose column is >= c (binary search in the sorted column keys)
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c <= N; c += (int64_t)gridDim.x * blockDim.x) {
+    int64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)sorted_cols[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    colptr[c] = lo;
+  }
+}
+
+size_t csc_temp_bytes(int64_t nnz) { return sort_points_temp_bytes(nnz); }
+
+// CSR (row_ptr, colidx, vals; rows in ascending order) -> CSC (colptr, rowidx, vout): a STABLE sort of the entries by
+// column keeps the rows ascending inside every column. keys / keys_alt / ent / perm / rows: nnz uint32 each.
+cudaError_t csr_to_csc(const long long *row_ptr, const long long *colidx, const double *vals, int64_t M, int64_t N,
+                       int64_t nnz, uint32_t *keys, uint32_t *keys_alt, uint32_t *ent, uint32_t *perm, uint32_t *rows,
+                       void *temp, size_t temp_bytes, long long *colptr, long long *rowidx, double *vout, cudaStream_t st,
+                       int64_t *launches) {
+  if (nnz <= 0) {
+    k_csc_colptr<<<(int)((N + 256) / 256), 256, 0, st>>>(0, N, keys, colptr);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+  }
+  int64_t blocks = (M * 32 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_csr_expand<<<(int)blocks, 256, 0, st>>>(row_ptr, M, colidx, keys, ent, rows);
+  int bits = 1;
+  while (((int64_t)1 << bits) < N) ++bits;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t *)keys, keys_alt, (const uint32_t *)ent, perm,
+                                                  (int)nnz, 0, bits, st);
+  if (e != cudaSuccess) return e;
+  blocks = (nnz + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_csc_gather<<<(int)blocks, 256, 0, st>>>(nnz, perm, rows, vals, rowidx, vout);
+  k_csc_colptr<<<(int)((N + 256) / 256), 256, 0, st>>>(nnz, N, keys_alt, colptr);
+  if (launches) *launches += 3;
+  return cudaGetLastError();
+}
+
+}  // namespace asg

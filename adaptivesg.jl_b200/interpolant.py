@@ -402,13 +402,15 @@ def coefficients(G: SparseGridInterpolant) -> np.ndarray:
 # -------------------------------------------------------------------------------------------------
 # basis family (src/class.jl:434-567)
 # -------------------------------------------------------------------------------------------------
-def basis(*args, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16, dense: bool = False):
+def basis(*args, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16, dense: bool = False,
+          format: str = "csc"):
     """``basis(x, G)`` / ``basis(Xs, G)`` / ``basis(G)`` (src/class.jl:434-454, 483-503, 521-538).
 
     Documented intent (the reference body multiplies an all-zero sparse vector):
     row m, column n is ``prod_d phi(x01_md; l_nd, i_nd)``; entries ``< atol`` are dropped when
     ``dropzeros``; exact zeros are always dropped.  Returns a ``scipy.sparse.csc_matrix`` of shape
-    (M, N) (1 x N for a single point), or a dense ndarray with ``dense=True``.  ``safe`` is accepted
+    (M, N) (1 x N for a single point; ``format="csr"`` keeps the row-major form the device produces and skips the
+    host-side transposition), or a dense ndarray with ``dense=True``.  ``safe`` is accepted
     on all three methods (the reference forwards it to a method that lacks it)."""
     import scipy.sparse as sps
 
@@ -438,9 +440,17 @@ def basis(*args, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16,
     np.cumsum(nnz, out=ptr[1:])
     col = np.empty(int(ptr[-1]), dtype=np.int64)
     val = np.empty(int(ptr[-1]), dtype=np.float64)
-    check(lib.asg_basis_fill(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(col, i64p),
-                             _ptr(val, f64p)))
-    return sps.csr_matrix((val, col, ptr), shape=(M, N)).tocsc()
+    if format == "csr":
+        check(lib.asg_basis_fill(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(col, i64p),
+                                 _ptr(val, f64p)))
+        B = sps.csr_matrix((val, col, ptr), shape=(M, N))
+    else:  # the reference's SparseMatrixCSC: transposed on the device (stable sort of the entries by column)
+        cptr = np.empty(N + 1, dtype=np.int64)
+        check(lib.asg_basis_fill_csc(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(cptr, i64p),
+                                     _ptr(col, i64p), _ptr(val, f64p)))
+        B = sps.csc_matrix((val, col, cptr), shape=(M, N))
+    B.has_sorted_indices = True  # ascending columns in every row / ascending rows in every column
+    return B
 
 
 def dehierarchization_matrix(G, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16):

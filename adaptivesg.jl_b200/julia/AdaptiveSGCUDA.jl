@@ -229,13 +229,13 @@ function basis(Xs::AbstractMatrix, G::SparseGridInterpolant{D}; safe::Bool = tru
     GC.@preserve X check(ccall((:asg_basis_count, LIB), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Int32, Ptr{Int64}),
         h, X, M, 1, max(M, 1), atol, dropzeros, nnzr))
-    rowptr = vcat(0, cumsum(nnzr)); col = Vector{Int64}(undef, rowptr[end]); val = Vector{Float64}(undef, rowptr[end])
-    GC.@preserve X check(ccall((:asg_basis_fill, LIB), Int32,
-        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
-        h, X, M, 1, max(M, 1), atol, dropzeros, rowptr, col, val))
-    rows = Vector{Int}(undef, length(col))
-    for m in 1:M, p in (rowptr[m] + 1):rowptr[m + 1]; rows[p] = m; end
-    return sparse(rows, col .+ 1, val, M, N)                              # 0-based -> 1-based columns
+    rowptr = vcat(0, cumsum(nnzr)); rows = Vector{Int64}(undef, rowptr[end]); val = Vector{Float64}(undef, rowptr[end])
+    colptr = Vector{Int64}(undef, N + 1)
+    # compressed sparse COLUMNS straight from the device (stable sort of the entries by column): no host transposition
+    GC.@preserve X check(ccall((:asg_basis_fill_csc, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Int64, Float64, Int32, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        h, X, M, 1, max(M, 1), atol, dropzeros, rowptr, colptr, rows, val))
+    return SparseMatrixCSC(M, N, colptr .+ 1, rows .+ 1, val)             # 0-based -> 1-based
 end
 basis(x::AbstractVector, G::SparseGridInterpolant; kw...) = sparsevec(vec(Matrix(basis(reshape(collect(Float64, x), 1, :), G; kw...))))
 basis(G::SparseGridInterpolant{D}; kw...) where {D} =

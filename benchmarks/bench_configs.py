@@ -121,6 +121,7 @@ def main():
     M = 50000
     X = rng.random((M, 4))
     t_sparse = timed(lambda: asg.basis(X, G), reps=2)
+    t_sparse_csr = timed(lambda: asg.basis(X, G, format="csr"), reps=2)   # without the host-side CSR -> CSC transposition
     B = asg.basis(X, G)
     y = G.evaluate(X)
     err = float(np.max(np.abs(B @ G.coefs - y)))
@@ -145,7 +146,7 @@ def main():
     k_ms = float(np.median(ts))
     gbs = M * N * 8 / (k_ms * 1e-3) / 1e9
     nnz_dense = int(torch.count_nonzero(out).item())
-    print(json.dumps({"config": "cfg5", "nodes": N, "points": M, "sparse_basis_s": t_sparse, "nnz": int(B.nnz),
+    print(json.dumps({"config": "cfg5", "nodes": N, "points": M, "sparse_basis_s": t_sparse, "sparse_basis_csr_s": t_sparse_csr, "nnz": int(B.nnz),
                       "nnz_per_row": B.nnz / M, "B_times_C_vs_eval_max_abs": err, "dense_ms": k_ms,
                       "dense_bytes": M * N * 8, "dense_write_GBps": gbs, "hbm_peak_GBps": peaks.get("hbm_gbs"),
                       "dense_frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None,

@@ -189,6 +189,10 @@ int32_t asg_basis_count(asg_grid *g, const double *X, int64_t M, int64_t sp, int
 int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                        int32_t dropzeros, const int64_t *row_ptr, int64_t *colidx, double *vals);
 /* dense variant: out[m*ldm + n*ldn], every element written (zeros included) */
+/* the same entries as asg_basis_fill, transposed on the device into compressed sparse COLUMNS - the SparseMatrixCSC the
+ * reference returns (src/class.jl:483-503): colptr[N+1], rowidx / vals [row_ptr[M]], 0-based, rows ascending in a column */
+int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                           int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals);
 int32_t asg_basis_dense(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                         int32_t dropzeros, double *out, int64_t ldm, int64_t ldn);
 /* dense variant into a DEVICE buffer (bench: HBM-write roofline without the D2H copy) */

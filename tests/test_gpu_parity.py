@@ -637,3 +637,24 @@ def test_packed_persistence(asg, oracle, cfg2, cfg_d10):
         other = asg.SparseGridInterpolant(OG.D, lb=OG.lb - 1.0, ub=OG.ub)
         assert lib.asg_grid_import(other._grid(), dat["packed"].ctypes.data_as(C.c_void_p), dat["packed"].size) == asg._capi.ASG_EINVAL
         assert np.array_equal(G.evaluate(X), H.evaluate(X))    # the failed imports left H untouched
+
+
+def test_basis_csc_on_device(asg, cfg1, cfg2, cfg_nonunit):
+    """asg_basis_fill_csc: the CSR rows transposed on the device into the SparseMatrixCSC the reference returns
+    (src/class.jl:483-503) -- identical entries, canonical form (rows ascending inside every column)."""
+    rng = np.random.default_rng(17)
+    for OG in (cfg1, cfg2, cfg_nonunit):
+        G = _mirror(asg, OG)
+        X = np.vstack([OG.lb + (OG.ub - OG.lb) * rng.random((700, OG.D)), OG.stack()[:300]])
+        R = asg.basis(X, G, format="csr")
+        Cm = asg.basis(X, G)
+        assert Cm.format == "csc" and R.format == "csr" and Cm.shape == R.shape == (len(X), len(OG.levels))
+        Rc = R.tocsc()
+        Rc.sort_indices()
+        assert np.array_equal(Cm.indptr, Rc.indptr) and np.array_equal(Cm.indices, Rc.indices)
+        assert np.array_equal(Cm.data, Rc.data)
+        assert np.array_equal(Cm.toarray(), OG.basis(X))
+    E = asg.basis(_mirror(asg, cfg1))                      # basis(G): N x N, unit diagonal
+    assert E.format == "csc" and np.all(E.diagonal() == 1.0)
+    Z = asg.basis(np.full((3, 3), 7.5), _mirror(asg, cfg1))   # points outside the domain: empty matrix
+    assert Z.nnz == 0 and Z.shape == (3, len(cfg1.levels))
