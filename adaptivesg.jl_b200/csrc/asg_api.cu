@@ -705,9 +705,9 @@ int32_t asg_grid_set_path(asg_grid *g, int32_t path) {
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   if (path < ASG_PATH_AUTO || path > ASG_PATH_BLOCK) return set_err(ASG_EINVAL, "bad path");
-  if (path >= ASG_PATH_SUBSPACE && g->uploaded && !(g->canonical && g->finite))
+  if (path >= ASG_PATH_SUBSPACE && g->uploaded && g->N > 0 && !(g->canonical && g->finite))
     return set_err(ASG_EUNSUPPORTED, "grid is not canonical (" + g->why + "): only the sweep engine applies");
-  if (path == ASG_PATH_BLOCK && g->uploaded && !(g->blk_ok && block_kernel_fits(g->dg)))
+  if (path == ASG_PATH_BLOCK && g->uploaded && g->N > 0 && !(g->blk_ok && block_kernel_fits(g->dg)))
     return set_err(ASG_EUNSUPPORTED, "grid has no BLOCK layout (" + g->blk_why + ")");
   g->forced_path = path;
   return ASG_OK;
