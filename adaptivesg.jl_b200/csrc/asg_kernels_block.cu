@@ -42,8 +42,8 @@ cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream
   if (a.M <= 0) return cudaSuccess;
   const int sms = blk_sm_count();
   const int nt = blk_threads();
-  // two points per thread when the batch fills the machine and the shared memory fits, else one
-  bool two = a.M >= (int64_t)sms * nt * 2 && blk_smem_bytes(g, 2, nt) <= 227 * 1024;
+  // two points per thread as soon as one-point CTAs would need a second wave (and the shared memory fits)
+  bool two = a.M > (int64_t)sms * nt && blk_smem_bytes(g, 2, nt) <= 227 * 1024;
   if (const char *e = getenv("ASG_BLOCK_R")) two = (e[0] == '2') && blk_smem_bytes(g, 2, nt) <= 227 * 1024;  // experiment knob
   const int R = two ? 2 : 1;
   const size_t smem = blk_smem_bytes(g, R, nt);
