@@ -60,6 +60,9 @@ vp = C.c_void_p
 # name -> (argtypes); every function returns int32 except the two string getters
 SIGNATURES = {
     "asg_init": [C.c_int32],
+    "asg_init_devices": [C.POINTER(C.c_int32), C.c_int32],
+    "asg_context_devices": [C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)],
+    "asg_phi": [C.c_int64, C.c_int32, f64p, i64p, i64p, f64p],
     "asg_shutdown": [],
     "asg_device_count": [C.POINTER(C.c_int32)],
     "asg_launch_count": [i64p],
@@ -93,6 +96,7 @@ SIGNATURES = {
     "asg_measure_fp64_peak": [f64p],
     "asg_grid_export": [vp, vp, C.c_int64, i64p],
     "asg_grid_import": [vp, vp, C.c_int64],
+    "asg_grid_import_checked": [vp, vp, C.c_int64, C.c_int64, i64p, i64p, C.c_int64, C.c_int64, f64p],
     "asg_rsg_count": [C.c_int32, C.c_int64, i64p, i64p],
     "asg_rsg_fill": [C.c_int32, C.c_int64, i64p, C.c_int64, i64p, i64p, C.c_int64, C.c_int64],
     "asg_children": [vp, C.c_int64, i64p, i64p, i64p],
@@ -135,16 +139,46 @@ def check(rc: int):
 
 
 _init_device = None
+_init_devices = None
 
 
 def init(device: int | None = None) -> int:
     """asg_init on `device` (default: LOCAL_RANK or 0). Raises AsgError(ASG_ENODEVICE) without a B200."""
-    global _init_device
+    global _init_device, _init_devices
     if device is None:
-        device = int(os.environ.get("LOCAL_RANK", "0")) if _init_device is None else _init_device
+        if _init_device is not None:
+            return _init_device
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    if _init_devices is not None and len(_init_devices) > 1 and _init_devices[0] == int(device):
+        return _init_device  # a wider context with this primary device is already up
     check(load().asg_init(int(device)))
     _init_device = int(device)
+    _init_devices = [int(device)]
     return _init_device
+
+
+def init_devices(devices) -> list:
+    """asg_init_devices: one process drives several GPUs of the box; every grid keeps a replica per device and the
+    host-buffer calls (evaluate / surplus / train) split their points over them. devices[0] is the primary."""
+    global _init_device, _init_devices
+    devs = [int(d) for d in devices]
+    arr = (C.c_int32 * len(devs))(*devs)
+    check(load().asg_init_devices(arr, len(devs)))
+    _init_device, _init_devices = devs[0], devs
+    return devs
+
+
+def context_devices() -> list:
+    n = C.c_int32()
+    arr = (C.c_int32 * 16)()
+    check(load().asg_context_devices(arr, 16, C.byref(n)))
+    return [int(arr[k]) for k in range(n.value)]
+
+
+def shutdown():
+    global _init_device, _init_devices
+    check(load().asg_shutdown())
+    _init_device = _init_devices = None
 
 
 def device_ready() -> bool:

@@ -10,6 +10,8 @@
 #include <memory>
 #include <thread>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler is attached
+
 #include "asg_internal.h"
 
 using namespace asg;
@@ -25,18 +27,26 @@ int set_err(int code, const std::string &msg) {
   return code;
 }
 
+constexpr int kMaxDev = 16;   // devices one process may drive (asg_init_devices)
+constexpr int kPipeSlots = 3;  // host-buffer pipeline depth per device
+
+struct DevCtx {  // per device: streams and events of this library
+  int device = -1;
+  cudaStream_t stream = nullptr;                 // library stream (device-pointer entry points, uploads)
+  cudaStream_t pipe[kPipeSlots] = {};            // host-buffer pipeline: H2D k+1 / walk k / D2H k-1 overlap
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // around the last *_device call
+  cudaEvent_t evw0 = nullptr, evw1 = nullptr;    // around its walk kernel alone (BLOCK walk: after the point ordering)
+  bool walk_timed = false;
+  bool last_timed = false;
+};
+
 struct Context {
   std::mutex mu;
   bool ready = false;
-  int device = -1;
-  cudaStream_t stream = nullptr;      // library stream (device-pointer entry points)
-  cudaStream_t pipe[2] = {nullptr, nullptr};  // host-buffer pipelines (double buffering)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the last *_device call
-  cudaEvent_t evw0 = nullptr, evw1 = nullptr;  // around its walk kernel alone (BLOCK walk: after the point ordering)
-  bool walk_timed = false;
+  int ndev = 0;
+  DevCtx dev[kMaxDev];
+  int last_dev = 0;  // replica of the last timed *_device call
   std::atomic<long long> launches{0};
-  double last_ms = 0.0;
-  bool last_timed = false;
 } ctx;
 
 #define CK(call)                                                                                   \
@@ -49,11 +59,15 @@ struct Context {
     }                                                                                              \
   } while (0)
 
-int require_ctx() {
-  if (!ctx.ready) return set_err(ASG_ENODEVICE, "asg_init has not succeeded: no sm_100 device selected (no CPU fallback)");
-  cudaError_t e = cudaSetDevice(ctx.device);
+int use_dev(int r) {  // make replica r's device current for the calling thread
+  cudaError_t e = cudaSetDevice(ctx.dev[r].device);
   if (e != cudaSuccess) return set_err(ASG_ECUDA, cudaGetErrorString(e));
   return ASG_OK;
+}
+
+int require_ctx() {
+  if (!ctx.ready) return set_err(ASG_ENODEVICE, "asg_init has not succeeded: no sm_100 device selected (no CPU fallback)");
+  return use_dev(0);
 }
 
 template <class T>
@@ -80,7 +94,58 @@ struct DevBuf {  // grow-only device buffer
 
 void bump(int64_t n) { ctx.launches += n; }
 
+// NVTX range around a C-ABI call (tracing), visible in nsys / ncu --nvtx
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define ASG_TRACE() NvtxRange nvtx_range_(__func__)
+
 }  // namespace
+
+// device storage of one grid on one device (replica 0 is the primary: basis, children and node coordinates run there)
+struct Replica {
+  DeviceGrid dg{};
+  DevBuf<TrieRec> d_rec;
+  DevBuf<GroupRec> d_grp;
+  DevBuf<StreamTile> d_tiles;
+  DevBuf<double> d_bcoef;
+  DevBuf<BlockRec> d_brec;
+  DevBuf<BlockTile> d_btiles;
+  DevBuf<double> d_coef, d_sw_coef;
+  DevBuf<int32_t> d_orig, d_horig, d_sw_depth;
+  DevBuf<HashEnt> d_hent;
+  DevBuf<SweepDim> d_sw;
+  DevBuf<uint64_t> d_sw_low;
+  // scratch for host-buffer calls (one set per pipeline slot)
+  DevBuf<double> s_X[kPipeSlots], s_out[kPipeSlots], s_f[kPipeSlots];
+  DevBuf<long long> s_i64a, s_i64b;
+  DevBuf<double> s_tmp, s_tmp2;
+  DevBuf<int> s_flag;
+  // adapt! candidate generation (asg_kernels_adapt.cu): the unique children of the last asg_children call
+  DevBuf<long long> c_PL, c_PI, c_CL, c_CI, c_OL, c_OI;
+  DevBuf<unsigned char> c_valid;
+  DevBuf<int> c_table;
+  DevBuf<unsigned int> c_flags, c_sums;
+  // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
+  DevBuf<uint32_t> s_key[kPipeSlots], s_key2[kPipeSlots], s_idx[kPipeSlots], s_perm[kPipeSlots];
+  DevBuf<unsigned char> s_sorttmp[kPipeSlots];
+  cudaEvent_t sort_ev[kPipeSlots] = {};  // last use of the slot's scratch
+  void release_all() {
+    d_rec.release(); d_grp.release(); d_tiles.release(); d_bcoef.release(); d_brec.release(); d_btiles.release();
+    d_coef.release(); d_sw_coef.release(); d_orig.release(); d_horig.release(); d_sw_depth.release(); d_hent.release();
+    d_sw.release(); d_sw_low.release();
+    for (int s = 0; s < kPipeSlots; ++s) {
+      s_X[s].release(); s_out[s].release(); s_f[s].release();
+      s_key[s].release(); s_key2[s].release(); s_idx[s].release(); s_perm[s].release(); s_sorttmp[s].release();
+      if (sort_ev[s]) cudaEventDestroy(sort_ev[s]);
+      sort_ev[s] = nullptr;
+    }
+    c_PL.release(); c_PI.release(); c_CL.release(); c_CI.release(); c_OL.release(); c_OI.release();
+    c_valid.release(); c_table.release(); c_flags.release(); c_sums.release();
+    s_i64a.release(); s_i64b.release(); s_tmp.release(); s_tmp2.release(); s_flag.release();
+  }
+};
 
 struct asg_grid {
   std::recursive_mutex mu;
@@ -99,36 +164,10 @@ struct asg_grid {
   std::string why;
   int forced_path = ASG_PATH_AUTO;
   asg_grid_info_t info{};
-  DeviceGrid dg{};
-  // device storage
-  DevBuf<TrieRec> d_rec;
-  DevBuf<GroupRec> d_grp;
-  DevBuf<StreamTile> d_tiles;
-  DevBuf<double> d_bcoef;
-  DevBuf<BlockRec> d_brec;
-  DevBuf<BlockTile> d_btiles;
-  DevBuf<double> d_coef, d_sw_coef;
-  DevBuf<int32_t> d_orig, d_horig, d_sw_depth;
-  DevBuf<HashEnt> d_hent;
-  DevBuf<SweepDim> d_sw;
-  DevBuf<uint64_t> d_sw_low;
-  // scratch for host-buffer calls (two pipeline slots)
-  DevBuf<double> s_X[2], s_out[2], s_f[2];
-  DevBuf<long long> s_i64a, s_i64b;
-  DevBuf<double> s_tmp, s_tmp2;
-  DevBuf<int> s_flag;
-  // adapt! candidate generation (asg_kernels_adapt.cu): the unique children of the last asg_children call
-  DevBuf<long long> c_PL, c_PI, c_CL, c_CI, c_OL, c_OI;
-  DevBuf<unsigned char> c_valid;
-  DevBuf<int> c_table;
-  DevBuf<unsigned int> c_flags, c_sums;
+  Replica rep[kMaxDev];  // one per device of the context; all hold the same packed layouts
   int64_t ch_n = -1, ch_generation = -1;
   std::vector<unsigned char> blob;  // asg_grid_export: between the size query and the copy
   int64_t blob_generation = -1;
-  // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
-  DevBuf<uint32_t> s_key[2], s_key2[2], s_idx[2], s_perm[2];
-  DevBuf<unsigned char> s_sorttmp[2];
-  cudaEvent_t sort_ev[2] = {nullptr, nullptr};  // last use of the slot's scratch
   int path() const {
     if (forced_path == ASG_PATH_SWEEP) return ASG_PATH_SWEEP;
     return (canonical && finite) ? ASG_PATH_SUBSPACE : ASG_PATH_SWEEP;
@@ -138,6 +177,7 @@ struct asg_grid {
   // 2 = recursive trie walk (ASG_PATH_TRIE, D == 1, or ASG_EVAL_KERNEL=trie)
   int walk() const {
     static const char *env = getenv("ASG_EVAL_KERNEL");
+    const DeviceGrid &dg = rep[0].dg;
     if (forced_path == ASG_PATH_TRIE || D < 2 || dg.n_tiles == 0) return 2;
     if (forced_path == ASG_PATH_STREAM) return 0;
     if (forced_path == ASG_PATH_BLOCK) return (blk_ok && block_kernel_fits(dg)) ? 3 : 0;
@@ -149,6 +189,13 @@ struct asg_grid {
   }
 };
 
+// bring replica r of g into scope of a function body
+#define USE_REPLICA(g, r)        \
+  Replica &R = (g)->rep[(r)];    \
+  DevCtx &dc = ctx.dev[(r)];     \
+  (void)R;                       \
+  (void)dc
+
 struct asg_event {
   std::thread th;
   int rc = ASG_OK;
@@ -157,10 +204,12 @@ struct asg_event {
 
 namespace {
 
-int device_upload(asg_grid *g, const PackResult &pk) {
+int device_upload(asg_grid *g, int r, const PackResult &pk) {
+  if (int rc = use_dev(r)) return rc;
+  USE_REPLICA(g, r);
   const int D = g->D;
   const int64_t N = g->N;
-  DeviceGrid &dg = g->dg;
+  DeviceGrid &dg = R.dg;
   dg = DeviceGrid{};
   dg.D = D;
   for (int d = 0; d < D; ++d) {
@@ -169,71 +218,71 @@ int device_upload(asg_grid *g, const PackResult &pk) {
     dg.width[d] = w;
   }
   dg.N = N;
-  cudaStream_t st = ctx.stream;
+  cudaStream_t st = dc.stream;
   // sweep engine arrays (always present: they serve every node set)
-  if (int rc = g->d_sw.reserve((size_t)N * D)) return rc;
-  if (int rc = g->d_sw_low.reserve((size_t)N)) return rc;
-  if (int rc = g->d_sw_coef.reserve((size_t)N)) return rc;
-  if (int rc = g->d_sw_depth.reserve((size_t)N)) return rc;
+  if (int rc = R.d_sw.reserve((size_t)N * D)) return rc;
+  if (int rc = R.d_sw_low.reserve((size_t)N)) return rc;
+  if (int rc = R.d_sw_coef.reserve((size_t)N)) return rc;
+  if (int rc = R.d_sw_depth.reserve((size_t)N)) return rc;
   if (N) {
-    CK(cudaMemcpyAsync(g->d_sw.p, pk.sw.data(), (size_t)N * D * sizeof(SweepDim), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(g->d_sw_low.p, pk.sw_low.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(g->d_sw_coef.p, g->coefs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(g->d_sw_depth.p, pk.depth.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw.p, pk.sw.data(), (size_t)N * D * sizeof(SweepDim), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_low.p, pk.sw_low.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_coef.p, g->coefs.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_depth.p, pk.depth.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
   }
-  dg.sw = g->d_sw.p;
-  dg.sw_low = g->d_sw_low.p;
-  dg.sw_coef = g->d_sw_coef.p;
-  dg.sw_depth = g->d_sw_depth.p;
+  dg.sw = R.d_sw.p;
+  dg.sw_low = R.d_sw_low.p;
+  dg.sw_coef = R.d_sw_coef.p;
+  dg.sw_depth = R.d_sw_depth.p;
   // subspace engine arrays
   if (pk.canonical) {
     size_t total = 0;
     for (int k = 0; k < D; ++k) total += pk.rec[(size_t)k].size();
-    if (int rc = g->d_rec.reserve(total)) return rc;
+    if (int rc = R.d_rec.reserve(total)) return rc;
     size_t off = 0;
     for (int k = 0; k < D; ++k) {
       const auto &r = pk.rec[(size_t)k];
-      CK(cudaMemcpyAsync(g->d_rec.p + off, r.data(), r.size() * sizeof(TrieRec), cudaMemcpyHostToDevice, st));
-      dg.rec[k] = g->d_rec.p + off;
+      CK(cudaMemcpyAsync(R.d_rec.p + off, r.data(), r.size() * sizeof(TrieRec), cudaMemcpyHostToDevice, st));
+      dg.rec[k] = R.d_rec.p + off;
       off += r.size();
     }
     dg.n_root = (uint32_t)(pk.rec[0].size() - 1);
-    if (int rc = g->d_coef.reserve(pk.coef.size())) return rc;
-    if (int rc = g->d_orig.reserve(pk.orig.size())) return rc;
-    if (int rc = g->d_hent.reserve(pk.hent.size())) return rc;
-    if (int rc = g->d_horig.reserve(pk.horig.size())) return rc;
+    if (int rc = R.d_coef.reserve(pk.coef.size())) return rc;
+    if (int rc = R.d_orig.reserve(pk.orig.size())) return rc;
+    if (int rc = R.d_hent.reserve(pk.hent.size())) return rc;
+    if (int rc = R.d_horig.reserve(pk.horig.size())) return rc;
     if (!pk.coef.empty()) {
-      CK(cudaMemcpyAsync(g->d_coef.p, pk.coef.data(), pk.coef.size() * 8, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(g->d_orig.p, pk.orig.data(), pk.orig.size() * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_coef.p, pk.coef.data(), pk.coef.size() * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_orig.p, pk.orig.data(), pk.orig.size() * 4, cudaMemcpyHostToDevice, st));
     }
     if (!pk.hent.empty()) {
-      CK(cudaMemcpyAsync(g->d_hent.p, pk.hent.data(), pk.hent.size() * sizeof(HashEnt), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(g->d_horig.p, pk.horig.data(), pk.horig.size() * 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_hent.p, pk.hent.data(), pk.hent.size() * sizeof(HashEnt), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_horig.p, pk.horig.data(), pk.horig.size() * 4, cudaMemcpyHostToDevice, st));
     }
-    if (int rc = g->d_grp.reserve(pk.grp.size())) return rc;
-    if (int rc = g->d_tiles.reserve(pk.tiles.size())) return rc;
+    if (int rc = R.d_grp.reserve(pk.grp.size())) return rc;
+    if (int rc = R.d_tiles.reserve(pk.tiles.size())) return rc;
     if (!pk.grp.empty()) {
-      CK(cudaMemcpyAsync(g->d_grp.p, pk.grp.data(), pk.grp.size() * sizeof(GroupRec), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(g->d_tiles.p, pk.tiles.data(), pk.tiles.size() * sizeof(StreamTile), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_grp.p, pk.grp.data(), pk.grp.size() * sizeof(GroupRec), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_tiles.p, pk.tiles.data(), pk.tiles.size() * sizeof(StreamTile), cudaMemcpyHostToDevice, st));
     }
-    dg.grp = g->d_grp.p;
-    dg.tiles = g->d_tiles.p;
+    dg.grp = R.d_grp.p;
+    dg.tiles = R.d_tiles.p;
     dg.n_grp = (uint32_t)pk.grp.size();
     dg.n_tiles = (uint32_t)pk.tiles.size();
-    dg.coef = g->d_coef.p;
-    dg.orig = g->d_orig.p;
-    dg.hent = g->d_hent.p;
-    dg.horig = g->d_horig.p;
+    dg.coef = R.d_coef.p;
+    dg.orig = R.d_orig.p;
+    dg.hent = R.d_hent.p;
+    dg.horig = R.d_horig.p;
     if (pk.blk_ok) {
-      if (int rc = g->d_bcoef.reserve(pk.bcoef.size())) return rc;
-      if (int rc = g->d_brec.reserve(pk.brec.size())) return rc;
-      if (int rc = g->d_btiles.reserve(pk.btiles.size())) return rc;
-      CK(cudaMemcpyAsync(g->d_bcoef.p, pk.bcoef.data(), pk.bcoef.size() * 8, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(g->d_brec.p, pk.brec.data(), pk.brec.size() * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(g->d_btiles.p, pk.btiles.data(), pk.btiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, st));
-      dg.bcoef = g->d_bcoef.p;
-      dg.brec = g->d_brec.p;
-      dg.btiles = g->d_btiles.p;
+      if (int rc = R.d_bcoef.reserve(pk.bcoef.size())) return rc;
+      if (int rc = R.d_brec.reserve(pk.brec.size())) return rc;
+      if (int rc = R.d_btiles.reserve(pk.btiles.size())) return rc;
+      CK(cudaMemcpyAsync(R.d_bcoef.p, pk.bcoef.data(), pk.bcoef.size() * 8, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_brec.p, pk.brec.data(), pk.brec.size() * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_btiles.p, pk.btiles.data(), pk.btiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, st));
+      dg.bcoef = R.d_bcoef.p;
+      dg.brec = R.d_brec.p;
+      dg.btiles = R.d_btiles.p;
       dg.n_brec = (uint32_t)pk.brec.size();
       dg.n_btiles = (uint32_t)pk.btiles.size();
       dg.blk_slots = pk.blk_slots;
@@ -264,8 +313,12 @@ int install_pack(asg_grid *g, PackResult &pk) {
   g->finite = true;
   for (double c : g->coefs)
     if (!std::isfinite(c)) { g->finite = false; break; }
-  rc = device_upload(g, pk);
-  if (rc != ASG_OK) return rc;
+  // every device of the context gets the same packed layouts (packed once on the host)
+  for (int r = ctx.ndev - 1; r >= 0; --r) {
+    rc = device_upload(g, r, pk);
+    if (rc != ASG_OK) return rc;
+  }
+  USE_REPLICA(g, 0);
   g->slot_of_node.swap(pk.slot_of_node);
   g->bslot_of_node.swap(pk.bslot_of_node);
   g->blk_ok = pk.canonical && pk.blk_ok;
@@ -284,9 +337,9 @@ int install_pack(asg_grid *g, PackResult &pk) {
   I.trie_nodes = pk.trie_nodes;
   I.coef_slots = (int64_t)pk.coef.size() - pk.coef_pad;
   I.hash_slots = (int64_t)pk.hent.size();
-  I.device_bytes = (int64_t)(g->d_rec.bytes() + g->d_grp.bytes() + g->d_tiles.bytes() + g->d_coef.bytes() + g->d_orig.bytes() + g->d_hent.bytes() +
-                             g->d_horig.bytes() + g->d_sw.bytes() + g->d_sw_low.bytes() + g->d_sw_coef.bytes() +
-                             g->d_sw_depth.bytes());
+  I.device_bytes = (int64_t)(R.d_rec.bytes() + R.d_grp.bytes() + R.d_tiles.bytes() + R.d_coef.bytes() + R.d_orig.bytes() + R.d_hent.bytes() +
+                             R.d_horig.bytes() + R.d_sw.bytes() + R.d_sw_low.bytes() + R.d_sw_coef.bytes() +
+                             R.d_sw_depth.bytes());
   I.generation = gen;
   I.regular = pk.regular ? 1 : 0;
   I.block = g->blk_ok ? 1 : 0;
@@ -294,7 +347,7 @@ int install_pack(asg_grid *g, PackResult &pk) {
   I.block_records = g->blk_ok ? (int64_t)pk.brec.size() : 0;
   I.block_tiles = g->blk_ok ? (int64_t)pk.btiles.size() : 0;
   I.block_stack = g->blk_ok ? pk.blk_slots : 0;
-  if (g->blk_ok) I.device_bytes += (int64_t)(g->d_bcoef.bytes() + g->d_brec.bytes() + g->d_btiles.bytes());
+  if (g->blk_ok) I.device_bytes += (int64_t)(R.d_bcoef.bytes() + R.d_brec.bytes() + R.d_btiles.bytes());
   return ASG_OK;
 }
 
@@ -333,37 +386,47 @@ int64_t sort_threshold() {
   return thr;
 }
 
-int run_eval(asg_grid *g, const EvalArgs &a_in, cudaStream_t st, int slot = 0, bool timed = false) {
+int run_eval(asg_grid *g, int r, const EvalArgs &a_in, cudaStream_t st, int slot = 0, bool timed = false) {
+  USE_REPLICA(g, r);
   int64_t l = 0;
-  if (timed) ctx.walk_timed = false;
+  if (timed) dc.walk_timed = false;
   cudaError_t e;
   EvalArgs a = a_in;
-  if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(g->dg, a, st, &l);
+  if (g->path() != ASG_PATH_SUBSPACE) e = launch_eval_sweep(R.dg, a, st, &l);
   else if (g->walk() == 3) {
     bool sorted = false;
     // (grids of a few hundred subspaces walk in less time than the ordering's five launches take)
-    if (a.M >= sort_threshold() && a.M < ((int64_t)1 << 31) && g->info.subspaces >= 512) {
-      const size_t tb = sort_points_temp_bytes(a.M);
-      if (int rc = g->s_key[slot].reserve((size_t)a.M)) return rc;
-      if (int rc = g->s_key2[slot].reserve((size_t)a.M)) return rc;
-      if (int rc = g->s_idx[slot].reserve((size_t)a.M)) return rc;
-      if (int rc = g->s_perm[slot].reserve((size_t)a.M)) return rc;
-      if (int rc = g->s_sorttmp[slot].reserve(tb)) return rc;
-      if (!g->sort_ev[slot]) CK(cudaEventCreateWithFlags(&g->sort_ev[slot], cudaEventDisableTiming));
-      else CK(cudaStreamWaitEvent(st, g->sort_ev[slot], 0));  // an earlier launch on another stream may still read the scratch
-      CK(sort_points(g->dg, a.X, a.M, a.sp, a.sd, g->s_key[slot].p, g->s_key2[slot].p, g->s_idx[slot].p, g->s_perm[slot].p,
-                     g->s_sorttmp[slot].p, tb, st, &l));
-      a.perm = g->s_perm[slot].p;
-      sorted = true;
+    if (a.M >= sort_threshold() && g->info.subspaces >= 512) {
+      if (a.M >= ((int64_t)1 << 31)) {
+        // the permutation is 32-bit: callers with device-resident batches this large should split them (the host
+        // pipeline always does). Say so once instead of silently walking ~1.6x slower.
+        static std::atomic<bool> warned{false};
+        if (!warned.exchange(true))
+          fprintf(stderr, "libasg_cuda: batch of %lld points >= 2^31: cell-key ordering skipped (walk ~1.6x slower); "
+                          "split the batch\n", (long long)a.M);
+      } else {
+        const size_t tb = sort_points_temp_bytes(a.M);
+        if (int rc = R.s_key[slot].reserve((size_t)a.M)) return rc;
+        if (int rc = R.s_key2[slot].reserve((size_t)a.M)) return rc;
+        if (int rc = R.s_idx[slot].reserve((size_t)a.M)) return rc;
+        if (int rc = R.s_perm[slot].reserve((size_t)a.M)) return rc;
+        if (int rc = R.s_sorttmp[slot].reserve(tb)) return rc;
+        if (!R.sort_ev[slot]) CK(cudaEventCreateWithFlags(&R.sort_ev[slot], cudaEventDisableTiming));
+        else CK(cudaStreamWaitEvent(st, R.sort_ev[slot], 0));  // an earlier launch on another stream may still read the scratch
+        CK(sort_points(R.dg, a.X, a.M, a.sp, a.sd, R.s_key[slot].p, R.s_key2[slot].p, R.s_idx[slot].p, R.s_perm[slot].p,
+                       R.s_sorttmp[slot].p, tb, st, &l));
+        a.perm = R.s_perm[slot].p;
+        sorted = true;
+      }
     }
-    if (timed) CK(cudaEventRecord(ctx.evw0, st));
-    e = launch_eval_block(g->dg, a, st, &l);
-    if (timed) { CK(cudaEventRecord(ctx.evw1, st)); ctx.walk_timed = true; }
-    if (sorted && e == cudaSuccess) CK(cudaEventRecord(g->sort_ev[slot], st));
+    if (timed) CK(cudaEventRecord(dc.evw0, st));
+    e = launch_eval_block(R.dg, a, st, &l);
+    if (timed) { CK(cudaEventRecord(dc.evw1, st)); dc.walk_timed = true; }
+    if (sorted && e == cudaSuccess) CK(cudaEventRecord(R.sort_ev[slot], st));
   }
-  else if (g->walk() == 0) e = launch_eval_stream(g->dg, a, st, &l);
-  else if (g->walk() == 1) e = launch_eval_rsg(g->dg, g->rp, a, st, &l);
-  else e = launch_eval_subspace(g->dg, a, st, &l);
+  else if (g->walk() == 0) e = launch_eval_stream(R.dg, a, st, &l);
+  else if (g->walk() == 1) e = launch_eval_rsg(R.dg, g->rp, a, st, &l);
+  else e = launch_eval_subspace(R.dg, a, st, &l);
   bump(l);
   CK(e);
   return ASG_OK;
@@ -399,46 +462,107 @@ int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, in
   return ASG_OK;
 }
 
-// host-buffer evaluation pipeline: chunks alternate between two streams so that the H2D copy of
-// chunk k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k
-int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
-              int64_t max_depth, double *out) {
-  const int D = g->D;
-  // chunk sizes ramp up 1 Mi, 2 Mi, 4 Mi, 8 Mi, 8 Mi, ...: the first copy (the only one no kernel hides) is short,
-  // the later chunks are large enough for the cell-key ordering of the BLOCK walk to bite
-  const int64_t first = std::min<int64_t>(M, (int64_t)1 << 20);
-  const int64_t chunk = std::min<int64_t>(M, (int64_t)1 << 23);  // buffer size per pipeline slot
-  std::vector<double> repack_buf;
-  const int nslot = M > first ? 2 : 1;
-  for (int s = 0; s < nslot; ++s) {
-    if (int rc = g->s_X[s].reserve((size_t)chunk * D)) return rc;
-    if (int rc = g->s_out[s].reserve((size_t)chunk)) return rc;
-    if (fvals)
-      if (int rc = g->s_f[s].reserve((size_t)chunk)) return rc;
+// Chunk schedule of the host-buffer pipeline. Only the first H2D copy and the last walk + D2H copy are not hidden
+// behind other work, so the chunks ramp UP from a small first one (factor 3: a copy runs about three times faster
+// than the walk of the same points, so the next chunk is always there in time) and DOWN again at the end; in between
+// they are as large as the slot buffers allow, because the cell-key ordering of the BLOCK walk is sharper on large
+// batches. ASG_PIPE_FIRST / ASG_PIPE_CHUNK (points) override the two sizes.
+int64_t pipe_first() {
+  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_FIRST"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 18; }();
+  return v;
+}
+int64_t pipe_chunk() {
+  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_CHUNK"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 24; }();
+  return v;
+}
+void chunk_schedule(int64_t M, std::vector<int64_t> &sizes) {
+  sizes.clear();
+  const int64_t first = pipe_first(), big = std::max(pipe_chunk(), first);
+  if (M <= 2 * first) { if (M > 0) sizes.push_back(M); return; }
+  // ramp down: tail chunks first .. 3*first .. (reversed at the end), at most a quarter of the batch
+  std::vector<int64_t> tail;
+  int64_t tail_sum = 0;
+  for (int64_t c = first; c < big && tail.size() < 3 && tail_sum + c <= M / 4; c *= 3) { tail.push_back(c); tail_sum += c; }
+  int64_t left = M - tail_sum;
+  for (int64_t c = first; left > 0; c = std::min(3 * c, big)) {
+    const int64_t take = std::min(c, left);
+    sizes.push_back(take);
+    left -= take;
   }
-  int slot = 0;
-  int64_t next = first;
-  for (int64_t m0 = 0, cnt = 0; m0 < M; m0 += cnt, slot ^= (nslot - 1)) {
-    cnt = std::min(next, M - m0);
-    next = std::min(2 * next, chunk);
-    cudaStream_t st = ctx.pipe[slot];
+  for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
+}
+
+// host-buffer evaluation pipeline on replica r: chunks rotate over kPipeSlots streams so that the H2D copy of chunk
+// k+1 and the D2H copy of chunk k-1 overlap the point ordering and the walk of chunk k
+int eval_host_dev(asg_grid *g, int r, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
+                  int64_t max_depth, double *out) {
+  if (int rc = use_dev(r)) return rc;
+  USE_REPLICA(g, r);
+  const int D = g->D;
+  std::vector<int64_t> sizes;
+  chunk_schedule(M, sizes);
+  int64_t biggest = 0;
+  for (int64_t c : sizes) biggest = std::max(biggest, c);
+  std::vector<double> repack_buf;
+  const int nslot = (int)std::min<size_t>(sizes.size(), kPipeSlots);
+  for (int s = 0; s < nslot; ++s) {
+    if (int rc = R.s_X[s].reserve((size_t)biggest * D)) return rc;
+    if (int rc = R.s_out[s].reserve((size_t)biggest)) return rc;
+    if (fvals)
+      if (int rc = R.s_f[s].reserve((size_t)biggest)) return rc;
+  }
+  int64_t m0 = 0;
+  for (size_t k = 0; k < sizes.size(); ++k) {
+    const int slot = (int)(k % (size_t)nslot);
+    const int64_t cnt = sizes[k];
+    cudaStream_t st = dc.pipe[slot];
     EvalArgs a{};
-    if (int rc = stage_points(X, m0, cnt, D, sp, sdim, g->s_X[slot].p, a.sp, a.sd, st, repack_buf)) return rc;
-    a.X = g->s_X[slot].p;
+    if (int rc = stage_points(X, m0, cnt, D, sp, sdim, R.s_X[slot].p, a.sp, a.sd, st, repack_buf)) return rc;
+    a.X = R.s_X[slot].p;
     a.M = cnt;
     a.rem = rem_of(max_depth);
     a.fvals = nullptr;
     if (fvals) {
-      CK(cudaMemcpyAsync(g->s_f[slot].p, fvals + m0, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
-      a.fvals = g->s_f[slot].p;
+      CK(cudaMemcpyAsync(R.s_f[slot].p, fvals + m0, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
+      a.fvals = R.s_f[slot].p;
     }
-    a.out = g->s_out[slot].p;
-    if (int rc = run_eval(g, a, st, slot)) return rc;
-    CK(cudaMemcpyAsync(out + m0, g->s_out[slot].p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    a.out = R.s_out[slot].p;
+    if (int rc = run_eval(g, r, a, st, slot)) return rc;
+    CK(cudaMemcpyAsync(out + m0, R.s_out[slot].p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
+    m0 += cnt;
   }
-  CK(cudaStreamSynchronize(ctx.pipe[0]));
-  if (nslot > 1) CK(cudaStreamSynchronize(ctx.pipe[1]));
+  for (int s = 0; s < nslot; ++s) CK(cudaStreamSynchronize(dc.pipe[s]));
   return ASG_OK;
+}
+
+// minimum points per device before a host-buffer call is split over the devices of the context
+int64_t multi_dev_min() {
+  static const int64_t v = [] { const char *e = getenv("ASG_MULTI_MIN"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 16; }();
+  return v;
+}
+
+// Host-buffer evaluation over every device of the context (grid replicated, points split into
+// contiguous ranges, results written straight into the caller's buffer; no collective). One host thread per device
+// drives that device's pipeline. Small batches stay on the primary device.
+int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
+              int64_t max_depth, double *out) {
+  const int nd = (int)std::min<int64_t>(ctx.ndev, std::max<int64_t>(1, M / multi_dev_min()));
+  if (nd <= 1) return eval_host_dev(g, 0, X, M, sp, sdim, fvals, max_depth, out);
+  std::vector<int> rcs((size_t)nd, ASG_OK);
+  std::vector<std::string> errs((size_t)nd);
+  std::vector<std::thread> th;
+  const int64_t per = (M + nd - 1) / nd;
+  for (int r = 0; r < nd; ++r) {
+    const int64_t lo = std::min<int64_t>(M, (int64_t)r * per), hi = std::min<int64_t>(M, lo + per);
+    th.emplace_back([=, &rcs, &errs]() {
+      if (hi > lo) rcs[(size_t)r] = eval_host_dev(g, r, X + lo * sp, hi - lo, sp, sdim, fvals ? fvals + lo : nullptr, max_depth, out + lo);
+      if (rcs[(size_t)r] != ASG_OK) errs[(size_t)r] = t_err;  // thread-local message of the worker
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int r = 0; r < nd; ++r)
+    if (rcs[(size_t)r] != ASG_OK) return set_err(rcs[(size_t)r], "device " + std::to_string(ctx.dev[r].device) + ": " + errs[(size_t)r]);
+  return use_dev(0);
 }
 
 int check_eval_args(asg_grid *g, const void *X, int64_t M, const void *out) {
@@ -471,48 +595,85 @@ int32_t asg_device_count(int32_t *count) {
   return ASG_OK;
 }
 
-int32_t asg_init(int32_t device) {
-  std::lock_guard<std::mutex> lk(ctx.mu);
-  if (ctx.ready && ctx.device == device) return ASG_OK;
-  if (ctx.ready) return set_err(ASG_ESTATE, "already initialised on another device (one process per GPU)");
+static int init_locked(const int32_t *devices, int32_t ndev) {
+  if (!devices || ndev <= 0) return set_err(ASG_EINVAL, "empty device list");
+  if (ndev > kMaxDev) return set_err(ASG_EUNSUPPORTED, "more than 16 devices");
+  if (ctx.ready) {
+    bool same = ctx.ndev == ndev;
+    for (int r = 0; same && r < ndev; ++r) same = ctx.dev[r].device == devices[r];
+    if (same) return ASG_OK;
+    return set_err(ASG_ESTATE, "already initialised on another device list (asg_shutdown first)");
+  }
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n <= 0)
     return set_err(ASG_ENODEVICE, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
                                       " (libasg_cuda has no CPU fallback)");
-  if (device < 0 || device >= n) return set_err(ASG_ENODEVICE, "device index out of range");
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return set_err(ASG_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
-                                      ", this library is built for sm_100a only");
-  CK(cudaSetDevice(device));
-  CK(cudaStreamCreateWithFlags(&ctx.stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx.pipe[0], cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&ctx.pipe[1], cudaStreamNonBlocking));
-  CK(cudaEventCreate(&ctx.ev0));
-  CK(cudaEventCreate(&ctx.ev1));
-  CK(cudaEventCreate(&ctx.evw0));
-  CK(cudaEventCreate(&ctx.evw1));
-  ctx.device = device;
+  for (int r = 0; r < ndev; ++r) {
+    const int device = devices[r];
+    if (device < 0 || device >= n) return set_err(ASG_ENODEVICE, "device index out of range");
+    for (int q = 0; q < r; ++q)
+      if (devices[q] == device) return set_err(ASG_EINVAL, "device listed twice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      return set_err(ASG_ENODEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                        ", this library is built for sm_100a only");
+  }
+  for (int r = 0; r < ndev; ++r) {
+    DevCtx &dc = ctx.dev[r];
+    dc = DevCtx{};
+    dc.device = devices[r];
+    CK(cudaSetDevice(dc.device));
+    CK(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
+    for (int s = 0; s < kPipeSlots; ++s) CK(cudaStreamCreateWithFlags(&dc.pipe[s], cudaStreamNonBlocking));
+    CK(cudaEventCreate(&dc.ev0));
+    CK(cudaEventCreate(&dc.ev1));
+    CK(cudaEventCreate(&dc.evw0));
+    CK(cudaEventCreate(&dc.evw1));
+  }
+  CK(cudaSetDevice(ctx.dev[0].device));
+  ctx.ndev = ndev;
+  ctx.last_dev = 0;
   ctx.ready = true;
+  return ASG_OK;
+}
+
+int32_t asg_init(int32_t device) {
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  return init_locked(&device, 1);
+}
+
+int32_t asg_init_devices(const int32_t *devices, int32_t ndev) {
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  return init_locked(devices, ndev);
+}
+
+int32_t asg_context_devices(int32_t *devices, int32_t capacity, int32_t *ndev) {
+  if (!ndev) return set_err(ASG_EINVAL, "null pointer");
+  std::lock_guard<std::mutex> lk(ctx.mu);
+  *ndev = ctx.ready ? ctx.ndev : 0;
+  for (int r = 0; devices && r < *ndev && r < capacity; ++r) devices[r] = ctx.dev[r].device;
   return ASG_OK;
 }
 
 int32_t asg_shutdown(void) {
   std::lock_guard<std::mutex> lk(ctx.mu);
   if (!ctx.ready) return ASG_OK;
-  cudaSetDevice(ctx.device);
-  cudaDeviceSynchronize();
-  cudaStreamDestroy(ctx.stream);
-  cudaStreamDestroy(ctx.pipe[0]);
-  cudaStreamDestroy(ctx.pipe[1]);
-  cudaEventDestroy(ctx.ev0);
-  cudaEventDestroy(ctx.ev1);
-  cudaEventDestroy(ctx.evw0);
-  cudaEventDestroy(ctx.evw1);
+  for (int r = 0; r < ctx.ndev; ++r) {
+    DevCtx &dc = ctx.dev[r];
+    cudaSetDevice(dc.device);
+    cudaDeviceSynchronize();
+    cudaStreamDestroy(dc.stream);
+    for (int s = 0; s < kPipeSlots; ++s) cudaStreamDestroy(dc.pipe[s]);
+    cudaEventDestroy(dc.ev0);
+    cudaEventDestroy(dc.ev1);
+    cudaEventDestroy(dc.evw0);
+    cudaEventDestroy(dc.evw1);
+    dc = DevCtx{};
+  }
   ctx.ready = false;
-  ctx.device = -1;
+  ctx.ndev = 0;
   return ASG_OK;
 }
 
@@ -525,7 +686,7 @@ int32_t asg_launch_count(int64_t *count) {
 int32_t asg_host_register(void *ptr, size_t bytes) {
   if (int rc = require_ctx()) return rc;
   if (!ptr || !bytes) return set_err(ASG_EINVAL, "null buffer");
-  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
   return ASG_OK;
 }
 int32_t asg_host_unregister(void *ptr) {
@@ -559,17 +720,11 @@ int32_t asg_grid_destroy(asg_grid *g) {
   {
     std::lock_guard<std::recursive_mutex> lk(g->mu);
     if (ctx.ready) {
-      cudaSetDevice(ctx.device);
-      g->d_rec.release(); g->d_grp.release(); g->d_tiles.release(); g->d_bcoef.release(); g->d_brec.release(); g->d_btiles.release(); g->d_coef.release(); g->d_sw_coef.release(); g->d_orig.release(); g->d_horig.release();
-      g->d_sw_depth.release(); g->d_hent.release(); g->d_sw.release(); g->d_sw_low.release();
-      for (int s = 0; s < 2; ++s) { g->s_X[s].release(); g->s_out[s].release(); g->s_f[s].release(); }
-      for (int s = 0; s < 2; ++s) {
-        g->s_key[s].release(); g->s_key2[s].release(); g->s_idx[s].release(); g->s_perm[s].release(); g->s_sorttmp[s].release();
-        if (g->sort_ev[s]) cudaEventDestroy(g->sort_ev[s]);
+      for (int r = 0; r < ctx.ndev; ++r) {
+        cudaSetDevice(ctx.dev[r].device);
+        g->rep[r].release_all();
       }
-      g->c_PL.release(); g->c_PI.release(); g->c_CL.release(); g->c_CI.release(); g->c_OL.release(); g->c_OI.release();
-      g->c_valid.release(); g->c_table.release(); g->c_flags.release(); g->c_sums.release();
-      g->s_i64a.release(); g->s_i64b.release(); g->s_tmp.release(); g->s_tmp2.release(); g->s_flag.release();
+      cudaSetDevice(ctx.dev[0].device);
     }
   }
   delete g;
@@ -578,6 +733,7 @@ int32_t asg_grid_destroy(asg_grid *g) {
 
 int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int64_t *indices, int64_t sn,
                         int64_t sd, const double *coefs) {
+  ASG_TRACE();
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   if (N < 0 || (N > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "bad node arrays");
   if (int rc = require_ctx()) return rc;
@@ -590,6 +746,7 @@ int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int
 
 int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                         int64_t sd, const double *coefs) {
+  ASG_TRACE();
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   if (n < 0 || (n > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "bad node arrays");
   if (int rc = require_ctx()) return rc;
@@ -611,10 +768,9 @@ int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int
 
 static int scatter_coefs_locked(asg_grid *g, int64_t n, const int64_t *idx, int64_t first, const double *coefs,
                                 const double *dcoefs_or_null) {
-  // idx == nullptr: nodes first .. first+n-1
+  // idx == nullptr: nodes first .. first+n-1. dcoefs_or_null: the same values already on the PRIMARY device.
   if (n == 0) return ASG_OK;
-  cudaStream_t st = ctx.stream;
-  std::vector<long long> slots((size_t)n), nodes((size_t)n);
+  std::vector<long long> slots((size_t)n), bslots, nodes((size_t)n);
   bool any_hash = false, any_dense = false;
   for (int64_t k = 0; k < n; ++k) {
     const int64_t node = idx ? idx[k] : first + k;
@@ -629,35 +785,48 @@ static int scatter_coefs_locked(asg_grid *g, int64_t n, const int64_t *idx, int6
       (slots[(size_t)k] < 0 ? any_hash : any_dense) = true;
     }
   }
-  if (int rc = g->s_i64a.reserve((size_t)n)) return rc;
-  const double *dsrc = dcoefs_or_null;
-  if (!dsrc) {
-    if (int rc = g->s_tmp2.reserve((size_t)n)) return rc;
-    CK(cudaMemcpyAsync(g->s_tmp2.p, coefs, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    dsrc = g->s_tmp2.p;
+  if (g->canonical && g->blk_ok) {  // the BLOCK layout holds its own copy of the coefficients
+    bslots.resize((size_t)n);
+    for (int64_t k = 0; k < n; ++k) bslots[(size_t)k] = g->bslot_of_node[(size_t)nodes[(size_t)k]];
   }
   int64_t l = 0;
-  CK(cudaMemcpyAsync(g->s_i64a.p, nodes.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  CK(launch_scatter_f64(g->d_sw_coef.p, g->s_i64a.p, dsrc, n, st, &l));
-  if (g->canonical) {
-    if (int rc = g->s_i64b.reserve((size_t)n)) return rc;
-    CK(cudaMemcpyAsync(g->s_i64b.p, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (any_dense) CK(launch_scatter_f64(g->d_coef.p, g->s_i64b.p, dsrc, n, st, &l));
-    if (any_hash) CK(launch_scatter_hash(g->d_hent.p, g->s_i64b.p, dsrc, n, st, &l));
-    if (g->blk_ok) {  // the BLOCK layout holds its own copy of the coefficients
-      for (int64_t k = 0; k < n; ++k) slots[(size_t)k] = g->bslot_of_node[(size_t)nodes[(size_t)k]];
-      CK(cudaStreamSynchronize(st));  // s_i64b is about to be overwritten
-      CK(cudaMemcpyAsync(g->s_i64b.p, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
-      CK(launch_scatter_f64(g->d_bcoef.p, g->s_i64b.p, dsrc, n, st, &l));
+  for (int r = 0; r < ctx.ndev; ++r) {
+    if (int rc = use_dev(r)) return rc;
+    USE_REPLICA(g, r);
+    cudaStream_t st = dc.stream;
+    if (int rc = R.s_i64a.reserve((size_t)n)) return rc;
+    const double *dsrc = r == 0 ? dcoefs_or_null : nullptr;
+    if (!dsrc) {
+      if (!coefs) return set_err(ASG_EINVAL, "coefficient values are needed on the host to reach every device");
+      if (int rc = R.s_tmp2.reserve((size_t)n)) return rc;
+      CK(cudaMemcpyAsync(R.s_tmp2.p, coefs, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+      dsrc = R.s_tmp2.p;
+    }
+    CK(cudaMemcpyAsync(R.s_i64a.p, nodes.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(launch_scatter_f64(R.d_sw_coef.p, R.s_i64a.p, dsrc, n, st, &l));
+    if (g->canonical) {
+      if (int rc = R.s_i64b.reserve((size_t)n)) return rc;
+      CK(cudaMemcpyAsync(R.s_i64b.p, slots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+      if (any_dense) CK(launch_scatter_f64(R.d_coef.p, R.s_i64b.p, dsrc, n, st, &l));
+      if (any_hash) CK(launch_scatter_hash(R.d_hent.p, R.s_i64b.p, dsrc, n, st, &l));
+      if (g->blk_ok) {
+        CK(cudaMemcpyAsync(R.s_i64a.p, bslots.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));  // stream order: after the sweep scatter
+        CK(launch_scatter_f64(R.d_bcoef.p, R.s_i64a.p, dsrc, n, st, &l));
+      }
     }
   }
   bump(l);
-  CK(cudaStreamSynchronize(st));
+  for (int r = 0; r < ctx.ndev; ++r) {
+    if (int rc = use_dev(r)) return rc;
+    CK(cudaStreamSynchronize(ctx.dev[r].stream));
+  }
+  if (int rc = use_dev(0)) return rc;
   g->info.generation++;
   return ASG_OK;
 }
 
 int32_t asg_grid_set_coefs(asg_grid *g, int64_t first, int64_t n, const double *coefs) {
+  ASG_TRACE();
   if (!g || (n > 0 && !coefs)) return set_err(ASG_EINVAL, "null argument");
   if (n < 0 || first < 0) return set_err(ASG_EINVAL, "negative range");
   if (int rc = require_ctx()) return rc;
@@ -674,6 +843,7 @@ int32_t asg_grid_set_coefs(asg_grid *g, int64_t first, int64_t n, const double *
 }
 
 int32_t asg_grid_scatter_coefs(asg_grid *g, int64_t n, const int64_t *idx, const double *coefs) {
+  ASG_TRACE();
   if (!g || (n > 0 && (!coefs || !idx))) return set_err(ASG_EINVAL, "null argument");
   if (n < 0) return set_err(ASG_EINVAL, "negative count");
   if (int rc = require_ctx()) return rc;
@@ -686,10 +856,11 @@ int32_t asg_grid_get_coefs(asg_grid *g, int64_t first, int64_t n, double *coefs)
   if (!g || (n > 0 && !coefs)) return set_err(ASG_EINVAL, "null argument");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
   if (first < 0 || n < 0 || first + n > g->N) return set_err(ASG_EINVAL, "range exceeds node count");
   // read the DEVICE copy (caller's node order) so that this is a true read-back of what the kernels see
-  if (n) CK(cudaMemcpy(coefs, g->d_sw_coef.p + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (n) CK(cudaMemcpy(coefs, R.d_sw_coef.p + first, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return ASG_OK;
 }
 
@@ -706,16 +877,18 @@ int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info) {
 int32_t asg_grid_set_path(asg_grid *g, int32_t path) {
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (path < ASG_PATH_AUTO || path > ASG_PATH_BLOCK) return set_err(ASG_EINVAL, "bad path");
   if (path >= ASG_PATH_SUBSPACE && g->uploaded && g->N > 0 && !(g->canonical && g->finite))
     return set_err(ASG_EUNSUPPORTED, "grid is not canonical (" + g->why + "): only the sweep engine applies");
-  if (path == ASG_PATH_BLOCK && g->uploaded && g->N > 0 && !(g->blk_ok && block_kernel_fits(g->dg)))
+  if (path == ASG_PATH_BLOCK && g->uploaded && g->N > 0 && !(g->blk_ok && block_kernel_fits(R.dg)))
     return set_err(ASG_EUNSUPPORTED, "grid has no BLOCK layout (" + g->blk_why + ")");
   g->forced_path = path;
   return ASG_OK;
 }
 
 int32_t asg_eval(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth, double *out) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, out)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
@@ -724,6 +897,7 @@ int32_t asg_eval(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sd
 
 int32_t asg_surplus(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
                     int64_t max_depth, double *alpha) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, alpha)) return rc;
   if (M > 0 && !fvals) return set_err(ASG_EINVAL, "null fvals");
   if (int rc = require_ctx()) return rc;
@@ -731,56 +905,80 @@ int32_t asg_surplus(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t
   return eval_host(g, X, M, sp, sdim, fvals, max_depth, alpha);
 }
 
+// replica whose device owns a device pointer (device-pointer entry points work on any device of the context)
+static int replica_of_pointer(const void *p) {
+  if (ctx.ndev <= 1) return 0;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (at.type == cudaMemoryTypeDevice)
+    for (int r = 0; r < ctx.ndev; ++r)
+      if (ctx.dev[r].device == at.device) return r;
+  return at.type == cudaMemoryTypeDevice ? -1 : 0;
+}
+
+static int eval_device_common(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, const double *dfvals,
+                              int64_t max_depth, double *dout, void *stream) {
+  const int r = replica_of_pointer(dX);
+  if (r < 0) return set_err(ASG_EINVAL, "device pointer belongs to a device outside the context (asg_init_devices)");
+  if (int rc = use_dev(r)) return rc;
+  USE_REPLICA(g, r);
+  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
+  EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), dfvals, dout};
+  CK(cudaEventRecord(dc.ev0, st));
+  if (int rc = run_eval(g, r, a, st, 0, true)) return rc;
+  CK(cudaEventRecord(dc.ev1, st));
+  dc.last_timed = true;
+  ctx.last_dev = r;
+  return ASG_OK;
+}
+
 int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
                         double *dout, void *stream) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
-  EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), nullptr, dout};
-  CK(cudaEventRecord(ctx.ev0, st));
-  if (int rc = run_eval(g, a, st, 0, true)) return rc;
-  CK(cudaEventRecord(ctx.ev1, st));
-  ctx.last_timed = true;
-  return ASG_OK;
+  return eval_device_common(g, dX, M, sp, sdim, nullptr, max_depth, dout, stream);
 }
 
 int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, const double *dfvals,
                            int64_t max_depth, double *dalpha, void *stream) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, dX, M, dalpha)) return rc;
   if (M > 0 && !dfvals) return set_err(ASG_EINVAL, "null fvals");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
-  cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
-  EvalArgs a{dX, M, sp, sdim, rem_of(max_depth), dfvals, dalpha};
-  CK(cudaEventRecord(ctx.ev0, st));
-  if (int rc = run_eval(g, a, st, 0, true)) return rc;
-  CK(cudaEventRecord(ctx.ev1, st));
-  ctx.last_timed = true;
-  return ASG_OK;
+  return eval_device_common(g, dX, M, sp, sdim, dfvals, max_depth, dalpha, stream);
 }
 
 int32_t asg_last_kernel_ms(double *ms) {
   if (!ms) return set_err(ASG_EINVAL, "null pointer");
   if (int rc = require_ctx()) return rc;
-  if (!ctx.last_timed) return set_err(ASG_ESTATE, "no timed launch yet");
-  CK(cudaEventSynchronize(ctx.ev1));
+  DevCtx &dc = ctx.dev[ctx.last_dev];
+  if (!dc.last_timed) return set_err(ASG_ESTATE, "no timed launch yet");
+  if (int rc = use_dev(ctx.last_dev)) return rc;
+  CK(cudaEventSynchronize(dc.ev1));
   float f = 0.f;
-  CK(cudaEventElapsedTime(&f, ctx.ev0, ctx.ev1));
+  CK(cudaEventElapsedTime(&f, dc.ev0, dc.ev1));
   *ms = (double)f;
-  return ASG_OK;
+  return use_dev(0);
 }
 
 int32_t asg_last_walk_ms(double *ms) {
   if (!ms) return set_err(ASG_EINVAL, "null pointer");
   if (int rc = require_ctx()) return rc;
-  if (!ctx.last_timed) return set_err(ASG_ESTATE, "no timed launch yet");
-  cudaEvent_t a = ctx.walk_timed ? ctx.evw0 : ctx.ev0, b = ctx.walk_timed ? ctx.evw1 : ctx.ev1;
+  DevCtx &dc = ctx.dev[ctx.last_dev];
+  if (!dc.last_timed) return set_err(ASG_ESTATE, "no timed launch yet");
+  if (int rc = use_dev(ctx.last_dev)) return rc;
+  cudaEvent_t a = dc.walk_timed ? dc.evw0 : dc.ev0, b = dc.walk_timed ? dc.evw1 : dc.ev1;
   CK(cudaEventSynchronize(b));
   float f = 0.f;
   CK(cudaEventElapsedTime(&f, a, b));
   *ms = (double)f;
-  return ASG_OK;
+  return use_dev(0);
 }
 
 int32_t asg_eval_async(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, int64_t max_depth,
@@ -808,28 +1006,29 @@ int32_t asg_wait(asg_event *ev) {
   return rc;
 }
 
-static int nodes_x_device(asg_grid *g, int64_t n, const long long *h_lev, const long long *h_idx, double *dX,
+static int nodes_x_device(asg_grid *g, int r, int64_t n, const long long *h_lev, const long long *h_idx, double *dX,
                           int64_t sp, int64_t sd, cudaStream_t st) {
+  USE_REPLICA(g, r);
   const int D = g->D;
-  if (int rc = g->s_i64a.reserve((size_t)n * D)) return rc;
-  if (int rc = g->s_i64b.reserve((size_t)n * D)) return rc;
-  if (int rc = g->s_flag.reserve(1)) return rc;
-  CK(cudaMemsetAsync(g->s_flag.p, 0, sizeof(int), st));
-  CK(cudaMemcpyAsync(g->s_i64a.p, h_lev, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(g->s_i64b.p, h_idx, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+  if (int rc = R.s_i64a.reserve((size_t)n * D)) return rc;
+  if (int rc = R.s_i64b.reserve((size_t)n * D)) return rc;
+  if (int rc = R.s_flag.reserve(1)) return rc;
+  CK(cudaMemsetAsync(R.s_flag.p, 0, sizeof(int), st));
+  CK(cudaMemcpyAsync(R.s_i64a.p, h_lev, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(R.s_i64b.p, h_idx, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
   int64_t l = 0;
   // the kernel only reads lb / width of the DeviceGrid, valid even before any upload
-  DeviceGrid dg = g->dg;
+  DeviceGrid dg = R.dg;
   dg.D = D;
   for (int d = 0; d < D; ++d) {
     dg.lb[d] = g->lb[d];
     volatile double w = g->ub[d] - g->lb[d];
     dg.width[d] = w;
   }
-  CK(launch_nodes_x(D, nullptr, dg, g->s_i64a.p, g->s_i64b.p, n, dX, sp, sd, g->s_flag.p, st, &l));
+  CK(launch_nodes_x(D, nullptr, dg, R.s_i64a.p, R.s_i64b.p, n, dX, sp, sd, R.s_flag.p, st, &l));
   bump(l);
   int bad = 0;
-  CK(cudaMemcpyAsync(&bad, g->s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&bad, R.s_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (bad) return set_err(ASG_EINVALID_NODE, "invalid level-index pair (get_x, src/math.jl:474)");
   return ASG_OK;
@@ -851,25 +1050,29 @@ static int copy_out_matrix(const double *dX, int64_t n, int D, double *Xout, int
 }
 
 int32_t asg_nodes_x(asg_grid *g, int64_t first, int64_t n, double *Xout, int64_t sp, int64_t sdim) {
+  ASG_TRACE();
   if (!g || (n > 0 && !Xout)) return set_err(ASG_EINVAL, "null argument");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (first < 0 || n < 0 || first + n > g->N) return set_err(ASG_EINVAL, "range exceeds node count");
   if (n == 0) return ASG_OK;
   const int D = g->D;
-  if (int rc = g->s_tmp.reserve((size_t)n * D)) return rc;
-  if (int rc = nodes_x_device(g, n, (const long long *)g->levels.data() + first * D,
-                              (const long long *)g->indices.data() + first * D, g->s_tmp.p, D, 1, ctx.stream))
+  if (int rc = R.s_tmp.reserve((size_t)n * D)) return rc;
+  if (int rc = nodes_x_device(g, 0, n, (const long long *)g->levels.data() + first * D,
+                              (const long long *)g->indices.data() + first * D, R.s_tmp.p, D, 1, dc.stream))
     return rc;
-  return copy_out_matrix(g->s_tmp.p, n, D, Xout, sp, sdim, ctx.stream);
+  return copy_out_matrix(R.s_tmp.p, n, D, Xout, sp, sdim, dc.stream);
 }
 
 int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn, int64_t sd,
                        double *Xout, int64_t sp, int64_t sdim) {
+  ASG_TRACE();
   if (!g || (n > 0 && (!Xout || !levels || !indices))) return set_err(ASG_EINVAL, "null argument");
   if (n < 0) return set_err(ASG_EINVAL, "negative count");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (n == 0) return ASG_OK;
   const int D = g->D;
   std::vector<long long> L((size_t)n * D), I((size_t)n * D);
@@ -878,13 +1081,33 @@ int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int6
       L[(size_t)k * D + d] = levels[k * sn + d * sd];
       I[(size_t)k * D + d] = indices[k * sn + d * sd];
     }
-  if (int rc = g->s_tmp.reserve((size_t)n * D)) return rc;
-  if (int rc = nodes_x_device(g, n, L.data(), I.data(), g->s_tmp.p, D, 1, ctx.stream)) return rc;
-  return copy_out_matrix(g->s_tmp.p, n, D, Xout, sp, sdim, ctx.stream);
+  if (int rc = R.s_tmp.reserve((size_t)n * D)) return rc;
+  if (int rc = nodes_x_device(g, 0, n, L.data(), I.data(), R.s_tmp.p, D, 1, dc.stream)) return rc;
+  return copy_out_matrix(R.s_tmp.p, n, D, Xout, sp, sdim, dc.stream);
+}
+
+// surplus at n of the grid's own nodes on replica r: get_x on the device, fused alpha = f - G epilogue, D2H
+static int surplus_nodes_dev(asg_grid *g, int r, int64_t n, const long long *L, const long long *I, const double *fvals,
+                             int64_t max_depth, double *alpha) {
+  if (int rc = use_dev(r)) return rc;
+  USE_REPLICA(g, r);
+  const int D = g->D;
+  cudaStream_t st = dc.stream;
+  if (int rc = R.s_tmp.reserve((size_t)n * D)) return rc;
+  if (int rc = nodes_x_device(g, r, n, L, I, R.s_tmp.p, D, 1, st)) return rc;  // get_x on device
+  if (int rc = R.s_f[0].reserve((size_t)n)) return rc;
+  if (int rc = R.s_out[0].reserve((size_t)n)) return rc;
+  CK(cudaMemcpyAsync(R.s_f[0].p, fvals, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  EvalArgs a{R.s_tmp.p, n, D, 1, rem_of(max_depth), R.s_f[0].p, R.s_out[0].p};
+  if (int rc = run_eval(g, r, a, st)) return rc;
+  CK(cudaMemcpyAsync(alpha, R.s_out[0].p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return ASG_OK;
 }
 
 int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const double *fvals, int64_t max_depth,
                           int32_t store, double *alpha) {
+  ASG_TRACE();
   if (!g || (n > 0 && (!idx || !fvals || !alpha))) return set_err(ASG_EINVAL, "null argument");
   if (n < 0) return set_err(ASG_EINVAL, "negative count");
   if (int rc = require_ctx()) return rc;
@@ -898,28 +1121,81 @@ int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const doub
     std::memcpy(&L[(size_t)k * D], &g->levels[(size_t)idx[k] * D], (size_t)D * 8);
     std::memcpy(&I[(size_t)k * D], &g->indices[(size_t)idx[k] * D], (size_t)D * 8);
   }
-  cudaStream_t st = ctx.stream;
-  if (int rc = g->s_tmp.reserve((size_t)n * D)) return rc;
-  if (int rc = nodes_x_device(g, n, L.data(), I.data(), g->s_tmp.p, D, 1, st)) return rc;  // get_x on device
-  if (int rc = g->s_f[0].reserve((size_t)n)) return rc;
-  if (int rc = g->s_out[0].reserve((size_t)n)) return rc;
-  CK(cudaMemcpyAsync(g->s_f[0].p, fvals, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-  EvalArgs a{g->s_tmp.p, n, D, 1, rem_of(max_depth), g->s_f[0].p, g->s_out[0].p};
-  if (int rc = run_eval(g, a, st)) return rc;
-  CK(cudaMemcpyAsync(alpha, g->s_out[0].p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  // the nodes of one depth are independent query points: split them over the devices like asg_eval does
+  const int nd = (int)std::min<int64_t>(ctx.ndev, std::max<int64_t>(1, n / multi_dev_min()));
+  if (nd <= 1) {
+    if (int rc = surplus_nodes_dev(g, 0, n, L.data(), I.data(), fvals, max_depth, alpha)) return rc;
+  } else {
+    std::vector<int> rcs((size_t)nd, ASG_OK);
+    std::vector<std::string> errs((size_t)nd);
+    std::vector<std::thread> th;
+    const int64_t per = (n + nd - 1) / nd;
+    for (int r = 0; r < nd; ++r) {
+      const int64_t lo = std::min<int64_t>(n, (int64_t)r * per), hi = std::min<int64_t>(n, lo + per);
+      th.emplace_back([=, &rcs, &errs, &L, &I]() {
+        if (hi > lo)
+          rcs[(size_t)r] = surplus_nodes_dev(g, r, hi - lo, L.data() + lo * D, I.data() + lo * D, fvals + lo, max_depth, alpha + lo);
+        if (rcs[(size_t)r] != ASG_OK) errs[(size_t)r] = t_err;
+      });
+    }
+    for (auto &t : th) t.join();
+    if (int rc = use_dev(0)) return rc;
+    for (int r = 0; r < nd; ++r)
+      if (rcs[(size_t)r] != ASG_OK) return set_err(rcs[(size_t)r], "device " + std::to_string(ctx.dev[r].device) + ": " + errs[(size_t)r]);
+  }
   if (store) {
-    // alpha is now on the host too: keep the host mirror, the finite flag and the device slots in step
-    return scatter_coefs_locked(g, n, idx, 0, alpha, g->s_out[0].p);
+    // alpha is on the host: keep the host mirror, the finite flag and the slots of every replica in step
+    return scatter_coefs_locked(g, n, idx, 0, alpha, (nd <= 1) ? g->rep[0].s_out[0].p : nullptr);
   }
   return ASG_OK;
 }
 
+// ---- phi: the exported basis function itself (src/math.jl:332-391) -------------------------------------------
+int32_t asg_phi(int64_t n, int32_t D, const double *x01, const int64_t *levels, const int64_t *indices, double *out) {
+  ASG_TRACE();
+  if (n < 0 || D <= 0 || D > kMaxDim) return set_err(ASG_EINVAL, "bad size");
+  if (n > 0 && (!x01 || !out)) return set_err(ASG_EINVAL, "null buffer");
+  if ((levels == nullptr) != (indices == nullptr)) return set_err(ASG_EINVAL, "levels and indices go together");
+  if (int rc = require_ctx()) return rc;
+  if (n == 0) return ASG_OK;
+  DevCtx &dc = ctx.dev[0];
+  cudaStream_t st = dc.stream;
+  const size_t e = (size_t)n * D;
+  double *dx = nullptr, *dout = nullptr;
+  long long *dl = nullptr, *di = nullptr;
+  int *dbad = nullptr;
+  int bad = 0, rc = ASG_OK;
+  cudaError_t ce = cudaSuccess;
+  auto ok = [&](cudaError_t c) { if (ce == cudaSuccess) ce = c; return ce == cudaSuccess; };
+  if (ok(cudaMalloc(&dx, e * 8)) && ok(cudaMalloc(&dout, (size_t)n * 8)) && ok(cudaMalloc(&dbad, sizeof(int))) &&
+      (!levels || (ok(cudaMalloc(&dl, e * 8)) && ok(cudaMalloc(&di, e * 8))))) {
+    ok(cudaMemcpyAsync(dx, x01, e * 8, cudaMemcpyHostToDevice, st));
+    if (levels) {
+      ok(cudaMemcpyAsync(dl, levels, e * 8, cudaMemcpyHostToDevice, st));
+      ok(cudaMemcpyAsync(di, indices, e * 8, cudaMemcpyHostToDevice, st));
+    }
+    ok(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+    int64_t l = 0;
+    ok(launch_phi(D, n, dx, dl, di, dout, dbad, st, &l));
+    bump(l);
+    ok(cudaMemcpyAsync(out, dout, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    ok(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ok(cudaStreamSynchronize(st));
+  }
+  cudaFree(dx); cudaFree(dout); cudaFree(dl); cudaFree(di); cudaFree(dbad);
+  if (ce != cudaSuccess) rc = set_err(ce == cudaErrorMemoryAllocation ? ASG_ENOMEM : ASG_ECUDA, std::string("asg_phi: ") + cudaGetErrorString(ce));
+  else if (bad == 1) rc = set_err(ASG_EINVALID_NODE, "invalid level-index pair (phi, src/math.jl:355)");
+  else if (bad == 2) rc = set_err(ASG_EUNSUPPORTED, "level > 62: power2(l - 1) leaves the Int64 range");
+  return rc;
+}
+
 // ---- adapt! candidate generation ----------------------------------------------------------------
 int32_t asg_children(asg_grid *g, int64_t depth, int64_t *n_parents, int64_t *n_candidates, int64_t *n_unique) {
+  ASG_TRACE();
   if (!g || !n_unique) return set_err(ASG_EINVAL, "null argument");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
   const int D = g->D;
   std::vector<long long> PL, PI;
@@ -946,23 +1222,23 @@ int32_t asg_children(asg_grid *g, int64_t depth, int64_t *n_parents, int64_t *n_
   int64_t tsize = 1024;
   while (tsize < 2 * n_cand) tsize <<= 1;
   const int64_t nblk = (n_cand + 1023) / 1024;
-  if (int rc = g->c_PL.reserve((size_t)n_p * D)) return rc;
-  if (int rc = g->c_PI.reserve((size_t)n_p * D)) return rc;
-  if (int rc = g->c_CL.reserve((size_t)n_cand * D)) return rc;
-  if (int rc = g->c_CI.reserve((size_t)n_cand * D)) return rc;
-  if (int rc = g->c_OL.reserve((size_t)n_cand * D)) return rc;
-  if (int rc = g->c_OI.reserve((size_t)n_cand * D)) return rc;
-  if (int rc = g->c_valid.reserve((size_t)n_cand)) return rc;
-  if (int rc = g->c_table.reserve((size_t)tsize)) return rc;
-  if (int rc = g->c_flags.reserve((size_t)n_cand)) return rc;
-  if (int rc = g->c_sums.reserve((size_t)nblk + 1)) return rc;
-  cudaStream_t st = ctx.stream;
-  CK(cudaMemcpyAsync(g->c_PL.p, PL.data(), PL.size() * 8, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(g->c_PI.p, PI.data(), PI.size() * 8, cudaMemcpyHostToDevice, st));
+  if (int rc = R.c_PL.reserve((size_t)n_p * D)) return rc;
+  if (int rc = R.c_PI.reserve((size_t)n_p * D)) return rc;
+  if (int rc = R.c_CL.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = R.c_CI.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = R.c_OL.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = R.c_OI.reserve((size_t)n_cand * D)) return rc;
+  if (int rc = R.c_valid.reserve((size_t)n_cand)) return rc;
+  if (int rc = R.c_table.reserve((size_t)tsize)) return rc;
+  if (int rc = R.c_flags.reserve((size_t)n_cand)) return rc;
+  if (int rc = R.c_sums.reserve((size_t)nblk + 1)) return rc;
+  cudaStream_t st = dc.stream;
+  CK(cudaMemcpyAsync(R.c_PL.p, PL.data(), PL.size() * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(R.c_PI.p, PI.data(), PI.size() * 8, cudaMemcpyHostToDevice, st));
   int64_t l = 0;
-  unsigned int *total = g->c_sums.p + nblk;
-  CK(launch_children(D, n_p, g->c_PL.p, g->c_PI.p, g->c_CL.p, g->c_CI.p, g->c_valid.p, g->c_table.p, tsize, g->c_flags.p,
-                     g->c_sums.p, total, g->c_OL.p, g->c_OI.p, st, &l));
+  unsigned int *total = R.c_sums.p + nblk;
+  CK(launch_children(D, n_p, R.c_PL.p, R.c_PI.p, R.c_CL.p, R.c_CI.p, R.c_valid.p, R.c_table.p, tsize, R.c_flags.p,
+                     R.c_sums.p, total, R.c_OL.p, R.c_OI.p, st, &l));
   bump(l);
   unsigned int nu = 0;
   CK(cudaMemcpyAsync(&nu, total, sizeof nu, cudaMemcpyDeviceToHost, st));
@@ -974,23 +1250,25 @@ int32_t asg_children(asg_grid *g, int64_t depth, int64_t *n_parents, int64_t *n_
 
 int32_t asg_children_fetch(asg_grid *g, int64_t n, int64_t *levels, int64_t *indices, int64_t sn, int64_t sd, double *X,
                            int64_t sp, int64_t sdim) {
+  ASG_TRACE();
   if (!g || (n > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "null argument");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (g->ch_n < 0 || g->ch_generation != g->info.generation)
     return set_err(ASG_ESTATE, "asg_children has not been called on this state of the grid");
   if (n != g->ch_n) return set_err(ASG_EINVAL, "n differs from the count asg_children returned");
   if (n == 0) return ASG_OK;
   const int D = g->D;
-  cudaStream_t st = ctx.stream;
+  cudaStream_t st = dc.stream;
   std::vector<long long> L((size_t)n * D), I((size_t)n * D);
-  CK(cudaMemcpyAsync(L.data(), g->c_OL.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(I.data(), g->c_OI.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(L.data(), R.c_OL.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(I.data(), R.c_OI.p, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
   if (X) {  // coordinates of the children: the bit-exact get_x of the evaluation path (mul + add, never fused)
-    if (int rc = g->s_tmp.reserve((size_t)n * D)) return rc;
-    if (int rc = g->s_flag.reserve(1)) return rc;
-    CK(cudaMemsetAsync(g->s_flag.p, 0, sizeof(int), st));
-    DeviceGrid dg = g->dg;
+    if (int rc = R.s_tmp.reserve((size_t)n * D)) return rc;
+    if (int rc = R.s_flag.reserve(1)) return rc;
+    CK(cudaMemsetAsync(R.s_flag.p, 0, sizeof(int), st));
+    DeviceGrid dg = R.dg;
     dg.D = D;
     for (int d = 0; d < D; ++d) {
       dg.lb[d] = g->lb[d];
@@ -998,9 +1276,9 @@ int32_t asg_children_fetch(asg_grid *g, int64_t n, int64_t *levels, int64_t *ind
       dg.width[d] = w;
     }
     int64_t l = 0;
-    CK(launch_nodes_x(D, nullptr, dg, g->c_OL.p, g->c_OI.p, n, g->s_tmp.p, D, 1, g->s_flag.p, st, &l));
+    CK(launch_nodes_x(D, nullptr, dg, R.c_OL.p, R.c_OI.p, n, R.s_tmp.p, D, 1, R.s_flag.p, st, &l));
     bump(l);
-    if (int rc = copy_out_matrix(g->s_tmp.p, n, D, X, sp, sdim, st)) return rc;
+    if (int rc = copy_out_matrix(R.s_tmp.p, n, D, X, sp, sdim, st)) return rc;
   }
   CK(cudaStreamSynchronize(st));
   for (int64_t k = 0; k < n; ++k)
@@ -1014,65 +1292,71 @@ int32_t asg_children_fetch(asg_grid *g, int64_t n, int64_t *levels, int64_t *ind
 // ---- basis ------------------------------------------------------------------------------------
 static int upload_points(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, int64_t &dsp, int64_t &dsd,
                          cudaStream_t st) {
+  USE_REPLICA(g, 0);
   std::vector<double> rb;
-  if (int rc = g->s_X[0].reserve((size_t)M * g->D)) return rc;
-  if (int rc = stage_points(X, 0, M, g->D, sp, sdim, g->s_X[0].p, dsp, dsd, st, rb)) return rc;
+  if (int rc = R.s_X[0].reserve((size_t)M * g->D)) return rc;
+  if (int rc = stage_points(X, 0, M, g->D, sp, sdim, R.s_X[0].p, dsp, dsd, st, rb)) return rc;
   CK(cudaStreamSynchronize(st));
   return ASG_OK;
 }
 
 static cudaError_t run_basis(asg_grid *g, const BasisArgs &a, cudaStream_t st) {
+  USE_REPLICA(g, 0);
   int64_t l = 0;
-  cudaError_t e = (g->path() == ASG_PATH_SUBSPACE) ? launch_basis_subspace(g->dg, a, st, &l)
-                                                   : launch_basis_sweep(g->dg, a, st, &l);
+  cudaError_t e = (g->path() == ASG_PATH_SUBSPACE) ? launch_basis_subspace(R.dg, a, st, &l)
+                                                   : launch_basis_sweep(R.dg, a, st, &l);
   bump(l);
   return e;
 }
 
 int32_t asg_basis_count(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                         int32_t dropzeros, int64_t *row_nnz) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, row_nnz)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (M == 0) return ASG_OK;
-  cudaStream_t st = ctx.stream;
+  cudaStream_t st = dc.stream;
   BasisArgs a{};
   if (int rc = upload_points(g, X, M, sp, sdim, a.sp, a.sd, st)) return rc;
-  if (int rc = g->s_i64a.reserve((size_t)M)) return rc;
-  a.X = g->s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 0;
-  a.row_nnz = (unsigned long long *)g->s_i64a.p;
+  if (int rc = R.s_i64a.reserve((size_t)M)) return rc;
+  a.X = R.s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 0;
+  a.row_nnz = (unsigned long long *)R.s_i64a.p;
   CK(run_basis(g, a, st));
-  CK(cudaMemcpyAsync(row_nnz, g->s_i64a.p, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(row_nnz, R.s_i64a.p, (size_t)M * 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return ASG_OK;
 }
 
 int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                        int32_t dropzeros, const int64_t *row_ptr, int64_t *colidx, double *vals) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, row_ptr)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   if (M == 0) return ASG_OK;
   const int64_t nnz = row_ptr[M];
   if (nnz < 0 || (nnz > 0 && (!colidx || !vals))) return set_err(ASG_EINVAL, "bad CSR buffers");
-  cudaStream_t st = ctx.stream;
+  cudaStream_t st = dc.stream;
   BasisArgs a{};
   if (int rc = upload_points(g, X, M, sp, sdim, a.sp, a.sd, st)) return rc;
-  if (int rc = g->s_i64a.reserve((size_t)M + 1)) return rc;
-  if (int rc = g->s_i64b.reserve((size_t)nnz)) return rc;
-  if (int rc = g->s_tmp.reserve((size_t)nnz)) return rc;
-  CK(cudaMemcpyAsync(g->s_i64a.p, row_ptr, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, st));
-  a.X = g->s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 1;
-  a.row_ptr = g->s_i64a.p; a.colidx = g->s_i64b.p; a.vals = g->s_tmp.p;
+  if (int rc = R.s_i64a.reserve((size_t)M + 1)) return rc;
+  if (int rc = R.s_i64b.reserve((size_t)nnz)) return rc;
+  if (int rc = R.s_tmp.reserve((size_t)nnz)) return rc;
+  CK(cudaMemcpyAsync(R.s_i64a.p, row_ptr, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, st));
+  a.X = R.s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 1;
+  a.row_ptr = R.s_i64a.p; a.colidx = R.s_i64b.p; a.vals = R.s_tmp.p;
   CK(run_basis(g, a, st));
   if (g->path() == ASG_PATH_SUBSPACE) {  // trie order -> ascending node numbers inside each row
     int64_t l = 0;
-    CK(launch_sort_rows(g->s_i64a.p, g->s_i64b.p, g->s_tmp.p, M, st, &l));
+    CK(launch_sort_rows(R.s_i64a.p, R.s_i64b.p, R.s_tmp.p, M, st, &l));
     bump(l);
   }
   if (nnz) {
-    CK(cudaMemcpyAsync(colidx, g->s_i64b.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vals, g->s_tmp.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(colidx, R.s_i64b.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vals, R.s_tmp.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
   return ASG_OK;
@@ -1080,10 +1364,12 @@ int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int6
 
 int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                            int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, row_ptr)) return rc;
   if (!colptr) return set_err(ASG_EINVAL, "null colptr");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   const int64_t N = g->N;
   if (M == 0) {
     for (int64_t c = 0; c <= N; ++c) colptr[c] = 0;
@@ -1091,39 +1377,39 @@ int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, 
   }
   const int64_t nnz = row_ptr[M];
   if (nnz < 0 || nnz >= ((int64_t)1 << 31) || (nnz > 0 && (!rowidx || !vals))) return set_err(ASG_EINVAL, "bad CSC buffers");
-  cudaStream_t st = ctx.stream;
+  cudaStream_t st = dc.stream;
   BasisArgs a{};
   if (int rc = upload_points(g, X, M, sp, sdim, a.sp, a.sd, st)) return rc;
-  if (int rc = g->s_i64a.reserve((size_t)M + 1)) return rc;
-  if (int rc = g->s_i64b.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
-  if (int rc = g->s_tmp.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
-  CK(cudaMemcpyAsync(g->s_i64a.p, row_ptr, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, st));
-  a.X = g->s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 1;
-  a.row_ptr = g->s_i64a.p; a.colidx = g->s_i64b.p; a.vals = g->s_tmp.p;
+  if (int rc = R.s_i64a.reserve((size_t)M + 1)) return rc;
+  if (int rc = R.s_i64b.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
+  if (int rc = R.s_tmp.reserve((size_t)std::max<int64_t>(nnz, 1))) return rc;
+  CK(cudaMemcpyAsync(R.s_i64a.p, row_ptr, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, st));
+  a.X = R.s_X[0].p; a.M = M; a.atol = atol; a.dropzeros = dropzeros; a.mode = 1;
+  a.row_ptr = R.s_i64a.p; a.colidx = R.s_i64b.p; a.vals = R.s_tmp.p;
   CK(run_basis(g, a, st));
   // CSR -> CSC: stable sort of the entries by column (rows stay ascending inside a column); scratch shared with the
   // point ordering of the BLOCK walk (slot 1 holds the outputs)
   const size_t n1 = (size_t)std::max<int64_t>(nnz, 1);
   const size_t tb = csc_temp_bytes(std::max<int64_t>(nnz, 1));
-  if (int rc = g->s_key[0].reserve(n1)) return rc;
-  if (int rc = g->s_key2[0].reserve(n1)) return rc;
-  if (int rc = g->s_idx[0].reserve(n1)) return rc;
-  if (int rc = g->s_perm[0].reserve(n1)) return rc;
-  if (int rc = g->s_key[1].reserve(n1)) return rc;
-  if (int rc = g->s_sorttmp[0].reserve(tb)) return rc;
-  DevBuf<long long> &d_colptr = g->c_PL, &d_rowidx = g->c_PI;  // adapt! scratch, free between calls
+  if (int rc = R.s_key[0].reserve(n1)) return rc;
+  if (int rc = R.s_key2[0].reserve(n1)) return rc;
+  if (int rc = R.s_idx[0].reserve(n1)) return rc;
+  if (int rc = R.s_perm[0].reserve(n1)) return rc;
+  if (int rc = R.s_key[1].reserve(n1)) return rc;
+  if (int rc = R.s_sorttmp[0].reserve(tb)) return rc;
+  DevBuf<long long> &d_colptr = R.c_PL, &d_rowidx = R.c_PI;  // adapt! scratch, free between calls
   if (int rc = d_colptr.reserve((size_t)N + 1)) return rc;
   if (int rc = d_rowidx.reserve(n1)) return rc;
-  if (int rc = g->s_tmp2.reserve(n1)) return rc;
-  if (g->sort_ev[0]) CK(cudaStreamWaitEvent(st, g->sort_ev[0], 0));
+  if (int rc = R.s_tmp2.reserve(n1)) return rc;
+  if (R.sort_ev[0]) CK(cudaStreamWaitEvent(st, R.sort_ev[0], 0));
   int64_t l = 0;
-  CK(csr_to_csc(g->s_i64a.p, g->s_i64b.p, g->s_tmp.p, M, N, nnz, g->s_key[0].p, g->s_key2[0].p, g->s_idx[0].p,
-                g->s_perm[0].p, g->s_key[1].p, g->s_sorttmp[0].p, tb, d_colptr.p, d_rowidx.p, g->s_tmp2.p, st, &l));
+  CK(csr_to_csc(R.s_i64a.p, R.s_i64b.p, R.s_tmp.p, M, N, nnz, R.s_key[0].p, R.s_key2[0].p, R.s_idx[0].p,
+                R.s_perm[0].p, R.s_key[1].p, R.s_sorttmp[0].p, tb, d_colptr.p, d_rowidx.p, R.s_tmp2.p, st, &l));
   bump(l);
   CK(cudaMemcpyAsync(colptr, d_colptr.p, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, st));
   if (nnz) {
     CK(cudaMemcpyAsync(rowidx, d_rowidx.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vals, g->s_tmp2.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(vals, R.s_tmp2.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
   g->ch_n = -1;  // the adapt! scratch was reused
@@ -1132,15 +1418,18 @@ int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, 
 
 int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, double atol,
                                int32_t dropzeros, double *dout, int64_t ldm, int64_t ldn, void *stream) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   if (M == 0 || g->N == 0) return ASG_OK;
+  if (replica_of_pointer(dX) != 0) return set_err(ASG_EINVAL, "basis entry points run on the primary device of the context");
+  USE_REPLICA(g, 0);
   cudaStream_t st = (cudaStream_t)stream;  // NULL is the CUDA default stream, as everywhere in CUDA
   BasisArgs a{};
   a.X = dX; a.M = M; a.sp = sp; a.sd = sdim; a.atol = atol; a.dropzeros = dropzeros; a.mode = 2;
   a.dense = dout; a.ldm = ldm; a.ldn = ldn;
-  CK(cudaEventRecord(ctx.ev0, st));
+  CK(cudaEventRecord(dc.ev0, st));
   if (g->path() == ASG_PATH_SUBSPACE) {
     // the walk only visits supporting nodes: clear first (needs a dense M x N block)
     const bool rowmajor = (ldn == 1 && ldm >= g->N), colmajor = (ldm == 1 && ldn >= M);
@@ -1149,13 +1438,16 @@ int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t
     else return set_err(ASG_EUNSUPPORTED, "dense basis needs ldn == 1 (row-major) or ldm == 1 (column-major)");
   }
   CK(run_basis(g, a, st));
-  CK(cudaEventRecord(ctx.ev1, st));
-  ctx.last_timed = true;
+  CK(cudaEventRecord(dc.ev1, st));
+  dc.last_timed = true;
+  dc.walk_timed = false;
+  ctx.last_dev = 0;
   return ASG_OK;
 }
 
 int32_t asg_basis_dense(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                         int32_t dropzeros, double *out, int64_t ldm, int64_t ldn) {
+  ASG_TRACE();
   if (int rc = check_eval_args(g, X, M, out)) return rc;
   if (int rc = require_ctx()) return rc;
   const int64_t N = g->N;
@@ -1167,22 +1459,23 @@ int32_t asg_basis_dense(asg_grid *g, const double *X, int64_t M, int64_t sp, int
   const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(M, ((int64_t)1 << 27) / std::max<int64_t>(N, 1)));
   std::vector<double> rb;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  USE_REPLICA(g, 0);
   for (int64_t m0 = 0; m0 < M; m0 += chunk) {
     const int64_t cnt = std::min(chunk, M - m0);
     int64_t dsp, dsd;
-    if (int rc = g->s_X[1].reserve((size_t)cnt * g->D)) return rc;
-    if (int rc = g->s_tmp2.reserve((size_t)cnt * N)) return rc;
-    if (int rc = stage_points(X, m0, cnt, g->D, sp, sdim, g->s_X[1].p, dsp, dsd, ctx.stream, rb)) return rc;
+    if (int rc = R.s_X[1].reserve((size_t)cnt * g->D)) return rc;
+    if (int rc = R.s_tmp2.reserve((size_t)cnt * N)) return rc;
+    if (int rc = stage_points(X, m0, cnt, g->D, sp, sdim, R.s_X[1].p, dsp, dsd, dc.stream, rb)) return rc;
     const int64_t dldm = rowmajor ? N : 1, dldn = rowmajor ? 1 : cnt;
-    if (int rc = asg_basis_dense_device(g, g->s_X[1].p, cnt, dsp, dsd, atol, dropzeros, g->s_tmp2.p, dldm, dldn, ctx.stream))
+    if (int rc = asg_basis_dense_device(g, R.s_X[1].p, cnt, dsp, dsd, atol, dropzeros, R.s_tmp2.p, dldm, dldn, dc.stream))
       return rc;
     if (rowmajor)
-      CK(cudaMemcpy2DAsync(out + m0 * ldm, (size_t)ldm * 8, g->s_tmp2.p, (size_t)N * 8, (size_t)N * 8, (size_t)cnt,
-                           cudaMemcpyDeviceToHost, ctx.stream));
+      CK(cudaMemcpy2DAsync(out + m0 * ldm, (size_t)ldm * 8, R.s_tmp2.p, (size_t)N * 8, (size_t)N * 8, (size_t)cnt,
+                           cudaMemcpyDeviceToHost, dc.stream));
     else
-      CK(cudaMemcpy2DAsync(out + m0, (size_t)ldn * 8, g->s_tmp2.p, (size_t)cnt * 8, (size_t)cnt * 8, (size_t)N,
-                           cudaMemcpyDeviceToHost, ctx.stream));
-    CK(cudaStreamSynchronize(ctx.stream));
+      CK(cudaMemcpy2DAsync(out + m0, (size_t)ldn * 8, R.s_tmp2.p, (size_t)cnt * 8, (size_t)cnt * 8, (size_t)N,
+                           cudaMemcpyDeviceToHost, dc.stream));
+    CK(cudaStreamSynchronize(dc.stream));
   }
   return ASG_OK;
 }
@@ -1228,6 +1521,7 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
 
 // ---- device-format persistence -------------------------------------------------
 int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes) {
+  ASG_TRACE();
   if (!g || !bytes) return set_err(ASG_EINVAL, "null argument");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
@@ -1247,22 +1541,50 @@ int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes
   return ASG_OK;
 }
 
-int32_t asg_grid_import(asg_grid *g, const void *buf, int64_t bytes) {
-  if (!g || !buf || bytes <= 0) return set_err(ASG_EINVAL, "null argument");
-  if (int rc = require_ctx()) return rc;
-  std::lock_guard<std::recursive_mutex> lk(g->mu);
+static int import_common(asg_grid *g, const void *buf, int64_t bytes, int64_t N, const int64_t *levels,
+                         const int64_t *indices, int64_t sn, int64_t sd, const double *coefs, bool check) {
   PackResult pk;
   std::vector<int64_t> L, I;
   std::vector<double> c;
   std::string err;
   int rc = pack_deserialize((const unsigned char *)buf, (size_t)bytes, g->D, g->lb, g->ub, L, I, c, pk, err);
   if (rc != ASG_OK) return set_err(rc, err);
+  if (check) {
+    // the blob is a cache of THESE arrays: a blob written before an in-place coefficient update, or one of another
+    // grid with the same D / domain / node count, must not be installed
+    const int D = g->D;
+    bool same = (int64_t)c.size() == N;
+    for (int64_t k = 0; same && k < N; ++k) {
+      for (int d = 0; same && d < D; ++d)
+        same = L[(size_t)k * D + d] == levels[k * sn + d * sd] && I[(size_t)k * D + d] == indices[k * sn + d * sd];
+      if (same && coefs) same = std::memcmp(&c[(size_t)k], &coefs[k], 8) == 0;
+    }
+    if (!same) return set_err(ASG_ESTATE, "packed blob does not describe these node arrays (stale or foreign blob)");
+  }
   g->uploaded = false;
   g->levels.swap(L);
   g->indices.swap(I);
   g->coefs.swap(c);
   g->N = (int64_t)g->coefs.size();
   return install_pack(g, pk);
+}
+
+int32_t asg_grid_import(asg_grid *g, const void *buf, int64_t bytes) {
+  ASG_TRACE();
+  if (!g || !buf || bytes <= 0) return set_err(ASG_EINVAL, "null argument");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  return import_common(g, buf, bytes, 0, nullptr, nullptr, 0, 0, nullptr, false);
+}
+
+int32_t asg_grid_import_checked(asg_grid *g, const void *buf, int64_t bytes, int64_t N, const int64_t *levels,
+                                const int64_t *indices, int64_t sn, int64_t sd, const double *coefs) {
+  ASG_TRACE();
+  if (!g || !buf || bytes <= 0) return set_err(ASG_EINVAL, "null argument");
+  if (N < 0 || (N > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "bad node arrays");
+  if (int rc = require_ctx()) return rc;
+  std::lock_guard<std::recursive_mutex> lk(g->mu);
+  return import_common(g, buf, bytes, N, levels, indices, sn, sd, coefs, true);
 }
 
 int32_t asg_rsg_count(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N) {
@@ -1281,6 +1603,7 @@ int32_t asg_rsg_fill(int32_t D, int64_t maxdepth, const int64_t *maxlevels, int6
 }
 
 int32_t asg_measure_fp64_peak(double *fma_per_second) {
+  DevCtx &dc = ctx.dev[0];
   if (!fma_per_second) return set_err(ASG_EINVAL, "null pointer");
   if (int rc = require_ctx()) return rc;
   double *sink = nullptr;
@@ -1290,12 +1613,12 @@ int32_t asg_measure_fp64_peak(double *fma_per_second) {
   int64_t l = 0;
   double best = 0.0;
   for (int rep = 0; rep < 5; ++rep) {
-    CK(cudaEventRecord(ctx.ev0, ctx.stream));
-    CK(launch_fp64_peak(iters, sink, ctx.stream, &l, &blocks, &threads));
-    CK(cudaEventRecord(ctx.ev1, ctx.stream));
-    CK(cudaEventSynchronize(ctx.ev1));
+    CK(cudaEventRecord(dc.ev0, dc.stream));
+    CK(launch_fp64_peak(iters, sink, dc.stream, &l, &blocks, &threads));
+    CK(cudaEventRecord(dc.ev1, dc.stream));
+    CK(cudaEventSynchronize(dc.ev1));
     float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, ctx.ev0, ctx.ev1));
+    CK(cudaEventElapsedTime(&ms, dc.ev0, dc.ev1));
     const double rate = (double)blocks * threads * 8.0 * iters / (ms * 1e-3);
     if (rep > 0) best = std::max(best, rate);
   }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -182,6 +183,21 @@ int rsg_count(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t *N, std
 int rsg_fill(int D, int64_t maxdepth, const int64_t *maxlevels, int64_t N, int64_t *levels, int64_t *indices, int64_t sn,
              int64_t sd, std::string &err);
 
+// Raise a kernel's dynamic shared-memory limit ONCE PER DEVICE to `bytes` (its maximum over all launches): function
+// attributes are per device, and setting the limit per launch to that launch's own size races between host threads
+// that launch the same instantiation with different sizes. `mask` is one static per instantiation (bit = device).
+template <class K>
+inline cudaError_t smem_limit_once(K kernel, int bytes, std::atomic<unsigned> &mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned bit = 1u << (dev & 31);
+  if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+  return e;
+}
+
 // ---- kernel launchers (asg_kernels_*.cu) -------------------------------------------------------
 struct EvalArgs {
   const double *X;   // device
@@ -237,6 +253,9 @@ cudaError_t launch_children(int D, int64_t n_p, const long long *PL, const long 
                             unsigned char *valid, int *table, int64_t table_size, unsigned int *flags,
                             unsigned int *sums, unsigned int *total, long long *OL, long long *OI, cudaStream_t st,
                             int64_t *launches);
+// elementwise phi (src/math.jl:332-391): out[k] = prod_d phi(x[k,d]; lev[k,d], idx[k,d]); lev == nullptr: phi(x[k,d])
+cudaError_t launch_phi(int D, int64_t n, const double *x, const long long *lev, const long long *idx, double *out, int *bad,
+                       cudaStream_t st, int64_t *launches);
 cudaError_t launch_scatter_f64(double *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,
                                int64_t *launches);
 cudaError_t launch_scatter_hash(HashEnt *dst, const long long *slots, const double *src, int64_t n, cudaStream_t st,

@@ -26,16 +26,16 @@ static int blk_threads() { return kBlkThreads; }
 
 bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_bytes(g, 1, blk_threads()) <= 227 * 1024; }
 
-extern template void blk_launch<1, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template void blk_launch<1, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template void blk_launch<2, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template void blk_launch<2, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<1, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<1, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
 
 template <int NT>
-static void blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, int blocks, size_t smem,
-                          cudaStream_t st) {
-  if (two) { if (masked) blk_launch<2, true, NT>(g, a, blocks, smem, st); else blk_launch<2, false, NT>(g, a, blocks, smem, st); }
-  else     { if (masked) blk_launch<1, true, NT>(g, a, blocks, smem, st); else blk_launch<1, false, NT>(g, a, blocks, smem, st); }
+static cudaError_t blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, int blocks, size_t smem,
+                                 cudaStream_t st) {
+  if (two) return masked ? blk_launch<2, true, NT>(g, a, blocks, smem, st) : blk_launch<2, false, NT>(g, a, blocks, smem, st);
+  return masked ? blk_launch<1, true, NT>(g, a, blocks, smem, st) : blk_launch<1, false, NT>(g, a, blocks, smem, st);
 }
 
 cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
@@ -51,7 +51,8 @@ cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream
   const int64_t need = (a.M + per_block - 1) / per_block;
   const int blocks = (int)(need < sms ? need : sms);
   const bool masked = a.rem < INT_MAX / 4;
-  blk_launch_nt<kBlkThreads>(g, a, two, masked, blocks, smem, st);
+  const cudaError_t e = blk_launch_nt<kBlkThreads>(g, a, two, masked, blocks, smem, st);
+  if (e != cudaSuccess) return e;  // the shared-memory limit of the kernel could not be raised
   if (launches) ++*launches;
   return cudaGetLastError();
 }

@@ -5,7 +5,7 @@
 //
 // * One thread owns R = 2 query points, a CTA of 512 threads owns 1024 points and walks the whole record
 //   stream for them; one CTA per SM, grid-stride over the points.
-// * Records (16 B, one per prefix level vector) and the coefficient blocks they reference are streamed
+// * Records (32 B, pre-decoded, one per prefix level vector) and the coefficient blocks they reference are streamed
 //   from L2 into shared memory by 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completed on
 //   mbarriers, double buffered.
 // * A record applies ONE data-driven stage (the level of its last non-trivial prefix dimension) to the
@@ -398,13 +398,13 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
 // One launch function per (points per thread, masked) variant; each is instantiated in its own translation unit
 // (asg_kernels_block_r{1,2}{,m}.cu) so that the four large kernels compile in parallel.
 template <int R, bool MASKED, int NT>
-void blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
-  // one instantiation serves every grid: raise its dynamic shared-memory limit ONCE to the device maximum (setting
-  // it per launch to the launch's own size races between host threads that evaluate different grids)
-  static const cudaError_t once =
-      cudaFuncSetAttribute(k_eval_block<R, MASKED, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  (void)once;
+cudaError_t blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
+  // one instantiation serves every grid: raise its dynamic shared-memory limit once per device to the device maximum
+  static std::atomic<unsigned> limit_set{0};
+  const cudaError_t e = smem_limit_once(k_eval_block<R, MASKED, NT>, 227 * 1024, limit_set);
+  if (e != cudaSuccess) return e;
   k_eval_block<R, MASKED, NT><<<blocks, NT, smem, st>>>(g, a);
+  return cudaSuccess;
 }
 
 }  // namespace asg

@@ -45,6 +45,53 @@ cudaError_t launch_nodes_x(int D, const double *, const DeviceGrid &g, const lon
   return cudaGetLastError();
 }
 
+// phi of src/math.jl:332-334 (lev == nullptr: the plain hat on [-1, 1]), 345-357 (level / index form: three forms +
+// throw) and 376-391 (vector form: prod(phi.(x, levels, indices)), a left fold over the D dimensions). x is in
+// UNIT-CUBE coordinates like in the reference; every operation is the reference's own (mul, then sub, then 1 - |t|;
+// never fused), so the values are bit-identical to Julia's.
+__device__ __forceinline__ double phi_plain(double t) { return (-1.0 <= t && t <= 1.0) ? __dsub_rn(1.0, fabs(t)) : 0.0; }
+__global__ void k_phi(int D, int64_t n, const double *x, const long long *lev, const long long *idx, double *out, int *bad) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    double p = 1.0;
+    for (int d = 0; d < D; ++d) {
+      const double xv = x[k * D + d];
+      double v;
+      if (!lev) {
+        v = phi_plain(xv);
+      } else {
+        const long long l = lev[k * D + d], i = idx[k * D + d];
+        if (l > 2) {
+          // x * power2(l - 1) - i: Int -> Float64 promotion of 2^(l-1) and of i, two roundings (src/math.jl:347)
+          if (l > 62) atomicMax(bad, 2);  // power2(l - 1) leaves Int64: outside this library's range
+          const double s = __longlong_as_double((long long)(1023 + (l > 62 ? 62 : l) - 1) << 52);
+          v = phi_plain(__dsub_rn(__dmul_rn(xv, s), (double)i));
+        } else if (l == 2 && i == 0) {
+          v = (0.0 <= xv && xv <= 0.5) ? __dsub_rn(1.0, __dmul_rn(2.0, xv)) : 0.0;
+        } else if (l == 2 && i == 2) {
+          v = (0.5 <= xv && xv <= 1.0) ? __dsub_rn(__dmul_rn(2.0, xv), 1.0) : 0.0;
+        } else if (l == 1) {
+          v = (0.0 <= xv && xv <= 1.0) ? 1.0 : 0.0;
+        } else {
+          v = __longlong_as_double(0x7ff8000000000000ll);
+          atomicMax(bad, 1);  // ArgumentError("invalid level-index pair"), src/math.jl:355
+        }
+      }
+      p = d == 0 ? v : __dmul_rn(p, v);
+    }
+    out[k] = p;
+  }
+}
+
+cudaError_t launch_phi(int D, int64_t n, const double *x, const long long *lev, const long long *idx, double *out, int *bad,
+                       cudaStream_t st, int64_t *launches) {
+  if (n <= 0) return cudaSuccess;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  k_phi<<<(int)blocks, 256, 0, st>>>(D, n, x, lev, idx, out, bad);
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
 __global__ void k_scatter_f64(double *dst, const long long *slots, const double *src, int64_t n) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
     if (slots[k] >= 0) dst[slots[k]] = src[k];

@@ -549,10 +549,13 @@ cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStrea
   const int64_t cap = (int64_t)sms * resident;
   const int blocks = (int)(need < 1 ? 1 : (need < cap ? need : cap));
   const bool masked = a.rem < INT_MAX / 4;
+  cudaError_t lim = cudaSuccess;
+  // (the shared memory of an instantiation depends on D, R only: its limit is set once per device)
 #define LAUNCH(DD, RR, MM, VV)                                                                                    \
   do {                                                                                                            \
-    cudaFuncSetAttribute(k_eval_stream<DD, RR, MM, VV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    k_eval_stream<DD, RR, MM, VV><<<blocks, threads, smem, st>>>(g, a);                                           \
+    static std::atomic<unsigned> limit_set{0};                                                                    \
+    lim = smem_limit_once(k_eval_stream<DD, RR, MM, VV>, (int)smem, limit_set);                                   \
+    if (lim == cudaSuccess) k_eval_stream<DD, RR, MM, VV><<<blocks, threads, smem, st>>>(g, a);                   \
   } while (0)
 #define CALL(DD)                                                                                          \
   do {                                                                                                    \
@@ -562,6 +565,7 @@ cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStrea
   ASG_DISPATCH_D2(g.D, CALL)
 #undef CALL
 #undef LAUNCH
+  if (lim != cudaSuccess) return lim;
   if (launches) ++*launches;
   return cudaGetLastError();
 }

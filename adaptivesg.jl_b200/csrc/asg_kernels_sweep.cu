@@ -179,13 +179,17 @@ cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream
   if (a.M <= 0) return cudaSuccess;
   const size_t sm = sweep_smem(g.D);
   const int blocks = grid_for(a.M);
+  cudaError_t lim = cudaSuccess;
+  // limit raised once per device and instantiation to the largest tile the instantiation can need (D > 12 share one)
 #define CALL(DD)                                                                                        \
   do {                                                                                                  \
-    cudaFuncSetAttribute(k_eval_sweep<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);       \
-    k_eval_sweep<DD><<<blocks, kSweepThreads, sm, st>>>(g, a);                                          \
+    static std::atomic<unsigned> limit_set{0};                                                          \
+    lim = smem_limit_once(k_eval_sweep<DD>, (int)sweep_smem(DD ? DD : kMaxDim), limit_set);            \
+    if (lim == cudaSuccess) k_eval_sweep<DD><<<blocks, kSweepThreads, sm, st>>>(g, a);                  \
   } while (0)
   ASG_DISPATCH_DT(g.D, CALL)
 #undef CALL
+  if (lim != cudaSuccess) return lim;
   if (launches) ++*launches;
   return cudaGetLastError();
 }
@@ -194,13 +198,16 @@ cudaError_t launch_basis_sweep(const DeviceGrid &g, const BasisArgs &a, cudaStre
   if (a.M <= 0) return cudaSuccess;
   const size_t sm = sweep_smem(g.D);
   const int blocks = grid_for(a.M);
+  cudaError_t lim = cudaSuccess;
 #define CALL(DD)                                                                                        \
   do {                                                                                                  \
-    cudaFuncSetAttribute(k_basis_sweep<DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);      \
-    k_basis_sweep<DD><<<blocks, kSweepThreads, sm, st>>>(g, a);                                         \
+    static std::atomic<unsigned> limit_set{0};                                                          \
+    lim = smem_limit_once(k_basis_sweep<DD>, (int)sweep_smem(DD ? DD : kMaxDim), limit_set);           \
+    if (lim == cudaSuccess) k_basis_sweep<DD><<<blocks, kSweepThreads, sm, st>>>(g, a);                 \
   } while (0)
   ASG_DISPATCH_DT(g.D, CALL)
 #undef CALL
+  if (lim != cudaSuccess) return lim;
   if (launches) ++*launches;
   return cudaGetLastError();
 }

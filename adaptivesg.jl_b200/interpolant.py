@@ -26,6 +26,8 @@ __all__ = [
     "SparseGridInterpolant", "rsg", "train", "adapt", "coefficients", "basis", "dehierarchization_matrix",
     "hierarchization_matrix", "serialize", "deserialize", "maxlevels", "stack", "nodedepth", "isvalid",
     "allindices_of_level", "child", "isbig2add", "hierarchize", "AsgError", "InvalidNodeError",
+    "phi", "scale", "get_x", "parent", "perturb", "isboundary", "boundaryflag", "allnodes1d", "fraction2li",
+    "ghost_neighbor", "ghost_distance", "extrapolate",
 ]
 
 _NODE_FIELDS = ("levels", "indices", "depths", "coefs", "lb", "ub")
@@ -322,6 +324,196 @@ def _candidates_host(PL, PI):
     return CL, CI
 
 
+def phi(x, levels=None, indices=None, safe: bool = False):
+    """The exported basis function ``ϕ`` (src/math.jl:332-334, 345-357, 376-391), evaluated on the device
+    (``asg_phi``): ``phi(x)`` the plain hat on [-1, 1]; ``phi(x, l, i)`` the level / index form with its three
+    branches (``ArgumentError`` -> ``InvalidNodeError`` for an invalid pair, src/math.jl:355); ``phi(x, levels,
+    indices)`` with vectors the tensor product ``prod(ϕ.(x, levels, indices))`` for ONE node. ``x`` is in unit-cube
+    coordinates as in the reference. Additive: 2-D ``x`` (n x D) with matching n x D ``levels`` / ``indices``
+    evaluates n (point, node) pairs in one call and returns a vector. Values are bit-identical to the reference's
+    (same operations in the same order, no fused multiply-add)."""
+    lib = _capi.load()
+    _capi.init()
+    xa = np.asarray(x, dtype=np.float64)
+    if levels is None:
+        assert indices is None, "levels and indices go together"
+        flat = np.ascontiguousarray(xa.reshape(-1))
+        out = np.empty(flat.size, dtype=np.float64)
+        check(lib.asg_phi(flat.size, 1, _ptr(flat, f64p), None, None, _ptr(out, f64p)))
+        return float(out[0]) if xa.ndim == 0 else out.reshape(xa.shape)
+    La = np.asarray(levels, dtype=np.int64)
+    Ia = np.asarray(indices, dtype=np.int64)
+    if xa.ndim == 0:      # phi(x::Float64, l::Int, i::Int)
+        assert La.ndim == 0 and Ia.ndim == 0, "scalar x takes a scalar level and index"
+        n, D = 1, 1
+    elif xa.ndim == 1:    # phi(x::AbstractVector, levels, indices): one node, D dimensions
+        D = xa.shape[0]
+        if safe:
+            assert La.shape == (D,), "levels must match the dimension of x."
+            assert Ia.shape == (D,), "indices must match the dimension of x."
+        assert La.shape == (D,) and Ia.shape == (D,), "levels / indices must have the length of x"
+        n = 1
+    else:
+        assert xa.ndim == 2 and La.shape == xa.shape and Ia.shape == xa.shape, "n x D arrays of equal shape"
+        n, D = xa.shape
+    xf = np.ascontiguousarray(xa.reshape(n, D))
+    Lf = np.ascontiguousarray(La.reshape(n, D))
+    If = np.ascontiguousarray(Ia.reshape(n, D))
+    out = np.empty(n, dtype=np.float64)
+    check(lib.asg_phi(n, D, _ptr(xf, f64p), _ptr(Lf, i64p), _ptr(If, i64p), _ptr(out, f64p)))
+    return out if xa.ndim == 2 else float(out[0])
+
+
+def scale(x, from_lb, from_ub, to_lb=0.0, to_ub=1.0):
+    """src/math.jl:301-309: ``to_lb + (to_ub - to_lb) * (x - from_lb) / (from_ub - from_lb)``, element by element, in
+    the reference's order of operations (host helper; the kernels apply the same map to every query point)."""
+    x = np.asarray(x, dtype=np.float64)
+    return to_lb + ((to_ub - to_lb) * (x - np.asarray(from_lb, dtype=np.float64))) / (
+        np.asarray(from_ub, dtype=np.float64) - np.asarray(from_lb, dtype=np.float64))
+
+
+def get_x(l, i, lb=None, ub=None):
+    """src/math.jl:464-476 (scalar ``(l, i)`` -> unit-interval coordinate) and 490-497 (vectors + domain). The vector
+    form with a domain runs on the device (``asg_nodes_x_li``); the scalar form is integer arithmetic."""
+    if np.ndim(l) == 0:
+        l, i = int(l), int(i)
+        if l > 2 and (i & 1):
+            return float(i / (1 << (l - 1)))
+        if (l, i) == (2, 0):
+            return 0.0
+        if (l, i) == (2, 2):
+            return 1.0
+        if (l, i) == (1, 1):
+            return 0.5
+        raise InvalidNodeError(_capi.ASG_EINVALID_NODE, f"invalid level-index pair ({l}, {i})")
+    L = np.asarray(l, dtype=np.int64).reshape(1, -1)
+    I = np.asarray(i, dtype=np.int64).reshape(1, -1)
+    G = SparseGridInterpolant(L.shape[1], lb=lb, ub=ub)
+    return G.nodes_x(L, I)[0]
+
+
+def perturb(Ls, Is, dims: int, l: int, i: int):
+    """src/math.jl:544-556 (``dims`` 1-based)."""
+    L = np.array(Ls, dtype=np.int64)
+    I = np.array(Is, dtype=np.int64)
+    L[dims - 1], I[dims - 1] = l, i
+    return L, I
+
+
+def isboundary(l: int, i: int) -> bool:
+    """src/math.jl:572-578"""
+    return l == 2 and i in (0, 2)
+
+
+def boundaryflag(l: int, i: int) -> int:
+    """src/math.jl:596-607"""
+    if l == 2:
+        if i == 0:
+            return -1
+        if i == 2:
+            return 1
+        raise InvalidNodeError(_capi.ASG_EINVALID_NODE, f"invalid level-index pair ({l}, {i})")
+    return 0
+
+
+def fraction2li(num: int, den: int):
+    """src/math.jl:516-530: the node of the reduced fraction num/den (den a power of two)."""
+    from math import gcd
+    g = gcd(num, den) or 1
+    num, den = num // g, den // g
+    if num == 0:
+        return 2, 0
+    if (num, den) == (1, 1):
+        return 2, 2
+    if (num, den) == (1, 2):
+        return 1, 1
+    if den & (den - 1):
+        raise ValueError("denominator must be a power of two")
+    return den.bit_length(), num   # invpower2(den) + 1
+
+
+def allnodes1d(l: int):
+    """src/math.jl:621-639: all nodes of the full level-l grid in ascending order of their coordinate."""
+    if l < 1:
+        raise ValueError(f"level must be >= 1 but got {l}")
+    if l == 1:
+        return [1], [1]
+    if l == 2:
+        return [1, 2, 2], [1, 0, 2]
+    den = 1 << (l - 1)
+    pairs = [fraction2li(k, den) for k in range(den + 1)]
+    return [p[0] for p in pairs], [p[1] for p in pairs]
+
+
+def parent(Ls, Is, dims: int):
+    """src/math.jl:1002-1024"""
+    l, i = int(Ls[dims - 1]), int(Is[dims - 1])
+    if l > 3:
+        inew = (i // 4) * 2 + 1
+    elif (l, i) == (3, 1):
+        inew = 0
+    elif (l, i) == (3, 3):
+        inew = 2
+    elif (l, i) in ((2, 0), (2, 2)):
+        inew = 1
+    elif l == 1:
+        inew = 0
+    else:
+        raise InvalidNodeError(_capi.ASG_EINVALID_NODE, f"invalid level-index pair ({l}, {i})")
+    return perturb(Ls, Is, dims, l - 1, inew)
+
+
+def ghost_distance(lmax: int) -> float:
+    """src/math.jl:888-890"""
+    return 1.0 / float(1 << (lmax - 1))
+
+
+def ghost_neighbor(Ls, Is, dims: int, l0: int, side: str = "left"):
+    """src/math.jl:704-879: nearest nodal neighbour on the full level-``l0`` grid along ``dims``; ``(0, -1)`` in that
+    dimension when there is none."""
+    side = side.lstrip(":")
+    if side not in ("left", "right"):
+        raise ValueError("side must be :left or :right")
+    if l0 < 1:
+        raise ValueError(f"invalid level {l0}")
+    lj, ij = int(Ls[dims - 1]), int(Is[dims - 1])
+    step = -1 if side == "left" else 1
+    none = (0, -1)
+    if l0 == 1:
+        new = none
+    elif l0 == 2:
+        order = [(2, 0), (1, 1), (2, 2)]
+        if (lj, ij) in order:
+            k = order.index((lj, ij)) + step
+            new = order[k] if 0 <= k <= 2 else none
+        else:
+            new = none
+    else:
+        if lj < 1:
+            raise ValueError("lj<1, invalid input node")
+        den = 1 << (l0 - 1)
+        if lj == 1:
+            if ij != 1:
+                raise ValueError("invalid input node")
+            pos = den // 2
+        elif lj == 2:
+            if ij not in (0, 2):
+                raise ValueError("invalid input node")
+            pos = 0 if ij == 0 else den
+        elif lj <= l0:
+            pos = ij * (1 << (l0 - lj))
+        else:
+            raise ValueError("lj > l0 found, no grid defined")
+        k = pos + step
+        if k < 0 or k > den:
+            new = none
+        elif lj == 2 and 0 < k < den:
+            new = (l0, k)   # the reference names the boundary's neighbour (l0, 1) / (l0, 2^(l0-1) - 1) directly
+        else:
+            new = fraction2li(k, den)
+    return perturb(Ls, Is, dims, new[0], new[1])
+
+
 def isbig2add(alpha, fx, rtol, atol, use_rtol):
     """src/math.jl:257-274, vectorised; isapprox(fx, 0, atol = rtol) is |fx| <= rtol."""
     alpha, fx = np.asarray(alpha), np.asarray(fx)
@@ -368,6 +560,7 @@ def extrapolate(G: SparseGridInterpolant, X, dims: int = 1) -> np.ndarray:
     X = np.atleast_2d(X)
     D = G.ndims
     assert X.shape[1] == D, "x must have the same dimension as the grid."
+    assert len(G) > 0, "The grid structure in G is empty."
     lb, ub = np.asarray(G.lb, dtype=np.float64), np.asarray(G.ub, dtype=np.float64)
     w = ub - lb
     with np.errstate(invalid="ignore"):
@@ -526,14 +719,20 @@ def deserialize(dat: dict) -> SparseGridInterpolant:
     G.fvals = dat["fvals"]
     G.coefs = dat["coefs"]
     if dat.get("packed") is not None:
-        # device-format blob: straight to the upload; a blob of another build (other layout constants) is ignored
+        # device-format blob: straight to the upload IF it describes exactly these arrays. serialize() aliases the
+        # arrays, so an in-place update after the blob was written (train!, hierarchize, the user) leaves it stale; a
+        # stale or foreign blob (ASG_ESTATE) and a blob of another build (ASG_EUNSUPPORTED) fall back to the normal
+        # upload on first use.
         buf = np.ascontiguousarray(dat["packed"], dtype=np.uint8)
-        rc = _capi.load().asg_grid_import(G._grid(), buf.ctypes.data_as(C.c_void_p), buf.size)
+        Lv = np.ascontiguousarray(G.levels, dtype=np.int64)
+        Ix = np.ascontiguousarray(G.indices, dtype=np.int64)
+        cf = np.ascontiguousarray(G.coefs, dtype=np.float64)
+        assert Lv.shape == Ix.shape == (len(cf), G.ndims), "inconsistent node arrays"
+        rc = _capi.load().asg_grid_import_checked(G._grid(), buf.ctypes.data_as(C.c_void_p), buf.size, len(cf),
+                                                  _ptr(Lv, i64p), _ptr(Ix, i64p), G.ndims, 1, _ptr(cf, f64p))
         if rc == 0:
-            info = G.info_raw()
-            assert info["N"] == len(G.levels), "packed blob does not belong to these node arrays"
             object.__setattr__(G, "_dirty", False)
-        elif rc != _capi.ASG_EUNSUPPORTED:
+        elif rc not in (_capi.ASG_EUNSUPPORTED, _capi.ASG_ESTATE):
             check(rc)
     return G
 

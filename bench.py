@@ -44,6 +44,16 @@ def build_grid_arrays():
     return G
 
 
+def build_oracle_grid():
+    """The same grid built by the ORACLE's own enumeration (the reference arm maps nothing of the product)."""
+    from oracle import oracle as o
+    OG = o.OracleGrid(D)
+    OG.rsg(DEPTH, MAXLEVEL)
+    rng = np.random.default_rng(1234)
+    OG.coefs = rng.standard_normal(len(OG)) * 2.0 ** (-OG.depths.astype(np.float64))
+    return OG
+
+
 def fp64_op_counts(levels):
     """FP64 work the stream kernel (asg_kernels_stream.cu, SUPER records) must do for ONE point, counted
     from the level vectors of `levels` (N x D). Dimensions 0..D-3 are walked: every trie node there with
@@ -225,14 +235,18 @@ def main():
         # the image, so this is the oracle port of its algorithm (kind = "port"); rank 0 only.
         if rank != 0:
             return
-        Gh = build_grid_arrays()
+        Gh = build_oracle_grid()
         rate, cores, n, sec, _, _ = cpu_reference_rate(Gh, seconds_target=15.0, steps=K, warmup=min(W, 1))
         line = {
             "impl": "reference", "metric": "interpolant evaluations per second", "value": rate, "unit": "points/s",
             "n_gpus": args.gpus, "steps": K, "warmup": min(W, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "nodes": int(len(Gh)), "points_per_step": n,
-                       "note": "bounded sample of the 1e8-point workload; per-point cost is independent of M"},
+                       "note": "bounded sample of the 1e8-point workload (the reference streams 224 MB per point, "
+                               "src/class.jl:638-642: 1e8 points would take ~1e5 s); per-point cost is independent of M, "
+                               "so steps / points differ from the product arm by design",
+                       "generous_to_reference": "-O2 OpenMP C port of the reference's loop structure; Julia's broadcast "
+                                                "additionally allocates N doubles per point"},
             "products_per_s": rate * len(Gh),
             "cpu_baseline": {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
                              "sample": f"{n} of {M_total} points, restated reference algorithm "
@@ -280,12 +294,19 @@ def main():
             key = (key << bits) | (X[:, d] * (1 << bits)).to(torch.int64).clamp_(0, (1 << bits) - 1)
         X = X[torch.argsort(key)].contiguous()
         del key
-    out = torch.empty(M, dtype=torch.float64, device=dev)
+    # C2: the all-gather of the result shards is part of every step for N > 1, inside the timed region;
+    # the walk writes its shard straight into the padded send buffer
+    per = -(-M_total // world)
+    pad = torch.zeros(per, dtype=torch.float64, device=dev)
+    out = pad[:M]
+    full = torch.empty(per * world, dtype=torch.float64, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream()
 
     def step_device():
         asg._capi.check(lib.asg_eval_device(h, C.c_void_p(X.data_ptr()), M, D, 1, -1, C.c_void_p(out.data_ptr()),
                                             C.c_void_p(stream.cuda_stream)))
+        if world > 1:
+            dist.all_gather_into_tensor(full, pad)
 
     def barrier():
         if world > 1:
@@ -318,6 +339,16 @@ def main():
         kern_ms.append(ms.value)
         asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))   # point ordering + walk
         call_ms.append(ms.value)
+    # the gather alone (reported; it is already inside ms_per_step)
+    gather_ms = None
+    if world > 1:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        g0.record()
+        dist.all_gather_into_tensor(full, pad)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
     t = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
@@ -328,22 +359,7 @@ def main():
     ms_per_step = ms_total / K
     value = M_total / (ms_per_step * 1e-3)
     checksum = float(out.sum().item())
-
-    # ---- C2: gather the result shards (NCCL all-gather), outside the timed kernel region --------
-    gather_ms = None
-    if world > 1:
-        per = -(-M_total // world)
-        pad = torch.zeros(per, dtype=torch.float64, device=dev)
-        pad[:M] = out
-        full = torch.empty(per * world, dtype=torch.float64, device=dev)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        g0.record()
-        dist.all_gather_into_tensor(full, pad)
-        g1.record()
-        barrier()
-        gather_ms = g0.elapsed_time(g1)
-        del full, pad
+    del full
 
     # ---- e2e: the public API with pinned host buffers (H2D and D2H inside the timed region) ------
     e2e = None
@@ -377,12 +393,17 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (k_eval_block<2,false,512>; k_eval_stream on other grids) ----
+    # The binding resource of the walk is the shared-memory data pipe: one 128-byte WAVEFRONT per clock per SM (ncu:
+    # l1tex__data_pipe_lsu_wavefronts_mem_shared). Counts per point (wavefronts, FP64 thread instructions, DRAM bytes)
+    # are MEASURED: they come from the committed ncu capture of this same kernel (profiles/*_summary.json, written by
+    # profiles/summarize_ncu.py); times, clocks and the FP64 peak are measured live in this run. So
+    # frac * peak * kernel_ms == the ncu wavefront count scaled to this launch's points, by construction.
     fma_rate = C.c_double()
     asg._capi.check(lib.asg_measure_fp64_peak(C.byref(fma_rate)))
     block = bool(info.get("block")) and os.environ.get("ASG_EVAL_KERNEL", "b")[0] == "b"
-    instr, flops, leaves = fp64_op_counts_block(G.levels, int(info["block_records"])) if block else fp64_op_counts(G.levels)
     kname = "k_eval_block<2,false,512>" if block else f"k_eval_stream<{D},R,false>"
-    prof_name = "r01b_final_eval_block_d10_summary.json" if block else "r01_final_eval_stream_d10_summary.json"
+    prof_names = (["r02_eval_block_d10_summary.json", "r01b_final_eval_block_d10_summary.json"] if block
+                  else ["r01_final_eval_stream_d10_summary.json"])
     k_ms = statistics.median(kern_ms)
     pts_per_launch = M
     peaks = {}
@@ -392,55 +413,95 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     alg_bytes = pts_per_launch * (8 * D + 8)
+    props = torch.cuda.get_device_properties(dev)
+    n_sm = props.multi_processor_count
+    sm_hz = (clocks["sm_mhz"] if clocks and clocks.get("sm_mhz") else peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    instr_model, flops_model, leaves = (fp64_op_counts_block(G.levels, int(info["block_records"])) if block
+                                        else fp64_op_counts(G.levels))
     roofline = {
-        "bound": "fp64",  # FP64 CUDA-core pipe: the path is a sparse gather-product, not HBM- or tensor-bound
-        "kernel": kname,
-        "achieved": flops * pts_per_launch / (k_ms * 1e-3) / 1e12,
-        "peak": 2.0 * fma_rate.value / 1e12,
-        "unit": "TFLOP/s",
-        "frac": (flops * pts_per_launch / (k_ms * 1e-3)) / (2.0 * fma_rate.value),
-        "peak_source": "DFMA microbenchmark measured live in this run (MEASURED_PEAKS.json has no FP64 entry)",
-        "fp64_pipe_slot_frac": (instr * pts_per_launch / (k_ms * 1e-3)) / fma_rate.value,
-        "fp64_instr_per_point": instr, "flop_per_point": flops, "terms_per_point": leaves,
-        "kernel_ms": k_ms, "points_per_launch": pts_per_launch,
+        "bound": "smem",  # shared-memory wavefronts; neither "hbm" nor "tensor" describes a sparse gather-product
+        "kernel": kname, "kernel_ms": k_ms, "points_per_launch": pts_per_launch,
         "point_order_ms": statistics.median(call_ms) - k_ms,
-        "traffic": None,
+        "achieved": None, "peak": n_sm * sm_hz * 128.0 / 1e9, "unit": "GB/s", "frac": None, "traffic": None,
+        "peak_source": f"{n_sm} SMs x 128 B/clk x SM clock sampled under load in this run ({sm_hz / 1e6:.0f} MHz)",
+        "terms_per_point": leaves,
         "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_point": 8 * D + 8,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
         "dense_equivalent": {"products_per_s": N * pts_per_launch / (k_ms * 1e-3),
                              "fp64_instr_per_product": 3 * D + 1,
                              "frac_of_fp64_peak": (N * (3 * D + 1) * pts_per_launch / (k_ms * 1e-3)) / fma_rate.value,
                              "note": "N*M/t with every (node, point) pair counted, SURVEY.md 8d; > 1 because "
-                                     "only the one supporting node per subspace is visited"},
+                                     "only the one supporting node per subspace is visited; not a roofline"},
     }
-    prof = os.path.join(ROOT, "profiles", prof_name)
-    if os.path.exists(prof):
+    for prof_name in prof_names:
+        prof = os.path.join(ROOT, "profiles", prof_name)
+        if not os.path.exists(prof):
+            continue
         try:
             pj = json.load(open(prof))
-            # ncu capture is of a shorter launch: scale its measured DRAM bytes to this launch's point count
-            roofline["traffic"] = pj["dram_bytes_per_launch"] * pts_per_launch / pj["points_per_launch"]
-            roofline["traffic_source"] = os.path.basename(prof)
             k0 = pj["kernels"][0]
-            # the gate is read from ncu on the kernel actually run -- the binding pipe
+            ppl = float(pj["points_per_launch"])
+            roofline["counts_source"] = f"profiles/{prof_name} (ncu --set full of this kernel, {int(ppl)} points per launch)"
+            roofline["ncu_kernel"] = k0.get("kernel")
+            # ncu capture may be of a launch with another point count: per-point counts scale, DRAM bytes too
+            roofline["traffic"] = pj["dram_bytes_per_launch"] * pts_per_launch / ppl
+            if "smem_wavefronts" in k0:
+                wpp = k0["smem_wavefronts"] / ppl
+                roofline["smem_wavefronts_per_point"] = wpp
+                roofline["smem_ld_instructions_per_32_points"] = k0.get("smem_ld_warp_instructions", 0.0) / ppl * 32.0
+                roofline["achieved"] = wpp * pts_per_launch * 128.0 / (k_ms * 1e-3) / 1e9
+                roofline["frac"] = roofline["achieved"] / roofline["peak"]
+                roofline["ncu_frac_same_counter"] = k0.get("smem_wavefront_frac")
+            if "fp64_thread_inst" in k0:
+                fpp = k0["fp64_thread_inst"] / ppl
+                roofline["fp64"] = {"thread_instructions_per_point": fpp,
+                                    "achieved": fpp * pts_per_launch / (k_ms * 1e-3) / 1e12, "unit": "Tinstr/s",
+                                    "peak": fma_rate.value / 1e12,
+                                    "frac": fpp * pts_per_launch / (k_ms * 1e-3) / fma_rate.value,
+                                    "peak_source": "DFMA microbenchmark measured live in this run (64 lanes/clk/SM)",
+                                    "ncu_pipe_fp64_pct": k0.get("pipe_fp64_pct"),
+                                    "model_instr_per_point": instr_model,
+                                    "model_note": "analytic count of the FP64 operations in the source (stages, hats, "
+                                                  "Horner steps, terms); ptxas executes fewer: level-1 terms of a pole "
+                                                  "are plain loads and common sub-expressions of the two points' hats "
+                                                  "are shared -- the measured count is the one used"}
             pipes = {"issue_slots": k0.get("issue_slots_busy_pct"), "smem_lsu_wavefronts": k0.get("smem_wavefronts_pct"),
                      "alu": k0.get("pipe_alu_pct"), "fma_int": k0.get("pipe_fma_pct"), "fp64": k0.get("pipe_fp64_pct"),
                      "lsu": k0.get("pipe_lsu_pct"), "dram": k0.get("dram_throughput_pct")}
             pipes = {k: v for k, v in pipes.items() if v is not None}
             roofline["ncu_pipe_utilisation_pct"] = pipes
             roofline["ncu_binding_pipe"] = max(pipes, key=pipes.get) if pipes else None
-            roofline["ncu_kernel"] = k0.get("kernel")
-        except Exception:
-            pass
+            break
+        except Exception as ex:  # a malformed summary must not kill the bench line
+            roofline["counts_error"] = repr(ex)
+    if roofline["frac"] is None:  # no capture of this kernel in profiles/: fall back to the HBM figure
+        roofline.update({"bound": "hbm", "achieved": roofline["hbm"]["achieved"], "peak": hbm_peak,
+                         "frac": roofline["hbm"]["frac"], "note": "no ncu capture for this kernel: algorithmic HBM bytes"})
 
     cpu = None
     if world == 1 and not args.no_cpu:
         rate, cores, n, sec, ycpu, Xcpu = cpu_reference_rate(G, seconds_target=15.0)
         ygpu = G.evaluate(Xcpu)
+        # parity of the benchmarked configuration against the long-double oracle (src/class.jl:629-643), ASSERTED with
+        # the tolerance of the north star: 1e-12 relative or 1e-14 * max(1, sum |c phi|) absolute
+        from oracle import oracle as o
+        OG = o.OracleGrid(D)
+        OG.levels, OG.indices, OG.depths, OG.coefs, OG.fvals = G.levels, G.indices, G.depths, G.coefs, G.fvals
+        ns = min(len(Xcpu), 1000)
+        want, sc = OG.evaluate(Xcpu[:ns], return_abssum=True)
+        err = np.abs(ygpu[:ns] - want)
+        okp = (err <= 1e-12 * np.abs(want)) | (err <= 1e-14 * np.maximum(1.0, sc))
+        if not np.all(okp):
+            raise SystemExit(f"PARITY FAILURE on the benchmarked grid: {np.count_nonzero(~okp)} of {ns} points out of "
+                             f"tolerance, worst error {float(err.max()):.3e}")
         cpu = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
                "sample": f"{n} of {M_total} points in {sec:.1f} s, restated reference algorithm "
-                         "(src/class.jl:635-642), OpenMP over points",
-               "max_abs_diff_vs_gpu": float(np.max(np.abs(ygpu - ycpu)))}
+                         "(src/class.jl:635-642), -O2 OpenMP over points (generous to the reference: Julia's broadcast "
+                         "also allocates N doubles per point)",
+               "max_abs_diff_vs_gpu": float(np.max(np.abs(ygpu - ycpu))),
+               "parity_vs_long_double_oracle": {"points": int(ns), "max_abs_err": float(err.max()),
+                                                "tolerance": "1e-12 rel | 1e-14 * max(1, sum|c*phi|) abs", "asserted": True}}
 
     line = {
         "metric": "interpolant evaluations per second", "value": value, "unit": "points/s", "n_gpus": world,
@@ -451,7 +512,8 @@ def main():
                    "host_cores_bound_to_gpu_numa_node": numa,
                    "l2": "inputs larger than L2 (80 B/point * points_per_gpu >> 126 MB), no flush needed",
                    "engine": ("subspace/block" if block else "subspace/stream") if info["path"] == 2 else "sweep",
-                   "point_order": "cell-key sorted inside the timed region (asg_sort.cu)" if block else "as given"},
+                   "point_order": "cell-key sorted inside the timed region (asg_sort.cu)" if block else "as given",
+                   "timed_region": "point ordering + walk" + (" + all-gather of the result shards (C2)" if world > 1 else "")},
         "products_per_s": value * N,
         "gpu_launches": int(launches),
         "clocks": clocks,

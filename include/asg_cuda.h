@@ -82,6 +82,16 @@ typedef struct asg_grid_info_t {
 /* Select the CUDA device this process uses (one process per GPU). Fails with ASG_ENODEVICE when
  * the device is absent or is not compute capability 10.x. Idempotent. */
 int32_t asg_init(int32_t device);
+/* Select SEVERAL devices of one box for this process (the reference's only parallel entry is
+ * adapt!(...; parallel = true), src/train.jl:332-340): every grid handle then keeps one replica of its packed
+ * layouts per device (packed once on the host, uploaded to each), and the host-buffer entry points -- asg_eval,
+ * asg_surplus, asg_surplus_nodes -- split their points into contiguous ranges over the devices, one host thread and
+ * one copy/compute pipeline per device, results written straight into the caller's buffer. No collective, no NCCL,
+ * no torch. devices[0] is the primary device (basis, children, node coordinates run there). The device-pointer
+ * entry points run on whichever device of the list owns the pointers. asg_init(d) == asg_init_devices(&d, 1). */
+int32_t asg_init_devices(const int32_t *devices, int32_t ndev);
+/* the device list of the context (ndev = 0 before asg_init*) */
+int32_t asg_context_devices(int32_t *devices, int32_t capacity, int32_t *ndev);
 int32_t asg_shutdown(void);
 int32_t asg_device_count(int32_t *count);
 const char *asg_last_error(void);
@@ -114,6 +124,14 @@ int32_t asg_grid_scatter_coefs(asg_grid *g, int64_t n, const int64_t *idx, const
 int32_t asg_grid_get_coefs(asg_grid *g, int64_t first, int64_t n, double *coefs);
 int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info);
 int32_t asg_grid_set_path(asg_grid *g, int32_t path); /* force an engine (tests); AUTO restores */
+
+/* ---- the basis function itself: phi(x), phi(x, l, i), phi(x, levels, indices) (src/math.jl:332-334, 345-357,
+ *      376-391; exported by the reference, math.jl:13) ------------------------------------------------------------
+ * out[k] = prod_{d < D} phi(x01[k*D + d]; levels[k*D + d], indices[k*D + d]) for k < n, a left fold like Julia's
+ * prod; x01 in UNIT-CUBE coordinates as in the reference (no scale()). D = 1 is the scalar form. levels == indices
+ * == NULL: the plain hat phi(x) = 1 - |x| on [-1, 1]. Same operations in the same order as the reference (mul, sub,
+ * 1 - |t|, never fused): bit-identical values. ASG_EINVALID_NODE where the reference throws (math.jl:355). */
+int32_t asg_phi(int64_t n, int32_t D, const double *x01, const int64_t *levels, const int64_t *indices, double *out);
 
 /* ---- evaluation: _interpolate / _interpolate_if / _interpolate_until_level / G(x)
  *      (src/class.jl:629-643, 645-664, 666-680, 747-761) ----------------------------------- */
@@ -159,6 +177,11 @@ int32_t asg_nodes_x_li(asg_grid *g, int64_t n, const int64_t *levels, const int6
  * ASG_EINVAL: not a blob / checksum mismatch / other dimension or domain. */
 int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes);
 int32_t asg_grid_import(asg_grid *g, const void *buf, int64_t bytes);
+/* deserialize (src/io.jl:49-72) with a blob next to the Dict: install the blob only if it describes exactly the node
+ * arrays of the Dict (levels, indices bit for bit; coefs bit for bit when given) -- serialize aliases the arrays, so an
+ * in-place update after the blob was written leaves it stale. ASG_ESTATE on mismatch: fall back to asg_grid_upload. */
+int32_t asg_grid_import_checked(asg_grid *g, const void *buf, int64_t bytes, int64_t N, const int64_t *levels,
+                                const int64_t *indices, int64_t sn, int64_t sd, const double *coefs);
 
 /* ---- rsg! node enumeration (src/train.jl:40-78), host code, no device needed: the regular sparse grid node set
  * {l : l_d <= maxlevels_d, sum(l_d - 1) <= maxdepth - 1} in the reference's order (level vectors and index tuples in

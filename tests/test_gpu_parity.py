@@ -290,6 +290,22 @@ def test_noncanonical_falls_back_to_sweep(asg, oracle):
     g = G2.evaluate(X2)
     assert np.array_equal(np.isnan(g), np.isnan(w)) and np.any(np.isnan(w))
     assert G2.info()["path"] == 1
+    # the same on a D = 3 grid, which has a BLOCK layout whose self-check must not see the non-finite sums; the
+    # grid must also survive append (adapt!) and the packed round trip (round-1 advisor finding)
+    for bad in (np.inf, np.nan):
+        OG3 = oracle.OracleGrid(3)
+        OG3.train(sinsum, 5, 5)
+        OG3.coefs[3] = bad
+        G3 = _mirror(asg, OG3)
+        X3 = rng.random((256, 3))
+        w3 = OG3.evaluate(X3)
+        g3 = G3.evaluate(X3)
+        assert G3.info()["path"] == 1
+        assert np.array_equal(np.isnan(g3), np.isnan(w3)) and np.any(np.isnan(w3))
+        ok = ~np.isnan(w3)
+        assert_close(g3[ok], w3[ok], None, "finite part next to a non-finite coefficient")
+        H3 = asg.deserialize(asg.serialize(G3, packed=True))
+        assert np.array_equal(H3.evaluate(X3), g3, equal_nan=True)
 
 
 def test_invalid_nodes_rejected(asg):
@@ -658,3 +674,64 @@ def test_basis_csc_on_device(asg, cfg1, cfg2, cfg_nonunit):
     assert E.format == "csc" and np.all(E.diagonal() == 1.0)
     Z = asg.basis(np.full((3, 3), 7.5), _mirror(asg, cfg1))   # points outside the domain: empty matrix
     assert Z.nnz == 0 and Z.shape == (3, len(cfg1.levels))
+
+
+def test_phi_exports(asg, oracle):
+    """a4 and the scalar forms: phi(x), phi(x, l, i), phi(x, levels, indices) (src/math.jl:332-391) on the device,
+    bit-identical to the oracle's restatement; invalid pairs raise like the reference (src/math.jl:355)."""
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.random(200) * 1.4 - 0.2, [0.0, 0.5, 1.0, -0.0, 0.25, 0.75, np.nan, np.inf, -np.inf, 1.0 + 1e-16]])
+    t = np.concatenate([rng.random(100) * 3 - 1.5, [-1.0, 1.0, 0.0, np.nan]])
+    assert np.array_equal(asg.phi(t), np.array([oracle.phi(v) for v in t]), equal_nan=True)
+    assert asg.phi(0.25) == 0.75
+    pairs = [(1, 1), (1, 7), (2, 0), (2, 2), (3, 1), (3, 3), (4, 5), (7, 33), (12, 1001), (5, 4), (30, 12345677)]
+    for l, i in pairs:
+        got = asg.phi(xs.reshape(-1, 1), np.full((len(xs), 1), l), np.full((len(xs), 1), i))
+        want = np.array([oracle.phi(v, l, i) for v in xs])
+        assert np.array_equal(got, want, equal_nan=True), (l, i)
+        assert asg.phi(0.3, l, i) == oracle.phi(0.3, l, i)
+    for l, i in [(0, 1), (2, 1), (-1, 0), (2, 3)]:
+        with pytest.raises(ValueError):
+            asg.phi(0.5, l, i)
+        with pytest.raises(oracle.ArgumentError):
+            oracle.phi(0.5, l, i)
+    # vector form: one node, D dimensions, left fold; equals one entry of the basis matrix
+    OG = oracle.OracleGrid(5)
+    OG.rsg(5, 4)
+    G = _mirror(asg, OG)
+    X = rng.random((40, 5))
+    B = OG.basis(X, dropzeros=False, atol=0.0)
+    nodes = rng.choice(len(OG), size=40, replace=False)
+    got = asg.phi(X, OG.levels[nodes], OG.indices[nodes])
+    assert np.array_equal(got, B[np.arange(40), nodes])
+    assert asg.phi(X[0], OG.levels[nodes[0]], OG.indices[nodes[0]], safe=True) == B[0, nodes[0]]
+    with pytest.raises(AssertionError):
+        asg.phi(X[0], OG.levels[0][:4], OG.indices[0][:4], safe=True)
+
+
+def test_deserialize_ignores_stale_blob(asg, oracle, cfg1):
+    """serialize() aliases the arrays (src/io.jl:30-38): a blob written before an in-place coefficient update, or a
+    blob of another grid of the same shape, must not be installed (round-1 advisor finding)."""
+    G = _mirror(asg, cfg1)
+    dat = asg.serialize(G, packed=True)
+    X = np.random.default_rng(3).random((500, 3))
+    y0 = G.evaluate(X)
+    dat["coefs"][:] = 2.0 * dat["coefs"]              # in-place update after the blob was written
+    H = asg.deserialize(dat)
+    assert np.array_equal(H.evaluate(X), 2.0 * y0)    # exact: scaling by a power of two
+    # foreign blob: same D, domain and node count, other coefficients
+    G2 = _mirror(asg, cfg1)
+    G2.coefs = -cfg1.coefs
+    dat2 = asg.serialize(G2)
+    dat2["packed"] = asg.serialize(_mirror(asg, cfg1), packed=True)["packed"]
+    assert np.array_equal(asg.deserialize(dat2).evaluate(X), -y0)   # exact: every term changes sign
+    # a matching blob is still taken
+    dat3 = asg.serialize(_mirror(asg, cfg1), packed=True)
+    H3 = asg.deserialize(dat3)
+    assert H3._dirty is False and np.array_equal(H3.evaluate(X), y0)
+
+
+def test_extrapolate_empty_grid_asserts(asg):
+    G = asg.SparseGridInterpolant(2)
+    with pytest.raises(AssertionError):
+        asg.extrapolate(G, np.array([[1.5, 0.5]]))
