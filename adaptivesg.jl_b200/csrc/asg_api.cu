@@ -130,6 +130,7 @@ struct Replica {
   // point-order scratch of the BLOCK walk (asg_sort.cu), one set per pipeline slot
   DevBuf<uint32_t> s_key[kPipeSlots], s_key2[kPipeSlots], s_idx[kPipeSlots], s_perm[kPipeSlots];
   DevBuf<unsigned char> s_sorttmp[kPipeSlots];
+  DevBuf<uint32_t> s_left[kPipeSlots], s_leftcnt[kPipeSlots];  // PAIR mode of the BLOCK walk: points left to the follow-up launch
   cudaEvent_t sort_ev[kPipeSlots] = {};  // last use of the slot's scratch
   void release_all() {
     d_rec.release(); d_grp.release(); d_tiles.release(); d_bcoef.release(); d_brec.release(); d_btiles.release();
@@ -138,6 +139,7 @@ struct Replica {
     for (int s = 0; s < kPipeSlots; ++s) {
       s_X[s].release(); s_out[s].release(); s_f[s].release();
       s_key[s].release(); s_key2[s].release(); s_idx[s].release(); s_perm[s].release(); s_sorttmp[s].release();
+      s_left[s].release(); s_leftcnt[s].release();
       if (sort_ev[s]) cudaEventDestroy(sort_ev[s]);
       sort_ev[s] = nullptr;
     }
@@ -287,6 +289,7 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
       dg.n_btiles = (uint32_t)pk.btiles.size();
       dg.blk_slots = pk.blk_slots;
       dg.blk_tile_coefs = pk.blk_tile_coefs;
+      dg.blk_pair_ok = pk.blk_pair_ok ? 1 : 0;
     }
   }
   CK(cudaStreamSynchronize(st));
@@ -419,8 +422,15 @@ int run_eval(asg_grid *g, int r, const EvalArgs &a_in, cudaStream_t st, int slot
         sorted = true;
       }
     }
+    uint32_t *left = nullptr, *leftcnt = nullptr;
+    if (sorted && block_pair_mode(R.dg, a.M, true)) {
+      if (int rc = R.s_left[slot].reserve((size_t)a.M / 2 + 2)) return rc;
+      if (int rc = R.s_leftcnt[slot].reserve(4)) return rc;
+      left = R.s_left[slot].p;
+      leftcnt = R.s_leftcnt[slot].p;
+    }
     if (timed) CK(cudaEventRecord(dc.evw0, st));
-    e = launch_eval_block(R.dg, a, st, &l);
+    e = launch_eval_block(R.dg, a, st, &l, left, leftcnt);
     if (timed) { CK(cudaEventRecord(dc.evw1, st)); dc.walk_timed = true; }
     if (sorted && e == cudaSuccess) CK(cudaEventRecord(R.sort_ev[slot], st));
   }

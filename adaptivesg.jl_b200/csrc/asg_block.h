@@ -103,6 +103,13 @@ static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words"
 ASG_HD constexpr uint32_t blk_code(int S, int r) { return (uint32_t)(8 * S + r); }
 constexpr uint32_t kBrNone = 255u;  // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
+// PAIR mode of the walk (asg_kernels_block.cuh): two neighbours of the cell-key order share the cell of every level
+// <= kBlkPairLevel in every dimension. A record whose prefix stages all have such levels is flagged kBrShared: the
+// pair has ONE prefix position, so its chunk is read through one address. A grid takes PAIR mode when every other
+// record leaves a suffix budget <= kBlkPairMaxR (always true while budgets are <= 7: a level above 4 spends >= 4).
+constexpr int kBlkPairLevel = 4;
+constexpr int kBlkPairMaxR = 3;
+constexpr uint32_t kBrShared = 1u << 9;
 constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2: including dimension A): depth mask
 
 struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)

@@ -105,6 +105,7 @@ struct DeviceGrid {
   uint32_t n_brec, n_btiles;
   int blk_slots;                    // saved prefix slots the walk needs (<= kBlkMaxSlots)
   int blk_tile_coefs;               // doubles per coefficient tile buffer (chosen by the packer)
+  int blk_pair_ok;                  // the record set admits PAIR mode (asg_block.h)
   // sweep engine (caller's node order)
   int64_t N;
   const SweepDim *sw;       // [N][D]
@@ -151,6 +152,7 @@ struct PackResult {
   std::vector<int64_t> bslot_of_node;
   int blk_slots = 0;
   int blk_tile_coefs = 0;             // coefficient tile size the tiles were cut for
+  bool blk_pair_ok = false;           // every record without kBrShared has a budget <= kBlkPairMaxR
   // sweep engine
   std::vector<SweepDim> sw;
   std::vector<uint64_t> sw_low;
@@ -206,6 +208,11 @@ struct EvalArgs {
   const double *fvals; // optional: out = fvals - G
   double *out;
   const uint32_t *perm = nullptr;  // optional: thread j handles point perm[j] (points pre-sorted by cell key)
+  // PAIR mode of the BLOCK walk: second points of pairs that do not share a cell go to this list (original point
+  // numbers); a follow-up launch evaluates them with perm = left_list and its point count read from M_dev
+  uint32_t *left_list = nullptr;
+  uint32_t *left_count = nullptr;
+  const uint32_t *M_dev = nullptr;
 };
 struct BasisArgs {
   const double *X;
@@ -223,7 +230,10 @@ struct BasisArgs {
 
 cudaError_t launch_eval_subspace(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_stream(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
-cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
+// left_list (capacity M / 2 + 1) / left_count: scratch of PAIR mode, may be null (then PAIR mode is not used)
+cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches,
+                              uint32_t *left_list = nullptr, uint32_t *left_count = nullptr);
+bool block_pair_mode(const DeviceGrid &g, int64_t M, bool sorted);  // would launch_eval_block pair the points?
 bool block_kernel_fits(const DeviceGrid &g);  // shared memory of the BLOCK walk fits an SM for this grid
 // shared memory (bytes) of the BLOCK walk: R points per thread, `threads` threads, D dimensions, stack slots, tile size
 size_t block_smem_bytes(int D, int slots, int tile_coefs, int R, int threads);

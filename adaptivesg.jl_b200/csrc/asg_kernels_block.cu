@@ -1,5 +1,7 @@
 // asg_kernels_block.cu -- host side of the BLOCK walk (kernel: asg_kernels_block.cuh): shared-memory sizing, choice of
 // the variant (one / two points per thread, depth mask), launch.
+#include <cmath>
+
 #include "asg_kernels_block.cuh"
 
 namespace asg {
@@ -26,33 +28,71 @@ static int blk_threads() { return kBlkThreads; }
 
 bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_bytes(g, 1, blk_threads()) <= 227 * 1024; }
 
-extern template cudaError_t blk_launch<1, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<1, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, false, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, true, kBlkThreads>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<1, false, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<1, true, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, false, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, true, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, false, kBlkThreads, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+extern template cudaError_t blk_launch<2, true, kBlkThreads, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
 
 template <int NT>
-static cudaError_t blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, int blocks, size_t smem,
+static cudaError_t blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, bool pair, int blocks, size_t smem,
                                  cudaStream_t st) {
-  if (two) return masked ? blk_launch<2, true, NT>(g, a, blocks, smem, st) : blk_launch<2, false, NT>(g, a, blocks, smem, st);
-  return masked ? blk_launch<1, true, NT>(g, a, blocks, smem, st) : blk_launch<1, false, NT>(g, a, blocks, smem, st);
+  if (two && pair) return masked ? blk_launch<2, true, NT, true>(g, a, blocks, smem, st) : blk_launch<2, false, NT, true>(g, a, blocks, smem, st);
+  if (two) return masked ? blk_launch<2, true, NT, false>(g, a, blocks, smem, st) : blk_launch<2, false, NT, false>(g, a, blocks, smem, st);
+  return masked ? blk_launch<1, true, NT, false>(g, a, blocks, smem, st) : blk_launch<1, false, NT, false>(g, a, blocks, smem, st);
 }
 
-cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches) {
+// PAIR mode pays when most neighbours of the cell-key order share their 2-bit cells: about eight points per cell
+// (4^D cells) leave ~6 % of the points to the follow-up launch. ASG_BLOCK_PAIR=0 disables it, =<n> sets the
+// minimum number of points per cell.
+static double pair_min_per_cell() {  // read per call: the tests switch it between evaluations
+  const char *e = getenv("ASG_BLOCK_PAIR");
+  return e ? atof(e) : 8.0;
+}
+bool block_pair_mode(const DeviceGrid &g, int64_t M, bool sorted) {
+  if (!sorted || !g.blk_pair_ok || g.D > 15 || pair_min_per_cell() <= 0.0) return false;
+  if (M <= (int64_t)blk_sm_count() * blk_threads() || blk_smem_bytes(g, 2, blk_threads()) > 227 * 1024) return false;
+  return (double)M >= pair_min_per_cell() * std::ldexp(1.0, 2 * g.D);
+}
+
+cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a_in, cudaStream_t st, int64_t *launches,
+                              uint32_t *left_list, uint32_t *left_count) {
+  EvalArgs a = a_in;
   if (a.M <= 0) return cudaSuccess;
   const int sms = blk_sm_count();
   const int nt = blk_threads();
   // two points per thread as soon as one-point CTAs would need a second wave (and the shared memory fits)
   bool two = a.M > (int64_t)sms * nt && blk_smem_bytes(g, 2, nt) <= 227 * 1024;
   if (const char *e = getenv("ASG_BLOCK_R")) two = (e[0] == '2') && blk_smem_bytes(g, 2, nt) <= 227 * 1024;  // experiment knob
+  const bool pair = two && left_list && left_count && block_pair_mode(g, a.M, a.perm != nullptr);
   const int R = two ? 2 : 1;
   const size_t smem = blk_smem_bytes(g, R, nt);
   const int64_t per_block = (int64_t)nt * R;
   const int64_t need = (a.M + per_block - 1) / per_block;
   const int blocks = (int)(need < sms ? need : sms);
   const bool masked = a.rem < INT_MAX / 4;
-  const cudaError_t e = blk_launch_nt<kBlkThreads>(g, a, two, masked, blocks, smem, st);
+  if (pair) {
+    cudaError_t e = cudaMemsetAsync(left_count, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    a.left_list = left_list;
+    a.left_count = left_count;
+  }
+  cudaError_t e = blk_launch_nt<kBlkThreads>(g, a, two, masked, pair, blocks, smem, st);
   if (e != cudaSuccess) return e;  // the shared-memory limit of the kernel could not be raised
+  if (launches) ++*launches;
+  e = cudaGetLastError();
+  if (e != cudaSuccess || !pair) return e;
+  // follow-up: the second points of the pairs that straddle a cell boundary, one point per thread; their number is
+  // only known on the device, so the launch covers the worst case and surplus CTAs leave at once
+  EvalArgs b = a_in;
+  b.perm = left_list;
+  b.M_dev = left_count;
+  b.M = a.M / 2 + 1;
+  const size_t smem1 = blk_smem_bytes(g, 1, nt);
+  const int64_t need1 = (b.M + nt - 1) / nt;
+  e = blk_launch_nt<kBlkThreads>(g, b, false, masked, false, (int)(need1 < sms ? need1 : sms), smem1, st);
+  if (e != cudaSuccess) return e;
   if (launches) ++*launches;
   return cudaGetLastError();
 }

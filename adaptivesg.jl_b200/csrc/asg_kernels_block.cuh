@@ -26,6 +26,12 @@ namespace asg {
 
 constexpr int kBlkThreads = 512;  // default CTA size (384 threads x 168 registers was measured 6 % slower)
 constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulated in registers
+// PAIR mode (two points per thread, large ordered batches): the two points of a thread are NEIGHBOURS in the cell-key
+// order and share the cell of every level <= kBlkTab in EVERY dimension (checked per thread; the second point of a pair
+// that does not is evaluated by a follow-up launch). Wherever all levels on the path to a coefficient are <= kBlkTab
+// the two points read the SAME coefficient: one address, one LDS.64, two DFMA ("SH" below). 16 588 of the 19 448
+// terms of the D = 10 benchmark grid are of that kind.
+static_assert(kBlkTab == kBlkPairLevel, "the packer flags shared records with the level the tables cover");
 
 struct __align__(16) BlkSmem {
   BlockRec rec[2][kBlkTileRecs];
@@ -35,21 +41,22 @@ struct __align__(16) BlkSmem {
   //              double Ps[slots][R][threads], uint32_t Os[slots][R][threads]  (saved prefixes)
 };
 
-template <int R>
+template <int R, bool PAIR>
 struct BlkPoint {
-  double phC[R][kBlkTab + 1];    // last dimension: hat of level l
-  uint32_t wC8[R][kBlkTab + 1];  // last dimension: (off1(l) + cell_l) * 8
-  double phB[R][kBlkTab + 1];    // dimension D-2: hat of level l
-  uint32_t cB[R][kBlkTab + 1];   // dimension D-2: cell of level l
-  double xA[R];                  // unit-cube coordinate of dimension D-3 (its hats are formed on the fly)
-  uint32_t qA[R];                // and its 30-bit cell key
-  uint32_t xsBC;                 // shared byte address of this thread's coordinate of dimension D-2 (point 0)
+  static constexpr int RC = PAIR ? 1 : R;  // copies of the cell tables: the points of a pair share them
+  double phC[R][kBlkTab + 1];     // last dimension: hat of level l
+  uint32_t wC8[RC][kBlkTab + 1];  // last dimension: (off1(l) + cell_l) * 8
+  double phB[R][kBlkTab + 1];     // dimension D-2: hat of level l
+  uint32_t cB[RC][kBlkTab + 1];   // dimension D-2: cell of level l
+  double xA[R];                   // unit-cube coordinate of dimension D-3 (its hats are formed on the fly)
+  uint32_t qA[R];                 // and its 30-bit cell key
+  uint32_t xsBC;                  // shared byte address of this thread's coordinate of dimension D-2 (point 0)
 };
 
 // coordinate of dimension D-2+which (which = 0, 1: B, C at rare levels; which < 0: dimensions above A of the
 // deeper compiled suffixes) of point k, from shared memory
-template <int R>
-__device__ __forceinline__ double blk_x_rare(const BlkPoint<R> &pt, int which, int k) {
+template <int R, bool PAIR>
+__device__ __forceinline__ double blk_x_rare(const BlkPoint<R, PAIR> &pt, int which, int k) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (kBlkThreads * 8))));
   return v;
@@ -82,112 +89,158 @@ __device__ __forceinline__ void hat_ct(double x, uint32_t q, double &ph, uint32_
 
 // the same from the coordinate alone (dimensions whose key is not kept in a register)
 template <int L>
-__device__ __forceinline__ void hat_ct_x(double x, double &ph, uint32_t &cell) {
+__device__ __forceinline__ uint32_t cell_ct_x(double x) {
   constexpr int b = blk_bits(L);
-  cell = min((uint32_t)(x * (double)(1u << b)), (1u << b) - 1u);  // floor(x*2^b), clamped for x == 1 (exact)
+  return min((uint32_t)(x * (double)(1u << b)), (1u << b) - 1u);  // floor(x*2^b), clamped for x == 1 (exact)
+}
+template <int L>
+__device__ __forceinline__ void hat_ct_x(double x, double &ph, uint32_t &cell) {
+  cell = cell_ct_x<L>(x);
   const uint32_t i = (cell << 1) + (L > 2 ? 1u : 0u);
   const double t = fma(x, (double)(1u << (L - 1)), -u32_to_f64(i));
   ph = 1.0 - fabs(t);
 }
+// hat of level L at x when the cell is known (a pair's common cell): fi = (double)(2*cell + [L > 2])
+template <int L>
+__device__ __forceinline__ double hat_ct_cell(double x, double fi) {
+  return 1.0 - fabs(fma(x, (double)(1u << (L - 1)), -fi));
+}
 
-template <int L, int R>
-__device__ __forceinline__ void get_C(const BlkPoint<R> &pt, int k, double &ph, uint32_t &w8) {
+template <int L, int R, bool PAIR>
+__device__ __forceinline__ void get_C(const BlkPoint<R, PAIR> &pt, int k, double &ph, uint32_t &w8) {
   if constexpr (L <= kBlkTab) {
     ph = pt.phC[k][L];
-    w8 = pt.wC8[k][L];
+    w8 = pt.wC8[PAIR ? 0 : k][L];
   } else {
     uint32_t cell;
-    hat_ct_x<L>(blk_x_rare<R>(pt, 1, k), ph, cell);
+    hat_ct_x<L>(blk_x_rare<R, PAIR>(pt, 1, k), ph, cell);
     w8 = (blk_off1(L) + cell) * 8u;
   }
 }
-template <int L, int R>
-__device__ __forceinline__ void get_B(const BlkPoint<R> &pt, int k, double &ph, uint32_t &cell) {
+template <int L, int R, bool PAIR>
+__device__ __forceinline__ void get_B(const BlkPoint<R, PAIR> &pt, int k, double &ph, uint32_t &cell) {
   if constexpr (L <= kBlkTab) {
     ph = pt.phB[k][L];
-    cell = pt.cB[k][L];
+    cell = pt.cB[PAIR ? 0 : k][L];
   } else {
-    hat_ct_x<L>(blk_x_rare<R>(pt, 0, k), ph, cell);
+    hat_ct_x<L>(blk_x_rare<R, PAIR>(pt, 0, k), ph, cell);
   }
 }
 
 // ---- compiled suffix walk ---------------------------------------------------------------------------
+// SH (PAIR mode only): every level on the path so far is <= kBlkTab, so the R points share the address: only
+// element [0] of an address array is meaningful and one load serves all points.
 // pole: levels 1..RP+1 of the last dimension at shared byte address tp[k] + IMM
-template <int RP, int LC, int IMM, int R, bool MASKED>
-__device__ __forceinline__ void blk_pole(const BlkPoint<R> &pt, const uint32_t (&tp)[R], int reff, double (&inner)[R]) {
+template <int RP, int LC, int IMM, int R, bool MASKED, bool PAIR, bool SH>
+__device__ __forceinline__ void blk_pole(const BlkPoint<R, PAIR> &pt, const uint32_t (&tp)[R], int reff, double (&inner)[R]) {
   if constexpr (LC <= RP + 1) {
     if (MASKED && LC - 1 > reff) return;
+    if constexpr (SH && LC <= kBlkTab) {
+      const double c = lds_f64_imm<IMM>(tp[0] + pt.wC8[0][LC]);
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      double ph;
-      uint32_t w8;
-      get_C<LC, R>(pt, k, ph, w8);
-      const double c = lds_f64_imm<IMM>(tp[k] + w8);
-      inner[k] = fma(c, ph, inner[k]);
+      for (int k = 0; k < R; ++k) inner[k] = fma(c, pt.phC[k][LC], inner[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        double ph;
+        uint32_t w8;
+        get_C<LC, R, PAIR>(pt, k, ph, w8);
+        const double c = lds_f64_imm<IMM>(tp[SH ? 0 : k] + w8);
+        inner[k] = fma(c, ph, inner[k]);
+      }
     }
-    blk_pole<RP, LC + 1, IMM, R, MASKED>(pt, tp, reff, inner);
+    blk_pole<RP, LC + 1, IMM, R, MASKED, PAIR, SH>(pt, tp, reff, inner);
   }
 }
 
 // 2-D block of storage budget RB at shared byte address t2[k] + IMM: levels LB.. of dimension B (Horner form:
 // one DFMA per pole, none for level 1)
-template <int RB, int LB, int IMM, int R, bool MASKED>
-__device__ __forceinline__ void blk_suffix2(const BlkPoint<R> &pt, const uint32_t (&t2)[R], int reff, double (&accA)[R]) {
+template <int RB, int LB, int IMM, int R, bool MASKED, bool PAIR, bool SH>
+__device__ __forceinline__ void blk_suffix2(const BlkPoint<R, PAIR> &pt, const uint32_t (&t2)[R], int reff, double (&accA)[R]) {
   if constexpr (LB <= RB + 1) {
     if (MASKED && LB - 1 > reff) return;
     constexpr int RP = RB - (LB - 1);
     constexpr int IMM2 = IMM + (int)blk_offB(LB, RB) * 8;
+    constexpr bool SHN = SH && LB <= kBlkTab;  // the pole's address is still common to the points
     uint32_t tp[R];
     double phB[R], inner[R];
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
+    if constexpr (SHN) {
       if constexpr (LB == 1) {
-        tp[k] = t2[k];
+        tp[0] = t2[0];
       } else {
-        uint32_t cell;
-        get_B<(LB > 1 ? LB : 2), R>(pt, k, phB[k], cell);
-        tp[k] = t2[k] + cell * (blk_n1(RP) * 8u);
+        tp[0] = t2[0] + pt.cB[0][LB] * (blk_n1(RP) * 8u);
+#pragma unroll
+        for (int k = 0; k < R; ++k) phB[k] = pt.phB[k][LB];
       }
-      inner[k] = lds_f64_imm<IMM2>(tp[k]);  // level 1 of the last dimension: phi = 1, cell = 0
+      const double c = lds_f64_imm<IMM2>(tp[0]);  // level 1 of the last dimension: phi = 1, cell = 0
+#pragma unroll
+      for (int k = 0; k < R; ++k) inner[k] = c;
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if constexpr (LB == 1) {
+          tp[k] = t2[k];
+        } else {
+          uint32_t cell;
+          get_B<(LB > 1 ? LB : 2), R, PAIR>(pt, k, phB[k], cell);
+          tp[k] = t2[SH ? 0 : k] + cell * (blk_n1(RP) * 8u);
+        }
+        inner[k] = lds_f64_imm<IMM2>(tp[k]);  // level 1 of the last dimension: phi = 1, cell = 0
+      }
     }
-    blk_pole<RP, 2, IMM2, R, MASKED>(pt, tp, reff - (LB - 1), inner);
+    blk_pole<RP, 2, IMM2, R, MASKED, PAIR, SHN>(pt, tp, reff - (LB - 1), inner);
 #pragma unroll
     for (int k = 0; k < R; ++k) accA[k] = LB == 1 ? inner[k] : fma(phB[k], inner[k], accA[k]);
-    blk_suffix2<RB, LB + 1, IMM, R, MASKED>(pt, t2, reff, accA);
+    blk_suffix2<RB, LB + 1, IMM, R, MASKED, PAIR, SH>(pt, t2, reff, accA);
   }
 }
 
 // compiled suffix of S >= 3 dimensions (D-S .. D-1) of storage budget RS at shared byte address t[k] + IMM:
 // levels L.. of dimension D-S. S = 3: that dimension is A (coordinate and key in registers); S > 3: its
 // coordinate comes from shared memory (those records are few and small, see blk_max_r).
-template <int S, int RS, int L, int IMM, int R, bool MASKED>
-__device__ __forceinline__ void blk_suffixN(const BlkPoint<R> &pt, const uint32_t (&t)[R], int reff, double (&out)[R]) {
+template <int S, int RS, int L, int IMM, int R, bool MASKED, bool PAIR, bool SH>
+__device__ __forceinline__ void blk_suffixN(const BlkPoint<R, PAIR> &pt, const uint32_t (&t)[R], int reff, double (&out)[R]) {
   if constexpr (L <= RS + 1) {
     if (MASKED && L - 1 > reff) return;
     constexpr int RB = RS - (L - 1);
     constexpr int IMM2 = IMM + (int)blk_off(S, L, RS) * 8;
+    constexpr bool SHN = SH && L <= kBlkTab;
+    constexpr int LL = L > 1 ? L : 2;
     uint32_t t2[R];
     double ph[R], sub[R];
+    if constexpr (L == 1) {
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      if constexpr (L == 1) {
-        t2[k] = t[k];
-      } else {
+      for (int k = 0; k < R; ++k) t2[k] = t[k];
+    } else if constexpr (SHN) {
+      // the points' common cell comes from point 0; each point forms its own hat on it
+      uint32_t cell;
+      double x[R];
+#pragma unroll
+      for (int k = 0; k < R; ++k) x[k] = S == 3 ? pt.xA[k] : blk_x_rare<R, PAIR>(pt, 2 - S, k);
+      if constexpr (S == 3) cell = pt.qA[0] >> (kKeyBits - blk_bits(LL));
+      else cell = cell_ct_x<LL>(x[0]);
+      const double fi = u32_to_f64((cell << 1) + (LL > 2 ? 1u : 0u));
+#pragma unroll
+      for (int k = 0; k < R; ++k) ph[k] = hat_ct_cell<LL>(x[k], fi);
+      t2[0] = t[0] + cell * (blk_size(S - 1, RB) * 8u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
         uint32_t cell;
         if constexpr (S == 3) {
-          hat_ct<(L > 1 ? L : 2)>(pt.xA[k], pt.qA[k], ph[k], cell);
+          hat_ct<LL>(pt.xA[k], pt.qA[k], ph[k], cell);
         } else {
           // dimension D-S is S-2 rows above dimension D-2 in xs
-          hat_ct_x<(L > 1 ? L : 2)>(blk_x_rare<R>(pt, 2 - S, k), ph[k], cell);
+          hat_ct_x<LL>(blk_x_rare<R, PAIR>(pt, 2 - S, k), ph[k], cell);
         }
-        t2[k] = t[k] + cell * (blk_size(S - 1, RB) * 8u);
+        t2[k] = t[SH ? 0 : k] + cell * (blk_size(S - 1, RB) * 8u);
       }
     }
-    if constexpr (S == 3) blk_suffix2<RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
-    else blk_suffixN<S - 1, RB, 1, IMM2, R, MASKED>(pt, t2, reff - (L - 1), sub);
+    if constexpr (S == 3) blk_suffix2<RB, 1, IMM2, R, MASKED, PAIR, SHN>(pt, t2, reff - (L - 1), sub);
+    else blk_suffixN<S - 1, RB, 1, IMM2, R, MASKED, PAIR, SHN>(pt, t2, reff - (L - 1), sub);
 #pragma unroll
     for (int k = 0; k < R; ++k) out[k] = L == 1 ? sub[k] : fma(ph[k], sub[k], out[k]);
-    blk_suffixN<S, RS, L + 1, IMM, R, MASKED>(pt, t, reff, out);
+    blk_suffixN<S, RS, L + 1, IMM, R, MASKED, PAIR, SH>(pt, t, reff, out);
   }
 }
 
@@ -244,17 +297,45 @@ __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_
 
 // One record: the compiled suffix of the staged record. (Staging the NEXT record inside the same basic block,
 // so that ptxas interleaves the two dependency chains, was measured 5 % slower: registers.)
-template <int S, int RS, int R, bool MASKED>
-__device__ __forceinline__ void blk_record(const BlkPoint<R> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
+template <int S, int RS, int R, bool MASKED, bool PAIR, bool SH>
+__device__ __forceinline__ void blk_record(const BlkPoint<R, PAIR> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
   uint32_t t[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) t[k] = st.t[k] * (blk_size(S, RS) * 8u) + st.cb;
   const int reff = MASKED ? rem - (int)(st.sw >> kBrUsedShift) : 0;
   double v[R];
-  if constexpr (S == 2) blk_suffix2<RS, 1, 0, R, MASKED>(pt, t, reff, v);
-  else blk_suffixN<S, RS, 1, 0, R, MASKED>(pt, t, reff, v);
+  if constexpr (S == 2) blk_suffix2<RS, 1, 0, R, MASKED, PAIR, SH>(pt, t, reff, v);
+  else blk_suffixN<S, RS, 1, 0, R, MASKED, PAIR, SH>(pt, t, reff, v);
 #pragma unroll
   for (int k = 0; k < R; ++k) acc[k] = fma(st.cur[k], v[k], acc[k]);
+}
+
+// the compiled suffix of a staged record, chosen by its code. PAIR kernels compile the unshared form (a prefix level
+// above kBlkTab) only for the small budgets such a prefix can leave on the grids that take PAIR mode (kBlkPairMaxR).
+template <int R, bool MASKED, bool PAIR, bool SH>
+__device__ __forceinline__ void blk_dispatch(const BlkPoint<R, PAIR> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
+#define BLK_CASE(S, RS)                                                                                      \
+  case blk_code(S, RS):                                                                                      \
+    if constexpr ((S <= 3 || RS <= blk_max_r(S)) && (!PAIR || SH || RS <= kBlkPairMaxR))                     \
+      blk_record<S, RS, R, MASKED, PAIR, SH>(pt, st, rem, acc);                                              \
+    break;
+  // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
+  // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
+  const uint32_t code = st.sw & 0xffu;
+  if (code == blk_code(3, 0)) blk_record<3, 0, R, MASKED, PAIR, SH>(pt, st, rem, acc);
+  else if (code == blk_code(3, 1)) blk_record<3, 1, R, MASKED, PAIR, SH>(pt, st, rem, acc);
+  else if (code == blk_code(3, 2)) blk_record<3, 2, R, MASKED, PAIR, SH>(pt, st, rem, acc);
+  else switch (code) {
+    BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
+    BLK_CASE(2, 0) BLK_CASE(2, 1) BLK_CASE(2, 2) BLK_CASE(2, 3) BLK_CASE(2, 4) BLK_CASE(2, 5) BLK_CASE(2, 6) BLK_CASE(2, 7)
+    BLK_CASE(4, 1) BLK_CASE(4, 2) BLK_CASE(4, 3) BLK_CASE(4, 4) BLK_CASE(4, 5)
+    BLK_CASE(5, 1) BLK_CASE(5, 2) BLK_CASE(5, 3) BLK_CASE(5, 4)
+    BLK_CASE(6, 1) BLK_CASE(6, 2) BLK_CASE(6, 3) BLK_CASE(6, 4)
+    BLK_CASE(7, 1) BLK_CASE(7, 2) BLK_CASE(7, 3)
+    BLK_CASE(8, 1) BLK_CASE(8, 2)
+    default: break;  // kBrNone: a stage-only record
+  }
+#undef BLK_CASE
 }
 
 // producer side (one thread): start the copies of tile t into buffer `buf`
@@ -271,8 +352,9 @@ __device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm,
 }
 
 // registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
-template <int R, bool MASKED, int NT>
+template <int R, bool MASKED, int NT, bool PAIR>
 __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid g, const EvalArgs a) {
+  static_assert(!PAIR || R == 2, "PAIR mode pairs the two points of a thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BlkSmem &sm = *reinterpret_cast<BlkSmem *>(smem_raw);
   const int D = g.D;
@@ -286,9 +368,11 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
   uint32_t xs_t = smem_u32(xs) + tid * 8u;
   uint32_t ps_t = smem_u32(Ps) + tid * 8u;
   uint32_t os_t = smem_u32(Os) + tid * 4u;
+  const int64_t M = a.M_dev ? (int64_t)*a.M_dev : a.M;  // follow-up launch of PAIR mode: the count lives on the device
   const int64_t tile_pts = (int64_t)NT * R;
   const int64_t stride = (int64_t)gridDim.x * tile_pts;
   const uint32_t ntiles = g.n_btiles;
+  if ((int64_t)blockIdx.x * tile_pts >= M) return;
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
@@ -302,38 +386,66 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
   __syncthreads();
   uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
 
-  for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < a.M; base += stride) {
-    BlkPoint<R> pt;
+  for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < M; base += stride) {
+    BlkPoint<R, PAIR> pt;
     pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
     static_assert(NT == kBlkThreads, "blk_x_rare assumes the default CTA size");
     uint32_t inside = 0u;  // bit k: point k lies in the domain
+    uint32_t live = (1u << R) - 1u;  // bit k: point k's result is stored by this launch
+    uint32_t code2[R];     // PAIR: the cells of level <= kBlkTab of every dimension (2 bits each)
+    int64_t mms[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const int64_t j = base + (int64_t)k * NT + tid;
-      const int64_t jj = j < a.M ? j : a.M - 1;  // tail lanes redo the last point, never store
+      // PAIR: a thread owns two NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
+      const int64_t j = PAIR ? base + 2 * (int64_t)tid + k : base + (int64_t)k * NT + tid;
+      const int64_t jj = j < M ? j : M - 1;  // tail lanes redo the last point, never store
+      if (j >= M) live &= ~(1u << k);
       const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
+      mms[k] = mm;
       bool in = true;
+      uint32_t c2 = 0u;
       for (int d = 0; d < D; ++d) {
         const double xd = a.X[mm * a.sp + d * a.sd];
         const double u = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));  // scale(), src/math.jl:308
         in = in && (u >= 0.0) && (u <= 1.0);                                             // NaN fails both
         xs[(d * R + k) * NT + tid] = u;
+        if (PAIR) c2 = (c2 << 2) | min((uint32_t)(u * 4.0), 3u);
       }
       if (in) inside |= 1u << k;
-      else  // walked at the centre of the cube; the result is replaced by the exact 0.0
+      else {  // walked at the centre of the cube; the result is replaced by the exact 0.0
         for (int d = 0; d < D; ++d) xs[(d * R + k) * NT + tid] = 0.5;
+        c2 = 0xaaaaaaaau & ((D >= 16) ? 0xffffffffu : ((1u << (2 * D)) - 1u));
+      }
+      code2[k] = c2;
+    }
+    if constexpr (PAIR) {
+      if (code2[1] != code2[0]) {
+        // not in one cell: this launch evaluates point 0 twice, the follow-up launch takes point 1
+        if (live & 2u) a.left_list[atomicAdd(a.left_count, 1u)] = (uint32_t)mms[1];
+        live &= ~2u;
+        inside = (inside & 1u) * 3u;
+        for (int d = 0; d < D; ++d) xs[(d * R + 1) * NT + tid] = xs[(d * R + 0) * NT + tid];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
       const double uA = xs[(K * R + k) * NT + tid], uB = xs[((K + 1) * R + k) * NT + tid], uC = xs[((K + 2) * R + k) * NT + tid];
       const uint32_t qB = blk_key(uB), qC = blk_key(uC);
       pt.xA[k] = uA;
       pt.qA[k] = blk_key(uA);
 #pragma unroll
       for (int l = 2; l <= kBlkTab; ++l) {
-        uint32_t cell;
-        hat_cell(uC, qC, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phC[k][l], cell);
-        pt.wC8[k][l] = (blk_off1(l) + cell) * 8u;
-        hat_cell(uB, qB, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phB[k][l], pt.cB[k][l]);
-        pin_f64(pt.phC[k][l]); pin_u32(pt.wC8[k][l]);
-        pin_f64(pt.phB[k][l]); pin_u32(pt.cB[k][l]);
+        uint32_t cellC, cellB;
+        hat_cell(uC, qC, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phC[k][l], cellC);
+        hat_cell(uB, qB, l > 3 ? l - 2 : 1, l > 2 ? 1u : 0u, pow2_lm1(l), pt.phB[k][l], cellB);
+        if (!PAIR || k == 0) {
+          pt.wC8[PAIR ? 0 : k][l] = (blk_off1(l) + cellC) * 8u;
+          pt.cB[PAIR ? 0 : k][l] = cellB;
+          pin_u32(pt.wC8[PAIR ? 0 : k][l]);
+          pin_u32(pt.cB[PAIR ? 0 : k][l]);
+        }
+        pin_f64(pt.phC[k][l]);
+        pin_f64(pt.phB[k][l]);
       }
     }
     if (tid == 0) {
@@ -360,34 +472,21 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
         BlkStaged<R> st;
         blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, st);
-#define BLK_CASE(S, RS) \
-  case blk_code(S, RS): if constexpr (S <= 3 || RS <= blk_max_r(S)) blk_record<S, RS, R, MASKED>(pt, st, a.rem, acc); break;
-        // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
-        // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
-        const uint32_t code = st.sw & 0xffu;
-        if (code == blk_code(3, 0)) blk_record<3, 0, R, MASKED>(pt, st, a.rem, acc);
-        else if (code == blk_code(3, 1)) blk_record<3, 1, R, MASKED>(pt, st, a.rem, acc);
-        else if (code == blk_code(3, 2)) blk_record<3, 2, R, MASKED>(pt, st, a.rem, acc);
-        else switch (code) {
-          BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
-          BLK_CASE(2, 0) BLK_CASE(2, 1) BLK_CASE(2, 2) BLK_CASE(2, 3) BLK_CASE(2, 4) BLK_CASE(2, 5) BLK_CASE(2, 6) BLK_CASE(2, 7)
-          BLK_CASE(4, 1) BLK_CASE(4, 2) BLK_CASE(4, 3) BLK_CASE(4, 4) BLK_CASE(4, 5)
-          BLK_CASE(5, 1) BLK_CASE(5, 2) BLK_CASE(5, 3) BLK_CASE(5, 4)
-          BLK_CASE(6, 1) BLK_CASE(6, 2) BLK_CASE(6, 3) BLK_CASE(6, 4)
-          BLK_CASE(7, 1) BLK_CASE(7, 2) BLK_CASE(7, 3)
-          BLK_CASE(8, 1) BLK_CASE(8, 2)
-          default: break;  // kBrNone: a stage-only record
+        if constexpr (PAIR) {
+          // warp-uniform: every level of the record's prefix is <= kBlkTab, the pair shares the prefix position
+          if (st.sw & kBrShared) blk_dispatch<R, MASKED, true, true>(pt, st, a.rem, acc);
+          else blk_dispatch<R, MASKED, true, false>(pt, st, a.rem, acc);
+        } else {
+          blk_dispatch<R, MASKED, false, false>(pt, st, a.rem, acc);
         }
-#undef BLK_CASE
       }
       __syncthreads();  // every warp is done with buffer `buf`
       if (tid == 0 && t + 2 < ntiles) blk_issue_tile(g, sm, t + 2, buf);
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const int64_t j = base + (int64_t)k * NT + tid;
-      if (j < a.M) {
-        const int64_t mm = a.perm ? (int64_t)a.perm[j] : j;
+      if ((live >> k) & 1u) {
+        const int64_t mm = mms[k];
         const double v = ((inside >> k) & 1u) ? acc[k] : 0.0;
         a.out[mm] = a.fvals ? (a.fvals[mm] - v) : v;
       }
@@ -395,15 +494,15 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
   }
 }
 
-// One launch function per (points per thread, masked) variant; each is instantiated in its own translation unit
-// (asg_kernels_block_r{1,2}{,m}.cu) so that the four large kernels compile in parallel.
-template <int R, bool MASKED, int NT>
+// One launch function per (points per thread, masked, paired) variant; each is instantiated in its own translation
+// unit (asg_kernels_block_r{1,2,2p}{,m}.cu) so that the large kernels compile in parallel.
+template <int R, bool MASKED, int NT, bool PAIR>
 cudaError_t blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
   // one instantiation serves every grid: raise its dynamic shared-memory limit once per device to the device maximum
   static std::atomic<unsigned> limit_set{0};
-  const cudaError_t e = smem_limit_once(k_eval_block<R, MASKED, NT>, 227 * 1024, limit_set);
+  const cudaError_t e = smem_limit_once(k_eval_block<R, MASKED, NT, PAIR>, 227 * 1024, limit_set);
   if (e != cudaSuccess) return e;
-  k_eval_block<R, MASKED, NT><<<blocks, NT, smem, st>>>(g, a);
+  k_eval_block<R, MASKED, NT, PAIR><<<blocks, NT, smem, st>>>(g, a);
   return cudaSuccess;
 }
 

@@ -1,0 +1,6 @@
+// asg_kernels_block_r2p.cu -- the BLOCK walk with 2 points per thread, unmasked, PAIR mode (neighbours of the cell-key order share their coefficient loads) (see asg_kernels_block.cuh)
+#include "asg_kernels_block.cuh"
+
+namespace asg {
+template cudaError_t blk_launch<2, false, kBlkThreads, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+}  // namespace asg

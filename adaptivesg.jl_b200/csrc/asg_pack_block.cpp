@@ -323,18 +323,25 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     q.odd = l > 2 ? 1u : 0u;
     q.sw = (save ? kBrSave : 0u) | ((uint32_t)used << kBrUsedShift);
   };
+  out.blk_pair_ok = true;
   for (auto &kv : recs) {
     const Key &p = kv.first;
     const Rec &I = kv.second;
     BlockRec q{};
     const int l0 = I.nt ? p[(size_t)I.k0] : 1;
     stage_of(q, I.nt ? I.nt - 1 : 0, I.k0, l0, I.parent_of && I.nt, I.used);
+    // PAIR mode: neighbours of the cell-key order share every cell of level <= kBlkPairLevel, so they share the
+    // prefix position of this record iff every prefix level is that low
+    bool shared = true;
+    for (uint8_t l : p) shared = shared && l <= kBlkPairLevel;
+    if (shared) q.sw |= kBrShared;
     if (I.r < 0) {
       q.sw |= kBrNone;
       out.brec.push_back(q);
       lo.push_back(0); hi.push_back(0);
     } else if (!I.split) {
       q.sw |= blk_code(I.S, I.r);
+      if (!shared && I.r > kBlkPairMaxR) out.blk_pair_ok = false;
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
@@ -346,6 +353,8 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
         if (lA > 1) {  // stage = level lA of dimension A, restart from the prefix product this prefix saved
           stage_of(s, I.nt, K, lA, false, I.used + lA - 1);
         }
+        if (shared && lA <= kBlkPairLevel) s.sw |= kBrShared;
+        else if (rA > kBlkPairMaxR) out.blk_pair_ok = false;
         s.sw |= blk_code(2, rA);
         s.cbase = I.cbaseA[lA - 1];
         out.brec.push_back(s);

@@ -33,7 +33,7 @@ uint64_t checksum(const unsigned char *p, size_t n) {
 }
 
 uint64_t layout_fingerprint() {  // everything a blob's bytes depend on besides the grid itself
-  const uint32_t c[] = {1u /* format version */, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
+  const uint32_t c[] = {2u /* format version */, (uint32_t)kBlkPairLevel, (uint32_t)kBlkPairMaxR, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
                         (uint32_t)sizeof(StreamTile), (uint32_t)sizeof(BlockTile), (uint32_t)sizeof(HashEnt),
                         (uint32_t)sizeof(SweepDim), (uint32_t)sizeof(RsgParams), (uint32_t)kLeafTable, (uint32_t)kTileCoefs,
                         (uint32_t)kTileRecs, (uint32_t)kBlkTileCoefsMax, (uint32_t)kBlkTileRecs, (uint32_t)kBlkMaxS,
@@ -91,7 +91,7 @@ void fields(IO &io, PK &pk) {  // one list for both directions
   io.vec(pk.coef); io.pod(pk.coef_pad); io.vec(pk.orig); io.vec(pk.hent); io.vec(pk.horig); io.vec(pk.slot_of_node);
   io.vec(pk.grp); io.vec(pk.tiles); io.pod(pk.regular); io.pod(pk.rp);
   io.pod(pk.blk_ok); io.str(pk.blk_why); io.vec(pk.bcoef); io.vec(pk.brec); io.vec(pk.btiles); io.vec(pk.bslot_of_node);
-  io.pod(pk.blk_slots); io.pod(pk.blk_tile_coefs); io.vec(pk.sw); io.vec(pk.sw_low); io.vec(pk.depth);
+  io.pod(pk.blk_slots); io.pod(pk.blk_tile_coefs); io.pod(pk.blk_pair_ok); io.vec(pk.sw); io.vec(pk.sw_low); io.vec(pk.depth);
 }
 
 }  // namespace
@@ -145,6 +145,46 @@ int pack_deserialize(const unsigned char *buf, size_t bytes, int D, const double
       (pk.canonical && pk.rec.size() != (size_t)D) || (pk.blk_ok && pk.bslot_of_node.size() != N)) {
     err = "packed-grid blob is malformed";
     return ASG_EINVAL;
+  }
+  // The slot maps, tiles and records become device indices (coefficient scatters, tile copies, record fetches): a
+  // damaged or crafted file must fail here, not as an out-of-bounds access on the device. (The checksum only guards
+  // against accidents.)
+  auto bad = [&](const char *what) { err = std::string("packed-grid blob is inconsistent: ") + what; return ASG_EINVAL; };
+  if (pk.canonical) {
+    for (int64_t s : pk.slot_of_node)
+      if (s >= 0 ? (uint64_t)s >= pk.coef.size() : (uint64_t)(-s - 1) >= pk.hent.size()) return bad("node slot out of range");
+    if (pk.orig.size() != pk.coef.size() || pk.horig.size() != pk.hent.size()) return bad("slot maps differ in length");
+    for (int32_t o : pk.orig) if (o < -1 || (uint64_t)(o + 1) > N) return bad("slot owner out of range");
+    for (int32_t o : pk.horig) if (o < -1 || (uint64_t)(o + 1) > N) return bad("hash slot owner out of range");
+    for (const StreamTile &t : pk.tiles)
+      if (t.r0 > t.r1 || t.r1 > pk.grp.size() || t.c0 > t.c1 || t.c1 > pk.coef.size() || t.c1 - t.c0 > (uint32_t)kTileCoefs + 2u ||
+          t.r1 - t.r0 > (uint32_t)kTileRecs)
+        return bad("stream tile out of range");
+  }
+  if (pk.blk_ok) {
+    bool tile_ok = false;
+    for (int tc : kBlkTileCandidates) tile_ok = tile_ok || tc == pk.blk_tile_coefs;
+    if (!tile_ok || pk.blk_slots < 1 || pk.blk_slots > kBlkMaxSlots) return bad("BLOCK walk parameters");
+    for (int64_t s : pk.bslot_of_node)
+      if (s < 0 || (uint64_t)s >= pk.bcoef.size()) return bad("BLOCK node slot out of range");
+    for (const BlockTile &t : pk.btiles)
+      if (t.r0 > t.r1 || t.r1 > pk.brec.size() || t.c0 > t.c1 || t.c1 > pk.bcoef.size() || ((t.c0 | t.c1) & 1u) ||
+          t.c1 - t.c0 > (uint32_t)pk.blk_tile_coefs || t.r1 - t.r0 > (uint32_t)kBlkTileRecs)
+        return bad("BLOCK tile out of range");
+    for (size_t ti = 0; ti < pk.btiles.size(); ++ti) {
+      const BlockTile &t = pk.btiles[ti];
+      for (uint32_t q = t.r0; q < t.r1; ++q) {
+        const BlockRec &b = pk.brec[q];
+        const uint32_t code = b.sw & 0xffu;
+        const bool save = (b.sw & kBrSave) != 0;
+        if (b.slot + (save ? 1u : 0u) >= (uint32_t)pk.blk_slots || b.k0 >= (uint32_t)D || b.b > 24u || b.lim != (1u << b.b) - 1u)
+          return bad("BLOCK record stage");
+        if (code != kBrNone) {
+          const int S = (int)(code >> 3), r = (int)(code & 7u);
+          if (S < 2 || S > kBlkMaxS || (S > 3 && r > blk_max_r(S)) || b.cbase < t.c0 || b.cbase >= t.c1) return bad("BLOCK record suffix");
+        }
+      }
+    }
   }
   return ASG_OK;
 }

@@ -25,14 +25,27 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
-def broadcast_grid(G, src: int = 0):
-    """C1: make every rank's SparseGridInterpolant identical to rank `src`'s (arrays + bounds)."""
+def broadcast_grid(G, src: int = 0, packed: bool | None = None):
+    """C1: make every rank's SparseGridInterpolant identical to rank `src`'s (arrays + bounds).
+
+    With ``packed`` (default: on whenever the backend is NCCL, i.e. every rank has its GPU) the source also ships the
+    device-format blob of its uploaded grid (``asg_grid_export``): the other ranks install it with
+    ``asg_grid_import_checked`` instead of validating, sorting and packing the same node arrays once more per rank
+    (0.13 s instead of 0.3 s each for the 652 065-node benchmark grid)."""
+    import ctypes as C
+
+    from . import _capi
+    from .interpolant import serialize
+
     dev = _dev()
     D = G.ndims
-    meta = torch.tensor([len(G.levels) if dist.get_rank() == src else 0], dtype=torch.int64, device=dev)
-    dist.broadcast(meta, src)
-    N = int(meta.item())
     is_src = dist.get_rank() == src
+    if packed is None:
+        packed = dist.get_backend() == "nccl"
+    blob = serialize(G, packed=True)["packed"] if (packed and is_src and len(G.levels)) else None
+    meta = torch.tensor([len(G.levels), 0 if blob is None else blob.size] if is_src else [0, 0], dtype=torch.int64, device=dev)
+    dist.broadcast(meta, src)
+    N, nblob = int(meta[0].item()), int(meta[1].item())
 
     def bc(arr, shape, dtype):
         t = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev) if is_src else \
@@ -46,9 +59,19 @@ def broadcast_grid(G, src: int = 0):
     depths = bc(G.depths, (N,), np.int64)
     fvals = bc(G.fvals, (N,), np.float64)
     coefs = bc(G.coefs, (N,), np.float64)
+    blob_all = bc(blob, (nblob,), np.uint8) if nblob else None
     if not is_src:
         G.lb, G.ub = tuple(bounds[:D].tolist()), tuple(bounds[D:].tolist())
         G.levels, G.indices, G.depths, G.fvals, G.coefs = levels, indices, depths, fvals, coefs
+        if blob_all is not None:
+            buf = np.ascontiguousarray(blob_all)
+            rc = _capi.load().asg_grid_import_checked(
+                G._grid(), buf.ctypes.data_as(C.c_void_p), buf.size, N, levels.ctypes.data_as(_capi.i64p),
+                indices.ctypes.data_as(_capi.i64p), D, 1, coefs.ctypes.data_as(_capi.f64p))
+            if rc == 0:
+                object.__setattr__(G, "_dirty", False)
+            elif rc not in (_capi.ASG_EUNSUPPORTED, _capi.ASG_ESTATE):
+                _capi.check(rc)
     return G
 
 

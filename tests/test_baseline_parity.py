@@ -76,13 +76,28 @@ def test_cfg3_full_size_against_oracle(asg, cfg3):
     # depth masks (_interpolate_until_level, src/class.jl:666-680) and the surplus epilogue (src/train.jl:176-183)
     f = rng.standard_normal(M)
     sub = sel[::4]
+    G_masked = {}
     for L in (3, 6, 8):
         ym = G.evaluate(X, max_depth=L)
+        G_masked[L] = ym
         wm, scm = OG.evaluate(X[sub], max_depth=L, return_abssum=True)
         assert_close(ym[sub], wm, scm, f"cfg3 full size, depth <= {L}")
         al = G.surplus(X, f, max_depth=L)
         assert_close(al[sub], f[sub] - wm, scm + np.abs(f[sub]), f"cfg3 full size, surplus depth <= {L}")
     assert np.array_equal(G.evaluate(X, max_depth=8), y)            # depth 8 is the whole grid
+    # PAIR mode of the walk (neighbours of the cell-key order share their coefficient loads; default from ~8 points per
+    # 2-bit cell on, i.e. 8.4e6 points for D = 10): forced on here, where most pairs straddle a cell boundary and go to
+    # the follow-up launch -- the sums do not depend on the mode, bit for bit
+    import os
+    os.environ["ASG_BLOCK_PAIR"] = "1e-9"
+    try:
+        yp = G.evaluate(X)
+        assert np.array_equal(yp, y)
+        for L in (3, 6):
+            assert np.array_equal(G.evaluate(X, max_depth=L), G_masked[L])
+        assert np.array_equal(G.surplus(X, f, max_depth=6), f - G_masked[6])
+    finally:
+        del os.environ["ASG_BLOCK_PAIR"]
     # one point per thread (small batch) and the other walks of the same layout give the same sums
     small = G.evaluate(X[sel])
     assert_close(small, want, sc, "cfg3 full size, small batch")

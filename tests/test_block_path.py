@@ -249,3 +249,55 @@ def test_engines_differential_fuzz():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "all grids agree" in r.stdout
+
+
+@pytest.mark.gpu
+def test_block_walk_pair_mode(asg, oracle):
+    """PAIR mode (asg_kernels_block.cuh): two neighbours of the cell-key order per thread, one coefficient load for both
+    wherever every level on the path is <= 4. Regular and adapt!-grown grids, D = 3 .. 10, batches where nearly every
+    pair shares its cell (D small) and where nearly none does (D = 10: the follow-up launch does the work); unmasked,
+    masked and surplus; the results equal the unpaired walk's bit for bit and the oracle's within tolerance."""
+    rng = np.random.default_rng(21)
+    paired = 0
+    cfg4 = oracle.OracleGrid(6)
+    cfg4.rsg(7, tuple(range(6, 12)))             # 15 089 nodes, 923 subspaces, suffix levels up to 8
+    cfg4.coefs = rng.standard_normal(len(cfg4)) * 2.0 ** (-cfg4.depths.astype(float))
+    for OG in _grids(oracle) + [cfg4]:
+        D = OG.D
+        G = _mirror(asg, OG)
+        if G.info()["block"] != 1:
+            continue
+        G.set_path("block")
+        M = 300001
+        X = OG.lb + (OG.ub - OG.lb) * rng.random((M, D))
+        X[::777] = OG.lb + (OG.ub - OG.lb) * (rng.integers(0, 65, size=(len(X[::777]), D)) / 64.0)   # knots
+        X[5::1001, 0] = OG.ub[0] + 1.0
+        X[9::2003, D - 1] = np.nan
+        f = rng.standard_normal(M)
+        L = int(rng.integers(2, int(OG.depths.max()) + 1))
+        os.environ["ASG_BLOCK_PAIR"] = "0"
+        try:
+            y0 = G.evaluate(X)
+            m0 = G.evaluate(X, max_depth=L)
+            s0 = G.surplus(X, f)
+        finally:
+            del os.environ["ASG_BLOCK_PAIR"]
+        os.environ["ASG_BLOCK_PAIR"] = "1e-9"
+        try:
+            n0 = asg.launch_count()
+            y1 = G.evaluate(X)
+            if G.info()["subspaces"] >= 512:             # (smaller grids skip the point ordering, hence PAIR mode)
+                assert asg.launch_count() - n0 >= 3      # keys + paired walk + follow-up walk
+                paired += 1
+            m1 = G.evaluate(X, max_depth=L)
+            s1 = G.surplus(X, f)
+        finally:
+            del os.environ["ASG_BLOCK_PAIR"]
+        assert np.array_equal(y0, y1, equal_nan=True), D
+        assert np.array_equal(m0, m1, equal_nan=True), (D, L)
+        assert np.array_equal(s0, s1, equal_nan=True), D
+        sel = rng.choice(M, size=2000, replace=False)
+        want, sc = OG.evaluate(X[sel], return_abssum=True)
+        assert_close(y1[sel], want, sc, f"pair mode D={D}")
+        assert np.all(y1[5::1001] == 0.0) and np.all(y1[9::2003] == 0.0)
+    assert paired >= 2   # D = 10 depth 5 and the D = 6 anisotropic grid of BASELINE configs[3]

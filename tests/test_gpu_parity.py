@@ -301,9 +301,11 @@ def test_noncanonical_falls_back_to_sweep(asg, oracle):
         w3 = OG3.evaluate(X3)
         g3 = G3.evaluate(X3)
         assert G3.info()["path"] == 1
-        assert np.array_equal(np.isnan(g3), np.isnan(w3)) and np.any(np.isnan(w3))
-        ok = ~np.isnan(w3)
-        assert_close(g3[ok], w3[ok], None, "finite part next to a non-finite coefficient")
+        assert np.array_equal(np.isnan(g3), np.isnan(w3)) and np.any(~np.isfinite(w3))
+        assert np.array_equal(np.isinf(g3), np.isinf(w3)) and np.array_equal(np.sign(g3[np.isinf(g3)]), np.sign(w3[np.isinf(w3)]))
+        ok = np.isfinite(w3)
+        if ok.any():
+            assert_close(g3[ok], w3[ok], None, "finite part next to a non-finite coefficient")
         H3 = asg.deserialize(asg.serialize(G3, packed=True))
         assert np.array_equal(H3.evaluate(X3), g3, equal_nan=True)
 
