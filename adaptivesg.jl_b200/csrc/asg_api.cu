@@ -132,6 +132,8 @@ struct Replica {
   DevBuf<unsigned char> s_sorttmp[kPipeSlots];
   DevBuf<uint32_t> s_left[kPipeSlots], s_leftcnt[kPipeSlots];  // PAIR mode of the BLOCK walk: points left to the follow-up launch
   cudaEvent_t sort_ev[kPipeSlots] = {};  // last use of the slot's scratch
+  std::vector<cudaEvent_t> piece_ev;     // host-buffer pipeline: arrival of each piece of points
+  cudaEvent_t walk_ev[2] = {};           // and the end of the last two windows' walks
   void release_all() {
     d_rec.release(); d_grp.release(); d_tiles.release(); d_bcoef.release(); d_brec.release(); d_btiles.release();
     d_coef.release(); d_sw_coef.release(); d_orig.release(); d_horig.release(); d_sw_depth.release(); d_hent.release();
@@ -143,6 +145,9 @@ struct Replica {
       if (sort_ev[s]) cudaEventDestroy(sort_ev[s]);
       sort_ev[s] = nullptr;
     }
+    for (cudaEvent_t e : piece_ev) cudaEventDestroy(e);
+    piece_ev.clear();
+    for (int k = 0; k < 2; ++k) { if (walk_ev[k]) cudaEventDestroy(walk_ev[k]); walk_ev[k] = nullptr; }
     c_PL.release(); c_PI.release(); c_CL.release(); c_CI.release(); c_OL.release(); c_OI.release();
     c_valid.release(); c_table.release(); c_flags.release(); c_sums.release();
     s_i64a.release(); s_i64b.release(); s_tmp.release(); s_tmp2.release(); s_flag.release();
@@ -350,6 +355,7 @@ int install_pack(asg_grid *g, PackResult &pk) {
   I.block_records = g->blk_ok ? (int64_t)pk.brec.size() : 0;
   I.block_tiles = g->blk_ok ? (int64_t)pk.btiles.size() : 0;
   I.block_stack = g->blk_ok ? pk.blk_slots : 0;
+  I.block_pair = (g->blk_ok && pk.blk_pair_ok) ? 1 : 0;
   if (g->blk_ok) I.device_bytes += (int64_t)(R.d_bcoef.bytes() + R.d_brec.bytes() + R.d_btiles.bytes());
   return ASG_OK;
 }
@@ -472,76 +478,157 @@ int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, in
   return ASG_OK;
 }
 
-// Chunk schedule of the host-buffer pipeline. Only the first H2D copy and the last walk + D2H copy are not hidden
-// behind other work, so the chunks ramp UP from a small first one (factor 3: a copy runs about three times faster
-// than the walk of the same points, so the next chunk is always there in time) and DOWN again at the end; in between
-// they are as large as the slot buffers allow, because the cell-key ordering of the BLOCK walk is sharper on large
-// batches. ASG_PIPE_FIRST / ASG_PIPE_CHUNK (points) override the two sizes.
-int64_t pipe_first() {
-  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_FIRST"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 18; }();
+// ---- host-buffer evaluation pipeline --------------------------------------------------------------------------------
+// The points of a call go to the device in PIECES of pipe_piece() points, issued back to back by a feeder thread on
+// the copy-in stream (so that a pageable source, whose cudaMemcpyAsync blocks the issuing thread, still overlaps with
+// the walks). The walk side is GREEDY: whenever the GPU is free it takes EVERY piece that has arrived since the last
+// window as one batch (point ordering + walk), then looks again. The window sizes therefore adapt to the machine by
+// themselves: with one GPU a copy runs ~3x faster than the walk of the same points and the windows grow 0.26 M,
+// 0.8 M, 2.4 M, ... until everything has arrived and the rest goes in one large, sharply ordered batch (PAIR mode);
+// with eight GPUs sharing the host's PCIe fabric (23-36 GB/s each, profiles/r02_pcie_bandwidth_8gpu.json) copy and
+// walk run at about the same rate and the windows stay moderate. Only the first piece's copy, and the walk + D2H copy
+// of the last window -- a short tail split off on purpose -- are not hidden behind other work. Results return on a
+// third stream, one window behind. Batches above pipe_super() points run as consecutive super-batches (device buffers).
+// ASG_PIPE_PIECE / ASG_PIPE_SUPER (points) override the two sizes.
+int64_t pipe_piece() {
+  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_PIECE"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 18; }();
   return v;
 }
-int64_t pipe_chunk() {
-  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_CHUNK"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 24; }();
+int64_t pipe_super() {
+  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_SUPER"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 27; }();
   return v;
-}
-void chunk_schedule(int64_t M, std::vector<int64_t> &sizes) {
-  sizes.clear();
-  const int64_t first = pipe_first(), big = std::max(pipe_chunk(), first);
-  if (M <= 2 * first) { if (M > 0) sizes.push_back(M); return; }
-  // ramp down: tail chunks first .. 3*first .. (reversed at the end), at most a quarter of the batch
-  std::vector<int64_t> tail;
-  int64_t tail_sum = 0;
-  for (int64_t c = first; c < big && tail.size() < 3 && tail_sum + c <= M / 4; c *= 3) { tail.push_back(c); tail_sum += c; }
-  int64_t left = M - tail_sum;
-  for (int64_t c = first; left > 0; c = std::min(3 * c, big)) {
-    const int64_t take = std::min(c, left);
-    sizes.push_back(take);
-    left -= take;
-  }
-  for (size_t k = tail.size(); k-- > 0;) sizes.push_back(tail[k]);
 }
 
-// host-buffer evaluation pipeline on replica r: chunks rotate over kPipeSlots streams so that the H2D copy of chunk
-// k+1 and the D2H copy of chunk k-1 overlap the point ordering and the walk of chunk k
+struct Feeder {  // copy-in side of one super-batch, run by its own host thread
+  std::atomic<int64_t> issued{0};  // pieces whose completion event has been recorded
+  std::atomic<bool> abort{false};
+  int rc = ASG_OK;
+  std::string err;
+};
+
+int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int64_t sdim, const double *fvals,
+               int64_t max_depth, double *out) {
+  USE_REPLICA(g, r);
+  const int D = g->D;
+  const int64_t P = pipe_piece();
+  const int64_t np = (cnt + P - 1) / P;
+  // device layout of the points: row-major unless the host matrix is column-major (Julia's M x D)
+  const bool colmajor = (sp == 1 && D > 1 && sdim != 1);
+  const bool rowlike = (sdim == 1 || D == 1);
+  const int64_t dsp = colmajor ? 1 : D, dsd = colmajor ? cnt : 1;
+  if (int rc = R.s_X[0].reserve((size_t)cnt * D)) return rc;
+  if (int rc = R.s_out[0].reserve((size_t)cnt)) return rc;
+  if (fvals)
+    if (int rc = R.s_f[0].reserve((size_t)cnt)) return rc;
+  // the ordering scratch of the largest possible window, so that no allocation happens while the pipeline runs
+  if (g->path() == ASG_PATH_SUBSPACE && g->walk() == 3 && cnt >= sort_threshold() && cnt < ((int64_t)1 << 31) && g->info.subspaces >= 512) {
+    if (int rc = R.s_key[0].reserve((size_t)cnt)) return rc;
+    if (int rc = R.s_key2[0].reserve((size_t)cnt)) return rc;
+    if (int rc = R.s_idx[0].reserve((size_t)cnt)) return rc;
+    if (int rc = R.s_perm[0].reserve((size_t)cnt)) return rc;
+    if (int rc = R.s_sorttmp[0].reserve(sort_points_temp_bytes(cnt))) return rc;
+    if (block_pair_mode(R.dg, cnt, true)) {
+      if (int rc = R.s_left[0].reserve((size_t)cnt / 2 + 2)) return rc;
+      if (int rc = R.s_leftcnt[0].reserve(4)) return rc;
+    }
+  }
+  while ((int64_t)R.piece_ev.size() < np) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    R.piece_ev.push_back(e);
+  }
+  for (int k = 0; k < 2; ++k)
+    if (!R.walk_ev[k]) CK(cudaEventCreateWithFlags(&R.walk_ev[k], cudaEventDisableTiming));
+  cudaStream_t s_in = dc.pipe[0], s_walk = dc.pipe[1], s_out = dc.pipe[2];
+  double *dX = R.s_X[0].p, *dOut = R.s_out[0].p, *dF = fvals ? R.s_f[0].p : nullptr;
+
+  Feeder fd;
+  std::thread feeder([&]() {
+    if (cudaSetDevice(dc.device) != cudaSuccess) { fd.rc = ASG_ECUDA; fd.err = "cudaSetDevice failed in the copy thread"; fd.issued = np; return; }
+    std::vector<double> repack;
+    auto fail = [&](cudaError_t e) {
+      fd.rc = e == cudaErrorMemoryAllocation ? ASG_ENOMEM : ASG_ECUDA;
+      fd.err = std::string("host -> device copy: ") + cudaGetErrorString(e);
+    };
+    for (int64_t k = 0; k < np && !fd.abort.load(); ++k) {
+      const int64_t p0 = k * P, n = std::min(P, cnt - p0);
+      cudaError_t e = cudaSuccess;
+      if (rowlike && sp == D) {
+        e = cudaMemcpyAsync(dX + p0 * D, X + p0 * sp, (size_t)n * D * 8, cudaMemcpyHostToDevice, s_in);
+      } else if (rowlike) {
+        e = cudaMemcpy2DAsync(dX + p0 * D, (size_t)D * 8, X + p0 * sp, (size_t)sp * 8, (size_t)D * 8, (size_t)n, cudaMemcpyHostToDevice, s_in);
+      } else if (colmajor) {
+        for (int d = 0; d < D && e == cudaSuccess; ++d)
+          e = cudaMemcpyAsync(dX + (size_t)d * cnt + p0, X + p0 + d * sdim, (size_t)n * 8, cudaMemcpyHostToDevice, s_in);
+      } else {  // generic strides: repack on the host
+        repack.resize((size_t)n * D);
+        for (int64_t q = 0; q < n; ++q)
+          for (int d = 0; d < D; ++d) repack[(size_t)q * D + d] = X[(p0 + q) * sp + d * sdim];
+        e = cudaMemcpyAsync(dX + p0 * D, repack.data(), (size_t)n * D * 8, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_in);  // the staging vector is reused by the next piece
+      }
+      if (e == cudaSuccess && fvals) e = cudaMemcpyAsync(dF + p0, fvals + p0, (size_t)n * 8, cudaMemcpyHostToDevice, s_in);
+      if (e == cudaSuccess) e = cudaEventRecord(R.piece_ev[(size_t)k], s_in);
+      if (e != cudaSuccess) { fail(e); fd.issued = np; return; }
+      fd.issued.store(k + 1, std::memory_order_release);
+    }
+    fd.issued = np;
+  });
+  auto finish = [&](int rc) {  // every exit joins the copy thread first
+    if (rc != ASG_OK) fd.abort = true;
+    feeder.join();
+    return rc;
+  };
+
+  int64_t done = 0, prev_p0 = -1, prev_n = 0;
+  int wk = 0;
+  while (done < np) {
+    // at least one more piece: wait until its copy has been issued, then until it has arrived
+    while (fd.issued.load(std::memory_order_acquire) <= done) std::this_thread::yield();
+    if (fd.rc != ASG_OK) { const int rc = fd.rc; const std::string m = fd.err; finish(rc); return set_err(rc, m); }
+    cudaError_t e = cudaEventSynchronize(R.piece_ev[(size_t)done]);
+    if (e != cudaSuccess) { finish(ASG_ECUDA); return set_err(ASG_ECUDA, std::string("cudaEventSynchronize: ") + cudaGetErrorString(e)); }
+    int64_t arrived = done + 1;
+    const int64_t iss = fd.issued.load(std::memory_order_acquire);
+    while (arrived < np && arrived < iss && cudaEventQuery(R.piece_ev[(size_t)arrived]) == cudaSuccess) ++arrived;
+    cudaGetLastError();  // cudaErrorNotReady of the query is not an error
+    // everything is here: split a short tail off the last window, so that little is left un-overlapped at the end
+    if (arrived == np && np - done > 8) arrived = np - std::max<int64_t>(1, std::min<int64_t>(4, (np - done) / 8));
+    const int64_t p0 = done * P, n = std::min(cnt, arrived * P) - p0;
+    EvalArgs a{};
+    a.X = colmajor ? dX + p0 : dX + p0 * D;
+    a.sp = dsp;
+    a.sd = dsd;
+    a.M = n;
+    a.rem = rem_of(max_depth);
+    a.fvals = dF ? dF + p0 : nullptr;
+    a.out = dOut + p0;
+    if (int rc = run_eval(g, r, a, s_walk, 0)) return finish(rc);
+    e = cudaEventRecord(R.walk_ev[wk], s_walk);
+    // results of the PREVIOUS window go home while this one walks (its walk has finished: we waited for it below)
+    if (e == cudaSuccess && prev_p0 >= 0) e = cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out);
+    if (e == cudaSuccess) e = cudaEventSynchronize(R.walk_ev[wk]);
+    if (e != cudaSuccess) { finish(ASG_ECUDA); return set_err(ASG_ECUDA, std::string("evaluation pipeline: ") + cudaGetErrorString(e)); }
+    prev_p0 = p0;
+    prev_n = n;
+    wk ^= 1;
+    done = arrived;
+  }
+  feeder.join();
+  if (fd.rc != ASG_OK) return set_err(fd.rc, fd.err);
+  if (prev_p0 >= 0) CK(cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out));
+  CK(cudaStreamSynchronize(s_out));
+  return ASG_OK;
+}
+
 int eval_host_dev(asg_grid *g, int r, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
                   int64_t max_depth, double *out) {
   if (int rc = use_dev(r)) return rc;
-  USE_REPLICA(g, r);
-  const int D = g->D;
-  std::vector<int64_t> sizes;
-  chunk_schedule(M, sizes);
-  int64_t biggest = 0;
-  for (int64_t c : sizes) biggest = std::max(biggest, c);
-  std::vector<double> repack_buf;
-  const int nslot = (int)std::min<size_t>(sizes.size(), kPipeSlots);
-  for (int s = 0; s < nslot; ++s) {
-    if (int rc = R.s_X[s].reserve((size_t)biggest * D)) return rc;
-    if (int rc = R.s_out[s].reserve((size_t)biggest)) return rc;
-    if (fvals)
-      if (int rc = R.s_f[s].reserve((size_t)biggest)) return rc;
+  const int64_t S = pipe_super();
+  for (int64_t m0 = 0; m0 < M; m0 += S) {
+    const int64_t cnt = std::min(S, M - m0);
+    if (int rc = eval_super(g, r, X + m0 * sp, cnt, sp, sdim, fvals ? fvals + m0 : nullptr, max_depth, out + m0)) return rc;
   }
-  int64_t m0 = 0;
-  for (size_t k = 0; k < sizes.size(); ++k) {
-    const int slot = (int)(k % (size_t)nslot);
-    const int64_t cnt = sizes[k];
-    cudaStream_t st = dc.pipe[slot];
-    EvalArgs a{};
-    if (int rc = stage_points(X, m0, cnt, D, sp, sdim, R.s_X[slot].p, a.sp, a.sd, st, repack_buf)) return rc;
-    a.X = R.s_X[slot].p;
-    a.M = cnt;
-    a.rem = rem_of(max_depth);
-    a.fvals = nullptr;
-    if (fvals) {
-      CK(cudaMemcpyAsync(R.s_f[slot].p, fvals + m0, (size_t)cnt * 8, cudaMemcpyHostToDevice, st));
-      a.fvals = R.s_f[slot].p;
-    }
-    a.out = R.s_out[slot].p;
-    if (int rc = run_eval(g, r, a, st, slot)) return rc;
-    CK(cudaMemcpyAsync(out + m0, R.s_out[slot].p, (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
-    m0 += cnt;
-  }
-  for (int s = 0; s < nslot; ++s) CK(cudaStreamSynchronize(dc.pipe[s]));
   return ASG_OK;
 }
 
@@ -1439,15 +1526,48 @@ int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t
   BasisArgs a{};
   a.X = dX; a.M = M; a.sp = sp; a.sd = sdim; a.atol = atol; a.dropzeros = dropzeros; a.mode = 2;
   a.dense = dout; a.ldm = ldm; a.ldn = ldn;
+  // (measured on cfg5, 18.7 GB: memset + scatter 4.20 ms, CSR + one streaming pass 4.81 ms -- the count and fill
+  // passes cost more than the second pass over the output saves; ASG_DENSE_ONE_PASS=1 selects the streaming path)
+  static const bool two_pass = getenv("ASG_DENSE_ONE_PASS") == nullptr;
   CK(cudaEventRecord(dc.ev0, st));
   if (g->path() == ASG_PATH_SUBSPACE) {
-    // the walk only visits supporting nodes: clear first (needs a dense M x N block)
     const bool rowmajor = (ldn == 1 && ldm >= g->N), colmajor = (ldm == 1 && ldn >= M);
-    if (rowmajor) CK(cudaMemset2DAsync(dout, (size_t)ldm * 8, 0, (size_t)g->N * 8, (size_t)M, st));
-    else if (colmajor) CK(cudaMemset2DAsync(dout, (size_t)ldn * 8, 0, (size_t)M * 8, (size_t)g->N, st));
-    else return set_err(ASG_EUNSUPPORTED, "dense basis needs ldn == 1 (row-major) or ldm == 1 (column-major)");
+    if (rowmajor && !two_pass && M < ((int64_t)1 << 31)) {
+      // One streaming pass over the output: the rows are formed in CSR form first (count, scan, fill: at most one
+      // entry per subspace and row, a few per cent of the output's bytes) and k_dense_rows then writes every output
+      // byte exactly once with 16-byte streaming stores.
+      const int64_t cap = M * std::max<int64_t>(g->info.subspaces, 1);  // upper bound of the entries: no host sync
+      const size_t tb = scan_temp_bytes(M + 1);
+      if (int rc = R.s_i64a.reserve((size_t)M + 1)) return rc;
+      if (int rc = R.s_i64b.reserve((size_t)M + 1)) return rc;
+      if (int rc = R.c_CL.reserve((size_t)cap)) return rc;
+      if (int rc = R.s_tmp.reserve((size_t)cap)) return rc;
+      if (int rc = R.s_sorttmp[0].reserve(tb)) return rc;
+      g->ch_n = -1;  // the adapt! scratch is reused
+      BasisArgs c = a;
+      c.mode = 0;
+      c.row_nnz = (unsigned long long *)R.s_i64a.p;
+      CK(cudaMemsetAsync(R.s_i64a.p + M, 0, 8, st));
+      CK(run_basis(g, c, st));
+      CK(exclusive_scan_u64((const unsigned long long *)R.s_i64a.p, R.s_i64b.p, M + 1, R.s_sorttmp[0].p, tb, st));
+      c.mode = 1;
+      c.row_ptr = R.s_i64b.p;
+      c.colidx = R.c_CL.p;
+      c.vals = R.s_tmp.p;
+      CK(run_basis(g, c, st));
+      int64_t l = 0;
+      CK(launch_dense_rows(R.s_i64b.p, R.c_CL.p, R.s_tmp.p, M, g->N, dout, ldm, st, &l));
+      bump(l);
+    } else {
+      // the walk only visits supporting nodes: clear first (needs a dense M x N block), then scatter
+      if (rowmajor) CK(cudaMemset2DAsync(dout, (size_t)ldm * 8, 0, (size_t)g->N * 8, (size_t)M, st));
+      else if (colmajor) CK(cudaMemset2DAsync(dout, (size_t)ldn * 8, 0, (size_t)M * 8, (size_t)g->N, st));
+      else return set_err(ASG_EUNSUPPORTED, "dense basis needs ldn == 1 (row-major) or ldm == 1 (column-major)");
+      CK(run_basis(g, a, st));
+    }
+  } else {
+    CK(run_basis(g, a, st));
   }
-  CK(run_basis(g, a, st));
   CK(cudaEventRecord(dc.ev1, st));
   dc.last_timed = true;
   dc.walk_timed = false;
@@ -1524,6 +1644,7 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->block_records = info->block ? (int64_t)pk.brec.size() : 0;
   info->block_tiles = info->block ? (int64_t)pk.btiles.size() : 0;
   info->block_stack = info->block ? pk.blk_slots : 0;
+  info->block_pair = (info->block && pk.blk_pair_ok) ? 1 : 0;
   if (!pk.canonical) t_err = pk.why;
   else if (!pk.blk_ok) t_err = "no BLOCK layout: " + pk.blk_why;
   return ASG_OK;

@@ -248,6 +248,12 @@ cudaError_t csr_to_csc(const long long *row_ptr, const long long *colidx, const 
                        int64_t nnz, uint32_t *keys, uint32_t *keys_alt, uint32_t *ent, uint32_t *perm, uint32_t *rows,
                        void *temp, size_t temp_bytes, long long *colptr, long long *rowidx, double *vout, cudaStream_t st,
                        int64_t *launches);
+// dense basis rows written in one streaming pass from their CSR form (asg_sort.cu)
+size_t scan_temp_bytes(int64_t n);
+cudaError_t exclusive_scan_u64(const unsigned long long *in, long long *out, int64_t n, void *temp, size_t temp_bytes,
+                               cudaStream_t st);
+cudaError_t launch_dense_rows(const long long *row_ptr, const long long *colidx, const double *vals, int64_t M, int64_t N,
+                              double *out, int64_t ldm, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);

@@ -43,12 +43,12 @@ static cudaError_t blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool tw
   return masked ? blk_launch<1, true, NT, false>(g, a, blocks, smem, st) : blk_launch<1, false, NT, false>(g, a, blocks, smem, st);
 }
 
-// PAIR mode pays when most neighbours of the cell-key order share their 2-bit cells: about eight points per cell
-// (4^D cells) leave ~6 % of the points to the follow-up launch. ASG_BLOCK_PAIR=0 disables it, =<n> sets the
-// minimum number of points per cell.
+// PAIR mode pays when most neighbours of the cell-key order share their 2-bit cells. Measured on the D = 10
+// benchmark grid (benchmarks/pair_threshold.py, 4^10 cells): break-even at 4 points per cell, 1.09x at 8, 1.13x at 16,
+// 1.18x at 95 (1e8 points). ASG_BLOCK_PAIR=0 disables it, =<n> sets the minimum number of points per cell.
 static double pair_min_per_cell() {  // read per call: the tests switch it between evaluations
   const char *e = getenv("ASG_BLOCK_PAIR");
-  return e ? atof(e) : 8.0;
+  return e ? atof(e) : 5.0;
 }
 bool block_pair_mode(const DeviceGrid &g, int64_t M, bool sorted) {
   if (!sorted || !g.blk_pair_ok || g.D > 15 || pair_min_per_cell() <= 0.0) return false;

@@ -390,18 +390,16 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
     BlkPoint<R, PAIR> pt;
     pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
     static_assert(NT == kBlkThreads, "blk_x_rare assumes the default CTA size");
-    uint32_t inside = 0u;  // bit k: point k lies in the domain
-    uint32_t live = (1u << R) - 1u;  // bit k: point k's result is stored by this launch
+    // flags: bit k: point k lies in the domain; bit 8 + k: point k's result is stored by this launch
+    uint32_t flags = ((1u << R) - 1u) << 8;
     uint32_t code2[R];     // PAIR: the cells of level <= kBlkTab of every dimension (2 bits each)
-    int64_t mms[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       // PAIR: a thread owns two NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
       const int64_t j = PAIR ? base + 2 * (int64_t)tid + k : base + (int64_t)k * NT + tid;
       const int64_t jj = j < M ? j : M - 1;  // tail lanes redo the last point, never store
-      if (j >= M) live &= ~(1u << k);
+      if (j >= M) flags &= ~(0x100u << k);
       const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
-      mms[k] = mm;
       bool in = true;
       uint32_t c2 = 0u;
       for (int d = 0; d < D; ++d) {
@@ -411,7 +409,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
         xs[(d * R + k) * NT + tid] = u;
         if (PAIR) c2 = (c2 << 2) | min((uint32_t)(u * 4.0), 3u);
       }
-      if (in) inside |= 1u << k;
+      if (in) flags |= 1u << k;
       else {  // walked at the centre of the cube; the result is replaced by the exact 0.0
         for (int d = 0; d < D; ++d) xs[(d * R + k) * NT + tid] = 0.5;
         c2 = 0xaaaaaaaau & ((D >= 16) ? 0xffffffffu : ((1u << (2 * D)) - 1u));
@@ -421,9 +419,11 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
     if constexpr (PAIR) {
       if (code2[1] != code2[0]) {
         // not in one cell: this launch evaluates point 0 twice, the follow-up launch takes point 1
-        if (live & 2u) a.left_list[atomicAdd(a.left_count, 1u)] = (uint32_t)mms[1];
-        live &= ~2u;
-        inside = (inside & 1u) * 3u;
+        if (flags & 0x200u) {
+          const int64_t j1 = base + 2 * (int64_t)tid + 1;
+          a.left_list[atomicAdd(a.left_count, 1u)] = a.perm ? a.perm[j1] : (uint32_t)j1;
+        }
+        flags = (flags & 0x100u) | ((flags & 1u) * 3u);
         for (int d = 0; d < D; ++d) xs[(d * R + 1) * NT + tid] = xs[(d * R + 0) * NT + tid];
       }
     }
@@ -485,9 +485,10 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
     }
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      if ((live >> k) & 1u) {
-        const int64_t mm = mms[k];
-        const double v = ((inside >> k) & 1u) ? acc[k] : 0.0;
+      if ((flags >> (8 + k)) & 1u) {
+        const int64_t j = PAIR ? base + 2 * (int64_t)tid + k : base + (int64_t)k * NT + tid;
+        const int64_t mm = a.perm ? (int64_t)a.perm[j] : j;
+        const double v = ((flags >> k) & 1u) ? acc[k] : 0.0;
         a.out[mm] = a.fvals ? (a.fvals[mm] - v) : v;
       }
     }

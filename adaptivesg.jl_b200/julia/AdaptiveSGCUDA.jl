@@ -13,8 +13,10 @@ module AdaptiveSGCUDA
 using SparseArrays, Printf
 
 export SparseGridInterpolant, rsg!, train!, adapt!, coefficients, basis, dehierarchization_matrix,
-       hierarchization_matrix, hierarchize!, extrapolate, serialize, deserialize, maxlevels, sync!, nodedepth, isvalid,
-       allindices_of_level, child, scale, get_x
+       hierarchization_matrix, hierarchize!, extrapolate, serialize, deserialize, maxlevels, sync!
+# every export of the reference's math.jl (src/math.jl:9-22), so that the module can stand in for the package
+export nodedepth, perturb, scale, ϕ, isvalid, get_x, isboundary, boundaryflag, allnodes1d, allindices_of_level, child,
+       parent, ghost_neighbor
 
 const LIB = get(ENV, "ASG_CUDA_LIB", "libasg_cuda")
 
@@ -37,6 +39,21 @@ function init(device::Integer = parse(Int, get(ENV, "ASG_CUDA_DEVICE", "0")))
     check(ccall((:asg_init, LIB), Int32, (Int32,), device))
     _initialised[] = true
 end
+"""
+    init_devices(devices)
+
+One Julia process drives several GPUs of the box (`asg_init_devices`): every grid keeps a replica of its packed
+layouts per device and `evaluate` / `surplus` / `train!` / `hierarchize!` split their points over the devices inside
+the library -- no Distributed.jl, no MPI, no NCCL. `devices[1]` is the primary device. This is what stands in for the
+reference's only parallel entry, `adapt!(...; parallel = true)` (src/train.jl:332-340). `ENV["ASG_CUDA_DEVICES"] =
+"0,1,2,3"` makes the first constructor call do it.
+"""
+function init_devices(devices::AbstractVector{<:Integer})
+    d = Int32.(collect(devices))
+    check(ccall((:asg_init_devices, LIB), Int32, (Ptr{Int32}, Int32), d, length(d)))
+    _initialised[] = true
+end
+_auto_init() = haskey(ENV, "ASG_CUDA_DEVICES") ? init_devices(parse.(Int, split(ENV["ASG_CUDA_DEVICES"], ","))) : init()
 
 # ---------------------------------------------------------------------------------------------
 # node store: same public fields as src/class.jl:281-293, plus the device handle
@@ -60,7 +77,7 @@ mutable struct SparseGridInterpolant{D}
         @assert all(ub .> lb) "Upper bound must be greater than lower bound."
         @assert all(isfinite, lb) "Lower bound must be finite."
         @assert all(isfinite, ub) "Upper bound must be finite."
-        _initialised[] || init()
+        _initialised[] || _auto_init()
         lbv = collect(Float64, lb); ubv = collect(Float64, ub)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:asg_grid_create, LIB), Int32, (Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Ptr{Cvoid}}),
@@ -140,6 +157,80 @@ function child(Ls::AbstractVector{Int}, Is::AbstractVector{Int}, dims::Int; side
     L[dims], I[dims] = child1(L[dims], I[dims], side == :right)
     return (L, I)
 end
+
+# the basis function itself (src/math.jl:332-391): evaluated by the library (asg_phi), bit-identical to the reference's
+# operation order; an invalid (l, i) pair throws ArgumentError like src/math.jl:355
+function _phi(x::Vector{Float64}, L, I, n::Int, D::Int)
+    _initialised[] || _auto_init()
+    out = Vector{Float64}(undef, n)
+    GC.@preserve x L I out check(ccall((:asg_phi, LIB), Int32, (Int64, Int32, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                                       n, D, x, L === nothing ? C_NULL : L, I === nothing ? C_NULL : I, out))
+    return out
+end
+ϕ(x::Float64)::Float64 = _phi([x], nothing, nothing, 1, 1)[1]                                       # src/math.jl:332-334
+ϕ(x::Float64, l::Int, i::Int)::Float64 = _phi([x], Int64[l], Int64[i], 1, 1)[1]                     # src/math.jl:345-357
+function ϕ(x::AbstractVector, levels::AbstractVector, indices::AbstractVector; safe::Bool = false)::Float64  # 376-391
+    D = length(x)
+    if safe
+        @assert length(levels) == D "levels must match the dimension of x."
+        @assert length(indices) == D "indices must match the dimension of x."
+    end
+    return _phi(collect(Float64, x), collect(Int64, levels), collect(Int64, indices), 1, D)[1]
+end
+
+# node arithmetic the reference exports next to it (host-side integer helpers; src/math.jl:516-607, 621-639, 704-879,
+# 1002-1024), written against their documented behaviour
+perturb(Ls, Is, dims::Int, l::Int, i::Int) = (L = collect(Int, Ls); I = collect(Int, Is); L[dims] = l; I[dims] = i; (L, I))
+isboundary(l::Int, i::Int) = l == 2 && (i == 0 || i == 2)
+function boundaryflag(l::Int, i::Int)
+    l == 2 || return 0
+    i == 0 && return -1
+    i == 2 && return 1
+    throw(ArgumentError("invalid level-index pair ($l, $i)"))
+end
+function fraction2li(q::Rational)
+    q == 0 // 1 && return (2, 0)
+    q == 1 // 1 && return (2, 2)
+    q == 1 // 2 && return (1, 1)
+    return (trailing_zeros(q.den) + 1, Int(q.num))
+end
+function allnodes1d(l::Int)
+    l < 1 && throw(ArgumentError("level must be >= 1 but got $l"))
+    l == 1 && return ([1], [1])
+    l == 2 && return ([1, 2, 2], [1, 0, 2])
+    den = power2(l - 1)
+    pairs = [fraction2li(k // den) for k in 0:den]
+    return (first.(pairs), last.(pairs))
+end
+function parent(Ls::AbstractVector{Int}, Is::AbstractVector{Int}, dims::Int)
+    l, i = Ls[dims], Is[dims]
+    inew = l > 3 ? div(i, 4) * 2 + 1 : (l, i) == (3, 1) ? 0 : (l, i) == (3, 3) ? 2 :
+           (l == 2 && (i == 0 || i == 2)) ? 1 : l == 1 ? 0 : throw(ArgumentError("invalid level-index pair ($l, $i)"))
+    return perturb(Ls, Is, dims, l - 1, inew)
+end
+ghost_distance(lmax::Int) = 1.0 / power2(lmax - 1)
+function ghost_neighbor(Ls::AbstractVector{Int}, Is::AbstractVector{Int}, dims::Int, l0::Int, side::Symbol = :left)
+    side in (:left, :right) || throw(ArgumentError("side must be :left or :right"))
+    l0 < 1 && throw(ArgumentError("invalid level $l0"))
+    lj, ij = Ls[dims], Is[dims]; step = side == :left ? -1 : 1; none = (0, -1)
+    if l0 == 1
+        new = none
+    elseif l0 == 2
+        order = [(2, 0), (1, 1), (2, 2)]; k = findfirst(==((lj, ij)), order)
+        new = (k === nothing || !(1 <= k + step <= 3)) ? none : order[k + step]
+    else
+        lj < 1 && throw(ArgumentError("lj<1, invalid input node"))
+        den = power2(l0 - 1)
+        pos = lj == 1 ? (ij == 1 ? den ÷ 2 : throw(ArgumentError("invalid input node"))) :
+              lj == 2 ? (ij == 0 ? 0 : ij == 2 ? den : throw(ArgumentError("invalid input node"))) :
+              lj <= l0 ? ij * power2(l0 - lj) : throw(ArgumentError("lj > l0 found, no grid defined"))
+        k = pos + step
+        new = (k < 0 || k > den) ? none : (lj == 2 && 0 < k < den) ? (l0, k) : fraction2li(k // den)
+    end
+    return perturb(Ls, Is, dims, new[1], new[2])
+end
+get_x(l::Int, i::Int)::Float64 = l > 2 && isodd(i) ? Float64(i / power2(l - 1)) : (l, i) == (2, 0) ? 0.0 : (l, i) == (2, 2) ? 1.0 :
+                                 (l, i) == (1, 1) ? 0.5 : throw(ArgumentError("invalid level-index pair ($l, $i)"))
 
 # ---------------------------------------------------------------------------------------------
 # evaluation: replaces _interpolate / _interpolate_if / _interpolate_until_level / G(x)
@@ -286,8 +377,14 @@ function deserialize(dat::AbstractDict)
     G.levels = dat[:levels]; G.indices = dat[:indices]; G.depths = dat[:depths]; G.fvals = dat[:fvals]; G.coefs = dat[:coefs]
     if haskey(dat, :packed)
         buf = dat[:packed]::Vector{UInt8}
-        rc = GC.@preserve buf ccall((:asg_grid_import, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int64), G.handle, buf, length(buf))
-        rc == 0 ? setfield!(G, :synced, true) : (rc == -6 || check(rc))      # -6 = ASG_EUNSUPPORTED: repack on first use
+        # the blob is installed only if it describes exactly these arrays (serialize aliases them: an in-place update
+        # after the blob was written leaves it stale); -6 = ASG_EUNSUPPORTED (other build), -7 = ASG_ESTATE (stale /
+        # foreign blob): both fall back to the normal upload on first use
+        N = size(G.levels, 1)
+        rc = GC.@preserve buf G ccall((:asg_grid_import_checked, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{UInt8}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ptr{Float64}),
+            G.handle, buf, length(buf), N, G.levels, G.indices, 1, max(N, 1), G.coefs)
+        rc == 0 ? setfield!(G, :synced, true) : (rc in (-6, -7) || check(rc))
     end
     return G
 end

@@ -76,6 +76,8 @@ typedef struct asg_grid_info_t {
   int64_t block_records;   /* its prefix records                                                    */
   int64_t block_tiles;     /* shared-memory tiles the walk streams per batch of points              */
   int64_t block_stack;     /* saved prefix products per point the walk keeps in shared memory       */
+  int64_t block_pair;      /* 1: large ordered batches walk in PAIR mode (two neighbours of the cell-key order per   */
+                           /* thread share their coefficient loads)                                                  */
 } asg_grid_info_t;
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -286,7 +286,7 @@ def test_block_walk_pair_mode(asg, oracle):
         try:
             n0 = asg.launch_count()
             y1 = G.evaluate(X)
-            if G.info()["subspaces"] >= 512:             # (smaller grids skip the point ordering, hence PAIR mode)
+            if G.info()["subspaces"] >= 512 and G.info()["block_pair"] == 1:   # (smaller grids skip the point ordering)
                 assert asg.launch_count() - n0 >= 3      # keys + paired walk + follow-up walk
                 paired += 1
             m1 = G.evaluate(X, max_depth=L)

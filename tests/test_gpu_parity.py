@@ -737,3 +737,51 @@ def test_extrapolate_empty_grid_asserts(asg):
     G = asg.SparseGridInterpolant(2)
     with pytest.raises(AssertionError):
         asg.extrapolate(G, np.array([[1.5, 0.5]]))
+
+
+def test_host_pipeline_pieces_and_layouts():
+    """The host-buffer pipeline (pieces, greedy windows, super-batches; csrc/asg_api.cu eval_super) with tiny piece /
+    super-batch sizes so that a 30 000-point call runs through dozens of pieces and several super-batches: every
+    host layout (row-major, Julia's column-major, D x n, generic strides), surplus, masked, against the oracle and
+    bit-identical to each other."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r)
+import asg_b200 as asg
+from oracle import oracle as o
+D = 5
+OG = o.OracleGrid(D, lb=-np.arange(1, D + 1.0), ub=np.arange(1, D + 1.0))
+OG.train(lambda x: float(np.sum(np.cos(x)) + x[0] * x[3]), 6, 5)
+G = asg.SparseGridInterpolant(D, lb=OG.lb, ub=OG.ub)
+G.levels, G.indices, G.depths, G.fvals, G.coefs = OG.levels, OG.indices, OG.depths, OG.fvals, OG.coefs
+rng = np.random.default_rng(3)
+M = 30011
+X = OG.lb + (OG.ub - OG.lb) * rng.random((M, D))
+X[::501, 1] = 99.0
+want, sc = OG.evaluate(X, return_abssum=True)
+a = G.evaluate(X)
+err = np.abs(a - want)
+assert np.all((err <= 1e-12 * np.abs(want)) | (err <= 1e-14 * np.maximum(1.0, sc)))
+assert np.all(a[::501] == 0.0)
+b = G.evaluate(np.asfortranarray(X))
+c = G.evaluate(np.ascontiguousarray(X.T), dims=2)
+d = G.evaluate(np.repeat(X, 2, axis=1)[:, ::2])
+e = G.evaluate(np.repeat(X, 3, axis=0)[::3])
+assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d) and np.array_equal(a, e)
+f = rng.standard_normal(M)
+assert np.array_equal(G.surplus(X, f), f - a)
+m = G.evaluate(X, max_depth=3)
+wm = OG.evaluate(X, max_depth=3)
+assert np.max(np.abs(m - wm)) < 1e-12
+for path in ("sweep", "stream", "trie"):
+    G.set_path(path)
+    assert np.max(np.abs(G.evaluate(X) - a)) < 1e-12, path
+print("pipeline ok")
+''' % root
+    env = dict(os.environ, ASG_PIPE_PIECE="1000", ASG_PIPE_SUPER="7777")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "pipeline ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -194,3 +194,36 @@ def test_packer_rejects_and_demotes(asg):
         assert rc == 0 and info["canonical"] == 0 and info["path"] == E.ASG_PATH_SWEEP and why in msg, (Lv, msg)
     rc, info, msg = _pack_info(asg, np.ones((1, 13), np.int64), np.ones((1, 13), np.int64))
     assert rc == 0 and info["canonical"] == 0 and "ASG_MAX_DIM_FAST" in msg
+
+
+def test_math_exports_host_helpers(asg, oracle):
+    """The reference exports these next to phi (src/math.jl:9-22); the mirror's versions against the oracle's
+    restatement and the docstring known answers (src/math.jl:513-514, 626-627, 997-999)."""
+    assert [asg.fraction2li(k, 4) for k in range(5)] == [(2, 0), (3, 1), (1, 1), (3, 3), (2, 2)]
+    for l in range(1, 8):
+        assert tuple(map(list, asg.allnodes1d(l))) == tuple(map(list, oracle.allnodes1d(l)))
+    for l, i in [(3, 1), (3, 3), (2, 0), (2, 2), (4, 5), (5, 7), (9, 201), (1, 1)]:
+        L, I = asg.parent([1, l, 1], [1, i, 1], 2)
+        assert (int(L[1]), int(I[1])) == oracle.parent1(l, i)
+    with pytest.raises(ValueError):
+        asg.parent([2], [1], 1)
+    assert asg.isboundary(2, 0) and asg.isboundary(2, 2) and not asg.isboundary(3, 1) and not asg.isboundary(1, 1)
+    assert [asg.boundaryflag(2, 0), asg.boundaryflag(2, 2), asg.boundaryflag(5, 3)] == [-1, 1, 0]
+    with pytest.raises(ValueError):
+        asg.boundaryflag(2, 1)
+    L, I = asg.perturb([1, 2, 3], [1, 0, 3], 2, 4, 5)
+    assert L.tolist() == [1, 4, 3] and I.tolist() == [1, 5, 3]
+    assert asg.get_x(1, 1) == 0.5 and asg.get_x(2, 0) == 0.0 and asg.get_x(2, 2) == 1.0 and asg.get_x(4, 5) == 0.625
+    assert np.array_equal(asg.scale(np.array([1.5, 2.0]), [1.0, 1.0], [2.0, 3.0]), [0.5, 0.5])
+    assert asg.ghost_distance(4) == 0.125
+    # ghost neighbours on the full level-l0 grid: walk the sorted node list of allnodes1d(l0)
+    for l0 in (1, 2, 3, 5):
+        Ls, Is = asg.allnodes1d(l0)
+        nodes = list(zip(Ls, Is)) if l0 != 2 else [(2, 0), (1, 1), (2, 2)]   # allnodes1d(2) lists the root first (math.jl:626-627)
+        for k, (l, i) in enumerate(nodes):
+            for side, step in (("left", -1), ("right", 1)):
+                L, I = asg.ghost_neighbor([l], [i], 1, l0, side)
+                want = nodes[k + step] if 0 <= k + step < len(nodes) else (0, -1)
+                assert (int(L[0]), int(I[0])) == want, (l0, l, i, side)
+    with pytest.raises(ValueError):
+        asg.ghost_neighbor([4], [3], 1, 3)      # node finer than the grid
