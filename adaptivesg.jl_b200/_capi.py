@@ -47,6 +47,7 @@ class GridInfo(C.Structure):
         ("device_bytes", C.c_int64), ("generation", C.c_int64), ("regular", C.c_int64),
         ("block", C.c_int64), ("block_slots", C.c_int64), ("block_records", C.c_int64),
         ("block_tiles", C.c_int64), ("block_stack", C.c_int64), ("block_pair", C.c_int64),
+        ("packs", C.c_int64), ("delta_nodes", C.c_int64),
     ]
 
     def as_dict(self):

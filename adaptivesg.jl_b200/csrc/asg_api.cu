@@ -84,6 +84,21 @@ struct DevBuf {  // grow-only device buffer
     cap = n;
     return ASG_OK;
   }
+  // grow to at least n elements KEEPING the first `keep` (device-to-device copy on `st`, then synchronised)
+  int grow_keep(size_t n, size_t keep, cudaStream_t st) {
+    if (n <= cap) return ASG_OK;
+    T *q = nullptr;
+    const size_t ncap = std::max<size_t>(n, cap + cap / 2 + 64);
+    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    if (e != cudaSuccess) return set_err(ASG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (p && keep) e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(q); return set_err(ASG_ECUDA, std::string("device copy: ") + cudaGetErrorString(e)); }
+    if (p) cudaFree(p);
+    p = q;
+    cap = ncap;
+    return ASG_OK;
+  }
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
@@ -161,6 +176,10 @@ struct asg_grid {
   // host copy of the caller's arrays (row-major N x D): the caller's struct stays the source of truth,
   // this copy exists so append / set_coefs / surplus_nodes need no second pass over caller memory
   int64_t N = 0;
+  // nodes 0 .. N_packed-1 are in the packed layouts; nodes N_packed .. N-1 (appended since, asg_grid_append) only in the
+  // sweep arrays: every evaluation adds their sum on top (run_eval) until the next full pack folds them in
+  int64_t N_packed = 0;
+  int64_t packs = 0;
   std::vector<int64_t> levels, indices;
   std::vector<double> coefs;
   std::vector<int64_t> slot_of_node, bslot_of_node;
@@ -332,6 +351,8 @@ int install_pack(asg_grid *g, PackResult &pk) {
   g->blk_ok = pk.canonical && pk.blk_ok;
   g->blk_why = pk.blk_why;
   g->uploaded = true;
+  g->N_packed = g->N;
+  g->packs++;
   asg_grid_info_t &I = g->info;
   const int64_t gen = I.generation + 1;
   I = asg_grid_info_t{};
@@ -356,6 +377,8 @@ int install_pack(asg_grid *g, PackResult &pk) {
   I.block_tiles = g->blk_ok ? (int64_t)pk.btiles.size() : 0;
   I.block_stack = g->blk_ok ? pk.blk_slots : 0;
   I.block_pair = (g->blk_ok && pk.blk_pair_ok) ? 1 : 0;
+  I.packs = g->packs;
+  I.delta_nodes = 0;
   if (g->blk_ok) I.device_bytes += (int64_t)(R.d_bcoef.bytes() + R.d_brec.bytes() + R.d_btiles.bytes());
   return ASG_OK;
 }
@@ -443,9 +466,27 @@ int run_eval(asg_grid *g, int r, const EvalArgs &a_in, cudaStream_t st, int slot
   else if (g->walk() == 0) e = launch_eval_stream(R.dg, a, st, &l);
   else if (g->walk() == 1) e = launch_eval_rsg(R.dg, g->rp, a, st, &l);
   else e = launch_eval_subspace(R.dg, a, st, &l);
+  if (e == cudaSuccess && g->path() == ASG_PATH_SUBSPACE && g->N_packed < g->N) {
+    // nodes appended since the last pack: their sum goes on top of the packed layouts' result
+    EvalArgs b = a_in;
+    b.n_first = g->N_packed;
+    b.accumulate = 1;
+    e = launch_eval_sweep(R.dg, b, st, &l);
+  }
   bump(l);
   CK(e);
   return ASG_OK;
+}
+
+// Fold appended nodes into the packed layouts when the extra sweep over them would cost more than it saves:
+// M points x delta nodes x D hat evaluations against a host pack of tens to hundreds of milliseconds.
+int consolidate(asg_grid *g) {
+  if (g->uploaded && g->N_packed < g->N) return repack(g);
+  return ASG_OK;
+}
+int maybe_consolidate(asg_grid *g, int64_t M) {
+  const double work = (double)M * (double)(g->N - g->N_packed) * g->D;
+  return work > 4e10 ? consolidate(g) : ASG_OK;
 }
 
 // Stage rows [m0, m0+cnt) of a strided host matrix into a dense device block and return the device
@@ -841,6 +882,92 @@ int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int
   return repack(g);
 }
 
+// adapt! appends children of the deepest nodes (src/train.jl:283, 434-438). Such rows cannot repeat a node the grid
+// holds (depth is a function of the level vector), so if they are canonical, finite and distinct they can join the
+// sweep arrays without touching the packed layouts. Returns false when the full pack is needed.
+static bool delta_rows_ok(const asg_grid *g, int64_t N0, int64_t n) {
+  if (!g->uploaded || !g->canonical || !g->finite || g->N_packed <= 0 || g->forced_path == ASG_PATH_SWEEP) return false;
+  static const bool off = getenv("ASG_APPEND_FULL_PACK") != nullptr;  // experiment knob: the round-1 behaviour
+  if (off) return false;
+  const int D = g->D;
+  const int64_t delta = N0 + n - g->N_packed;
+  if (delta > std::max<int64_t>(8192, g->N_packed / 2)) return false;
+  std::vector<int64_t> order((size_t)n);
+  for (int64_t k = 0; k < n; ++k) {
+    order[(size_t)k] = k;
+    int64_t dsum = 0;
+    for (int d = 0; d < D; ++d) {
+      const int64_t l = g->levels[(size_t)(N0 + k) * D + d], i = g->indices[(size_t)(N0 + k) * D + d];
+      if (l < 1 || l > kMaxLevelFast) return false;
+      if (l == 1 ? i != 1 : (l == 2 ? (i != 0 && i != 2) : (i < 1 || !(i & 1) || i > ((int64_t)1 << (l - 1)) - 1))) return false;
+      dsum += l;
+    }
+    if (dsum - D + 1 <= g->info.max_depth) return false;  // could repeat an existing node
+    if (!std::isfinite(g->coefs[(size_t)(N0 + k)])) return false;
+  }
+  const int64_t *L = g->levels.data() + (size_t)N0 * D, *I = g->indices.data() + (size_t)N0 * D;
+  auto cmp = [&](int64_t a, int64_t b) {
+    for (int d = 0; d < D; ++d) {
+      if (L[a * D + d] != L[b * D + d]) return L[a * D + d] < L[b * D + d];
+      if (I[a * D + d] != I[b * D + d]) return I[a * D + d] < I[b * D + d];
+    }
+    return false;
+  };
+  std::sort(order.begin(), order.end(), cmp);
+  for (int64_t k = 1; k < n; ++k)
+    if (!cmp(order[(size_t)k - 1], order[(size_t)k]) && !cmp(order[(size_t)k], order[(size_t)k - 1])) return false;  // repeated row
+  return true;
+}
+
+static int append_delta(asg_grid *g, int64_t N0, int64_t n) {
+  const int D = g->D;
+  std::vector<SweepDim> sw((size_t)n * D);
+  std::vector<uint64_t> low((size_t)n, 0);
+  std::vector<int32_t> depth((size_t)n);
+  int max_level = g->info.max_level;
+  int64_t max_depth = g->info.max_depth;
+  for (int64_t k = 0; k < n; ++k) {
+    int64_t dsum = 0;
+    for (int d = 0; d < D; ++d) {  // the (s, c) pairs of asg_pack.cpp: phi = hat(x * s - c)
+      const int64_t l = g->levels[(size_t)(N0 + k) * D + d], i = g->indices[(size_t)(N0 + k) * D + d];
+      SweepDim &q = sw[(size_t)k * D + d];
+      if (l == 1) { q.s = 0.0; q.c = 0.0; low[(size_t)k] |= 1ull << d; }
+      else { q.s = std::ldexp(1.0, (int)(l - 1)); q.c = (double)i; if (l == 2) low[(size_t)k] |= 1ull << d; }
+      dsum += l;
+      max_level = std::max(max_level, (int)l);
+    }
+    depth[(size_t)k] = (int32_t)(dsum - D + 1);
+    max_depth = std::max<int64_t>(max_depth, dsum - D + 1);
+  }
+  const int64_t N1 = N0 + n;
+  for (int r = 0; r < ctx.ndev; ++r) {
+    if (int rc = use_dev(r)) return rc;
+    USE_REPLICA(g, r);
+    cudaStream_t st = dc.stream;
+    if (int rc = R.d_sw.grow_keep((size_t)N1 * D, (size_t)N0 * D, st)) return rc;
+    if (int rc = R.d_sw_low.grow_keep((size_t)N1, (size_t)N0, st)) return rc;
+    if (int rc = R.d_sw_coef.grow_keep((size_t)N1, (size_t)N0, st)) return rc;
+    if (int rc = R.d_sw_depth.grow_keep((size_t)N1, (size_t)N0, st)) return rc;
+    CK(cudaMemcpyAsync(R.d_sw.p + (size_t)N0 * D, sw.data(), sw.size() * sizeof(SweepDim), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_low.p + N0, low.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_coef.p + N0, g->coefs.data() + N0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(R.d_sw_depth.p + N0, depth.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    R.dg.sw = R.d_sw.p;
+    R.dg.sw_low = R.d_sw_low.p;
+    R.dg.sw_coef = R.d_sw_coef.p;
+    R.dg.sw_depth = R.d_sw_depth.p;
+    R.dg.N = N1;
+  }
+  if (int rc = use_dev(0)) return rc;
+  g->info.N = N1;
+  g->info.max_level = max_level;
+  g->info.max_depth = max_depth;
+  g->info.delta_nodes = N1 - g->N_packed;
+  g->info.generation++;
+  return ASG_OK;
+}
+
 int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                         int64_t sd, const double *coefs) {
   ASG_TRACE();
@@ -848,10 +975,23 @@ int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int
   if (n < 0 || (n > 0 && (!levels || !indices))) return set_err(ASG_EINVAL, "bad node arrays");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (n == 0) return ASG_OK;
   const int64_t N0 = g->N;
   copy_nodes(g, N0, n, levels, indices, sn, sd, coefs);
+  int rc;
+  if (delta_rows_ok(g, N0, n)) {
+    rc = append_delta(g, N0, n);
+    if (rc != ASG_OK) {  // device trouble: the host arrays shrink back; the packed layouts were never touched
+      g->N = N0;
+      g->levels.resize((size_t)N0 * g->D);
+      g->indices.resize((size_t)N0 * g->D);
+      g->coefs.resize((size_t)N0);
+      for (int r = 0; r < ctx.ndev; ++r) g->rep[r].dg.N = N0;
+    }
+    return rc;
+  }
   g->uploaded = false;
-  int rc = repack(g);
+  rc = repack(g);
   if (rc != ASG_OK) {  // roll back: the reference would not have grown the grid either
     g->N = N0;
     g->levels.resize((size_t)N0 * g->D);
@@ -878,13 +1018,15 @@ static int scatter_coefs_locked(asg_grid *g, int64_t n, const int64_t *idx, int6
       if (!std::isfinite(coefs[k])) g->finite = false;
     }
     if (g->canonical) {
+      if (node >= g->N_packed) { slots[(size_t)k] = LLONG_MIN; continue; }  // appended, not packed yet: sweep arrays only
       slots[(size_t)k] = g->slot_of_node[(size_t)node];
       (slots[(size_t)k] < 0 ? any_hash : any_dense) = true;
     }
   }
   if (g->canonical && g->blk_ok) {  // the BLOCK layout holds its own copy of the coefficients
     bslots.resize((size_t)n);
-    for (int64_t k = 0; k < n; ++k) bslots[(size_t)k] = g->bslot_of_node[(size_t)nodes[(size_t)k]];
+    for (int64_t k = 0; k < n; ++k)
+      bslots[(size_t)k] = nodes[(size_t)k] >= g->N_packed ? -1 : g->bslot_of_node[(size_t)nodes[(size_t)k]];
   }
   int64_t l = 0;
   for (int r = 0; r < ctx.ndev; ++r) {
@@ -967,6 +1109,8 @@ int32_t asg_grid_info(asg_grid *g, asg_grid_info_t *info) {
   *info = g->info;
   info->D = g->D;
   info->N = g->N;
+  info->packs = g->packs;
+  info->delta_nodes = g->uploaded ? g->N - g->N_packed : 0;
   info->path = g->uploaded ? g->path() : 0;
   return ASG_OK;
 }
@@ -989,6 +1133,7 @@ int32_t asg_eval(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sd
   if (int rc = check_eval_args(g, X, M, out)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = maybe_consolidate(g, M)) return rc;
   return eval_host(g, X, M, sp, sdim, nullptr, max_depth, out);
 }
 
@@ -999,6 +1144,7 @@ int32_t asg_surplus(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t
   if (M > 0 && !fvals) return set_err(ASG_EINVAL, "null fvals");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = maybe_consolidate(g, M)) return rc;
   return eval_host(g, X, M, sp, sdim, fvals, max_depth, alpha);
 }
 
@@ -1038,6 +1184,7 @@ int32_t asg_eval_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, in
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = maybe_consolidate(g, M)) return rc;
   return eval_device_common(g, dX, M, sp, sdim, nullptr, max_depth, dout, stream);
 }
 
@@ -1048,6 +1195,7 @@ int32_t asg_surplus_device(asg_grid *g, const double *dX, int64_t M, int64_t sp,
   if (M > 0 && !dfvals) return set_err(ASG_EINVAL, "null fvals");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = maybe_consolidate(g, M)) return rc;
   return eval_device_common(g, dX, M, sp, sdim, dfvals, max_depth, dalpha, stream);
 }
 
@@ -1218,6 +1366,7 @@ int32_t asg_surplus_nodes(asg_grid *g, int64_t n, const int64_t *idx, const doub
     std::memcpy(&L[(size_t)k * D], &g->levels[(size_t)idx[k] * D], (size_t)D * 8);
     std::memcpy(&I[(size_t)k * D], &g->indices[(size_t)idx[k] * D], (size_t)D * 8);
   }
+  if (int rc = maybe_consolidate(g, n)) return rc;
   // the nodes of one depth are independent query points: split them over the devices like asg_eval does
   const int nd = (int)std::min<int64_t>(ctx.ndev, std::max<int64_t>(1, n / multi_dev_min()));
   if (nd <= 1) {
@@ -1412,6 +1561,7 @@ int32_t asg_basis_count(asg_grid *g, const double *X, int64_t M, int64_t sp, int
   if (int rc = check_eval_args(g, X, M, row_nnz)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = consolidate(g)) return rc;  // appended nodes join the packed layouts first
   USE_REPLICA(g, 0);
   if (M == 0) return ASG_OK;
   cudaStream_t st = dc.stream;
@@ -1432,6 +1582,7 @@ int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int6
   if (int rc = check_eval_args(g, X, M, row_ptr)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = consolidate(g)) return rc;  // appended nodes join the packed layouts first
   USE_REPLICA(g, 0);
   if (M == 0) return ASG_OK;
   const int64_t nnz = row_ptr[M];
@@ -1466,6 +1617,7 @@ int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, 
   if (!colptr) return set_err(ASG_EINVAL, "null colptr");
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = consolidate(g)) return rc;  // appended nodes join the packed layouts first
   USE_REPLICA(g, 0);
   const int64_t N = g->N;
   if (M == 0) {
@@ -1519,6 +1671,7 @@ int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t
   if (int rc = check_eval_args(g, dX, M, dout)) return rc;
   if (int rc = require_ctx()) return rc;
   std::lock_guard<std::recursive_mutex> lk(g->mu);
+  if (int rc = consolidate(g)) return rc;  // appended nodes join the packed layouts first
   if (M == 0 || g->N == 0) return ASG_OK;
   if (replica_of_pointer(dX) != 0) return set_err(ASG_EINVAL, "basis entry points run on the primary device of the context");
   USE_REPLICA(g, 0);
@@ -1656,6 +1809,10 @@ int32_t asg_grid_export(asg_grid *g, void *buf, int64_t capacity, int64_t *bytes
   if (!g || !bytes) return set_err(ASG_EINVAL, "null argument");
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   if (!g->uploaded) return set_err(ASG_ESTATE, "no nodes uploaded");
+  if (ctx.ready && g->N_packed < g->N) {
+    if (int rc = require_ctx()) return rc;
+    if (int rc = consolidate(g)) return rc;
+  }
   if (g->blob_generation != g->info.generation || g->blob.empty()) {
     PackResult pk;
     std::string err;

@@ -213,6 +213,10 @@ struct EvalArgs {
   uint32_t *left_list = nullptr;
   uint32_t *left_count = nullptr;
   const uint32_t *M_dev = nullptr;
+  // sweep engine only: nodes n_first .. N-1, and accumulate != 0 ADDS their sum to what `out` already holds
+  // (out += G_delta, or out -= G_delta for a surplus): the appended-but-not-yet-packed nodes of adapt! (asg_grid_append)
+  int64_t n_first = 0;
+  int accumulate = 0;
 };
 struct BasisArgs {
   const double *X;

@@ -1,6 +1,8 @@
 // asg_kernels_misc.cu -- small kernels around the hot path (sm_100a):
 //   node coordinates (get_x / stack, src/math.jl:464-497, src/class.jl:375-387),
 //   coefficient scatter (G.coefs[i] = alpha, src/train.jl:183), CSR row sort, FP64 peak probe.
+#include <climits>
+
 #include "asg_internal.h"
 
 namespace asg {
@@ -98,7 +100,7 @@ __global__ void k_scatter_f64(double *dst, const long long *slots, const double 
 }
 __global__ void k_scatter_hash(HashEnt *dst, const long long *slots, const double *src, int64_t n) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    if (slots[k] < 0) dst[-slots[k] - 1].coef = src[k];
+    if (slots[k] < 0 && slots[k] != LLONG_MIN) dst[-slots[k] - 1].coef = src[k];  // LLONG_MIN: node not in the packed layouts
 }
 
 static int blocks_for(int64_t n) {

@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_eval_sweep(const DeviceGrid g
     PointRegs<DT> p;
     load_point_sweep<DT>(g, a.X, m, active, a.sp, a.sd, D, p);
     double acc = 0.0;
-    for (int64_t n0 = 0; n0 < g.N; n0 += kSweepTile) {
+    for (int64_t n0 = a.n_first; n0 < g.N; n0 += kSweepTile) {
       const int cnt = (int)((g.N - n0) < kSweepTile ? (g.N - n0) : kSweepTile);
       __syncthreads();
       load_tile(g, t, n0, cnt, D);
@@ -110,7 +110,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_eval_sweep(const DeviceGrid g
         acc += node_product<DT>(t.sd + (size_t)k * D, t.low[k], t.coef[k], p, D);
       }
     }
-    if (active) a.out[m] = a.fvals ? (a.fvals[m] - acc) : acc;
+    if (active) {
+      if (a.accumulate) a.out[m] = a.fvals ? (a.out[m] - acc) : (a.out[m] + acc);  // on top of the packed nodes' result
+      else a.out[m] = a.fvals ? (a.fvals[m] - acc) : acc;
+    }
   }
 }
 

@@ -78,6 +78,9 @@ typedef struct asg_grid_info_t {
   int64_t block_stack;     /* saved prefix products per point the walk keeps in shared memory       */
   int64_t block_pair;      /* 1: large ordered batches walk in PAIR mode (two neighbours of the cell-key order per   */
                            /* thread share their coefficient loads)                                                  */
+  int64_t packs;           /* full host packs (validate + sort + pack + upload) this handle has done so far           */
+  int64_t delta_nodes;     /* nodes appended since the last pack: evaluated on top of the packed layouts by the sweep */
+                           /* kernel until the next pack folds them in (asg_grid_append)                              */
 } asg_grid_info_t;
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -115,7 +118,12 @@ int32_t asg_grid_destroy(asg_grid *g); /* safe from any thread (Julia finalizer)
  * l < 1 or (l == 2 and i not in {0,2}) -> ASG_EINVALID_NODE. Depths are derived (math.jl:103-108). */
 int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int64_t *indices, int64_t sn,
                         int64_t sd, const double *coefs);
-/* vcat of new rows (adapt!, src/train.jl:434-438) */
+/* vcat of new rows (adapt!, src/train.jl:434-438). Rows that are deeper than every node the grid holds (what adapt!
+ * appends: children of the deepest nodes), canonical and finite are NOT packed at once: they join the sweep arrays on
+ * the device and every evaluation adds their sum to the packed layouts' result (same nodes, same products; only the
+ * order of the final additions differs). The next full pack -- when they exceed half of the packed nodes (8192 at
+ * least), before a batch large enough for the extra sweep to cost more than packing, before basis / export -- folds
+ * them in. An adapt! loop therefore packs once, not once per level. Any other rows trigger a full pack at once. */
 int32_t asg_grid_append(asg_grid *g, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                         int64_t sd, const double *coefs);
 /* G.coefs[first .. first+n-1] = coefs  (0-based node numbers; train!, src/train.jl:183) */

@@ -785,3 +785,71 @@ print("pipeline ok")
     env = dict(os.environ, ASG_PIPE_PIECE="1000", ASG_PIPE_SUPER="7777")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "pipeline ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_append_without_repacking(asg, oracle):
+    """asg_grid_append (adapt!, src/train.jl:434-438): rows deeper than every node of the grid join the sweep arrays
+    and are evaluated on top of the packed layouts; the packs happen when the appended part has grown large, before
+    large batches and before basis / export -- not once per level. Same node set as the oracle's adapt!, same values."""
+    OG = oracle.OracleGrid(2)
+    OG.train(utility, 4, (3, 8))
+    OG.adapt(utility, 20, tol=1e-5)
+    G = asg.SparseGridInterpolant(2)
+    asg.train(G, utility, 4, (3, 8))
+    p0 = G.info()["packs"]
+    log = []
+    asg.adapt(G, utility, 20, tol=1e-5, verbose=False, log=log)
+    info = G.info()
+    levels_added = sum(1 for e in log if e.get("added"))
+    assert levels_added >= 10
+    assert info["packs"] - p0 <= 3 < levels_added           # round 1: one pack per level
+    assert len(G) == len(OG) == 12119
+    ko = np.lexsort(np.hstack([OG.levels, OG.indices]).T[::-1])
+    kg = np.lexsort(np.hstack([G.levels, G.indices]).T[::-1])
+    assert np.array_equal(OG.levels[ko], G.levels[kg]) and np.array_equal(OG.indices[ko], G.indices[kg])
+    assert np.max(np.abs(OG.coefs[ko] - G.coefs[kg])) <= 1e-12
+    # evaluation with appended nodes still outside the packed layouts: every engine, masked, surplus
+    rng = np.random.default_rng(17)
+    X = np.vstack([rng.random((5000, 2)), _edge_points(2, OG.lb, OG.ub, rng)])
+    H = asg.SparseGridInterpolant(2)
+    asg.train(H, utility, 4, (3, 8))
+    asg.adapt(H, utility, 12, tol=1e-5, verbose=False)       # stops early: a few hundred appended nodes, no pack since
+    assert H.info()["delta_nodes"] > 0
+    OH = oracle.OracleGrid(2)
+    OH.train(utility, 4, (3, 8))
+    OH.adapt(utility, 12, tol=1e-5)
+    assert len(H) == len(OH)
+    k1 = np.lexsort(np.hstack([OH.levels, OH.indices]).T[::-1])
+    k2 = np.lexsort(np.hstack([H.levels, H.indices]).T[::-1])
+    OH.levels, OH.indices, OH.depths, OH.coefs, OH.fvals = H.levels, H.indices, H.depths, H.coefs, H.fvals  # same order as H
+    want, sc = OH.evaluate(X, return_abssum=True)
+    for path in ("auto", "trie", "stream", "sweep"):
+        H.set_path(path)
+        assert_close(H.evaluate(X), want, sc, f"appended nodes, {path}")
+        assert_close(H.evaluate(X, max_depth=9), OH.evaluate(X, max_depth=9), sc, f"appended nodes, masked, {path}")
+    H.set_path("auto")
+    f = rng.standard_normal(len(X))
+    assert_close(H.surplus(X, f), f - want, sc + np.abs(f), "appended nodes, surplus")
+    assert H.info()["delta_nodes"] > 0                       # none of this packed
+    # coefficient updates reach appended nodes
+    nd = H.info()["delta_nodes"]
+    idx = np.arange(len(H) - nd, len(H), dtype=np.int64)[::3]
+    vals = np.ascontiguousarray(rng.standard_normal(len(idx)))
+    lib = asg._capi.load()
+    asg._capi.check(lib.asg_grid_scatter_coefs(H._ensure(), len(idx), idx.ctypes.data_as(asg._capi.i64p),
+                                               vals.ctypes.data_as(asg._capi.f64p)))
+    H.coefs[idx] = vals
+    OH.coefs = H.coefs
+    want2, sc2 = OH.evaluate(X, return_abssum=True)
+    assert_close(H.evaluate(X), want2, sc2, "appended nodes after scatter_coefs")
+    # basis folds them in first; the matrix then has a column for every node
+    B = asg.basis(X[:200], H)
+    assert H.info()["delta_nodes"] == 0 and B.shape == (200, len(H))
+    assert_close(B @ H.coefs, want2[:200], sc2[:200], "basis after the fold")
+    assert_close(H.evaluate(X), want2, sc2, "after the fold")
+    # rows that are NOT deeper than the grid (possible repeats) take the full pack at once, like before
+    p1 = H.info()["packs"]
+    asg._capi.check(lib.asg_grid_append(H._ensure(), 1, np.array([[2, 1]], dtype=np.int64).ctypes.data_as(asg._capi.i64p),
+                                        np.array([[0, 1]], dtype=np.int64).ctypes.data_as(asg._capi.i64p), 2, 1,
+                                        np.array([0.5]).ctypes.data_as(asg._capi.f64p)))
+    assert H.info()["packs"] == p1 + 1 and H.info()["canonical"] == 0      # a repeated node: the sweep engine takes over
