@@ -90,6 +90,8 @@ SIGNATURES = {
     "asg_basis_count": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, i64p],
     "asg_basis_fill": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, i64p, i64p, f64p],
     "asg_basis_fill_csc": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, i64p, i64p, i64p, f64p],
+    "asg_basis_fill_csc32": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, i64p, C.POINTER(C.c_int32),
+                             C.POINTER(C.c_int32), f64p],
     "asg_basis_dense": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, vp, C.c_int64, C.c_int64],
     "asg_basis_dense_device": [vp, vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, vp, C.c_int64,
                                C.c_int64, vp],

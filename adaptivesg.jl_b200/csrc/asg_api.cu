@@ -38,6 +38,11 @@ struct DevCtx {  // per device: streams and events of this library
   cudaEvent_t evw0 = nullptr, evw1 = nullptr;    // around its walk kernel alone (BLOCK walk: after the point ordering)
   bool walk_timed = false;
   bool last_timed = false;
+  // pinned staging of large device -> PAGEABLE host copies (d2h_fast)
+  static constexpr int kStage = 4;
+  void *stage[kStage] = {};
+  cudaEvent_t stage_ev[kStage] = {};
+  std::mutex stage_mu;
 };
 
 struct Context {
@@ -273,6 +278,7 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
       off += r.size();
     }
     dg.n_root = (uint32_t)(pk.rec[0].size() - 1);
+    dg.n_level1 = D >= 2 ? (uint32_t)(pk.rec[1].size() - 1) : 0u;
     if (int rc = R.d_coef.reserve(pk.coef.size())) return rc;
     if (int rc = R.d_orig.reserve(pk.orig.size())) return rc;
     if (int rc = R.d_hent.reserve(pk.hent.size())) return rc;
@@ -703,6 +709,62 @@ int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim,
   return use_dev(0);
 }
 
+// Device -> host copy of a LARGE result (basis matrices: hundreds of MB) that also runs at PCIe speed when the
+// destination is ordinary pageable memory (a numpy array, a Julia Vector). cudaMemcpy to pageable memory goes through
+// the driver's own staging at ~5 GB/s on this platform; here the data comes home in 16 MiB pieces through four pinned
+// buffers and four host threads move the pieces to their destination in parallel (~25 GB/s). Blocks until done; work
+// queued on `st` before the call is waited for like cudaMemcpy would. Pinned destinations take the direct path.
+int d2h_fast(DevCtx &dc, void *dst, const void *dsrc, size_t bytes, cudaStream_t st) {
+  constexpr size_t kPiece = (size_t)16 << 20;
+  if (bytes == 0) return ASG_OK;
+  cudaPointerAttributes at;
+  const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned || bytes < 4 * kPiece) {
+    CK(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return ASG_OK;
+  }
+  std::lock_guard<std::mutex> lk(dc.stage_mu);
+  constexpr int K = DevCtx::kStage;
+  for (int k = 0; k < K; ++k) {
+    if (!dc.stage[k]) CK(cudaHostAlloc(&dc.stage[k], kPiece, cudaHostAllocDefault));
+    if (!dc.stage_ev[k]) CK(cudaEventCreateWithFlags(&dc.stage_ev[k], cudaEventDisableTiming));
+  }
+  const int64_t np = (int64_t)((bytes + kPiece - 1) / kPiece);
+  std::atomic<int64_t> issued{0};
+  std::atomic<int64_t> done[K];
+  for (int k = 0; k < K; ++k) done[k] = 0;  // pieces of buffer k that have reached their destination
+  std::atomic<int> failed{0};
+  const int device = dc.device;
+  std::vector<std::thread> th;
+  for (int k = 0; k < K; ++k)
+    th.emplace_back([&, k]() {
+      cudaSetDevice(device);
+      for (int64_t c = k; c < np; c += K) {
+        while (issued.load(std::memory_order_acquire) <= c && !failed.load()) std::this_thread::yield();
+        if (failed.load()) return;
+        if (cudaEventSynchronize(dc.stage_ev[k]) != cudaSuccess) { failed = 1; return; }
+        const size_t off = (size_t)c * kPiece, n = std::min(kPiece, bytes - off);
+        std::memcpy((char *)dst + off, dc.stage[k], n);
+        done[k].fetch_add(1, std::memory_order_release);
+      }
+    });
+  cudaError_t e = cudaSuccess;
+  for (int64_t c = 0; c < np && e == cudaSuccess && !failed.load(); ++c) {
+    const int k = (int)(c % K);
+    while (done[k].load(std::memory_order_acquire) < c / K && !failed.load()) std::this_thread::yield();  // buffer k is free again
+    const size_t off = (size_t)c * kPiece, n = std::min(kPiece, bytes - off);
+    e = cudaMemcpyAsync(dc.stage[k], (const char *)dsrc + off, n, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaEventRecord(dc.stage_ev[k], st);
+    if (e == cudaSuccess) issued.store(c + 1, std::memory_order_release);
+  }
+  if (e != cudaSuccess) failed = 1;
+  for (auto &t : th) t.join();
+  if (e != cudaSuccess || failed.load()) return set_err(ASG_ECUDA, std::string("device -> host copy: ") + cudaGetErrorString(e));
+  return ASG_OK;
+}
+
 int check_eval_args(asg_grid *g, const void *X, int64_t M, const void *out) {
   if (!g) return set_err(ASG_EINVAL, "null grid handle");
   if (M < 0) return set_err(ASG_EINVAL, "M < 0");
@@ -760,7 +822,6 @@ static int init_locked(const int32_t *devices, int32_t ndev) {
   }
   for (int r = 0; r < ndev; ++r) {
     DevCtx &dc = ctx.dev[r];
-    dc = DevCtx{};
     dc.device = devices[r];
     CK(cudaSetDevice(dc.device));
     CK(cudaStreamCreateWithFlags(&dc.stream, cudaStreamNonBlocking));
@@ -808,7 +869,15 @@ int32_t asg_shutdown(void) {
     cudaEventDestroy(dc.ev1);
     cudaEventDestroy(dc.evw0);
     cudaEventDestroy(dc.evw1);
-    dc = DevCtx{};
+    for (int k = 0; k < DevCtx::kStage; ++k) {
+      if (dc.stage[k]) cudaFreeHost(dc.stage[k]);
+      if (dc.stage_ev[k]) cudaEventDestroy(dc.stage_ev[k]);
+      dc.stage[k] = nullptr;
+      dc.stage_ev[k] = nullptr;
+    }
+    dc.device = -1;
+    dc.stream = nullptr;
+    dc.walk_timed = dc.last_timed = false;
   }
   ctx.ready = false;
   ctx.ndev = 0;
@@ -1603,16 +1672,15 @@ int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int6
     bump(l);
   }
   if (nnz) {
-    CK(cudaMemcpyAsync(colidx, R.s_i64b.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vals, R.s_tmp.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
+    if (int rc = d2h_fast(dc, colidx, R.s_i64b.p, (size_t)nnz * 8, st)) return rc;
+    if (int rc = d2h_fast(dc, vals, R.s_tmp.p, (size_t)nnz * 8, st)) return rc;
   }
   CK(cudaStreamSynchronize(st));
   return ASG_OK;
 }
 
-int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
-                           int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals) {
-  ASG_TRACE();
+static int basis_fill_csc_common(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                                 int32_t dropzeros, const int64_t *row_ptr, void *colptr, void *rowidx, double *vals, bool narrow) {
   if (int rc = check_eval_args(g, X, M, row_ptr)) return rc;
   if (!colptr) return set_err(ASG_EINVAL, "null colptr");
   if (int rc = require_ctx()) return rc;
@@ -1621,7 +1689,8 @@ int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, 
   USE_REPLICA(g, 0);
   const int64_t N = g->N;
   if (M == 0) {
-    for (int64_t c = 0; c <= N; ++c) colptr[c] = 0;
+    for (int64_t c = 0; c <= N; ++c)
+      if (narrow) ((int32_t *)colptr)[c] = 0; else ((int64_t *)colptr)[c] = 0;
     return ASG_OK;
   }
   const int64_t nnz = row_ptr[M];
@@ -1654,15 +1723,40 @@ int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, 
   int64_t l = 0;
   CK(csr_to_csc(R.s_i64a.p, R.s_i64b.p, R.s_tmp.p, M, N, nnz, R.s_key[0].p, R.s_key2[0].p, R.s_idx[0].p,
                 R.s_perm[0].p, R.s_key[1].p, R.s_sorttmp[0].p, tb, d_colptr.p, d_rowidx.p, R.s_tmp2.p, st, &l));
-  bump(l);
-  CK(cudaMemcpyAsync(colptr, d_colptr.p, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, st));
-  if (nnz) {
-    CK(cudaMemcpyAsync(rowidx, d_rowidx.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(vals, R.s_tmp2.p, (size_t)nnz * 8, cudaMemcpyDeviceToHost, st));
-  }
-  CK(cudaStreamSynchronize(st));
   g->ch_n = -1;  // the adapt! scratch was reused
+  if (narrow) {  // 32-bit indices: the CSR column scratch (free now) takes the narrowed copies
+    if (int rc = R.s_idx[1].reserve((size_t)N + 1)) return rc;
+    int *n_colptr = reinterpret_cast<int *>(R.s_idx[1].p);
+    int *n_rowidx = reinterpret_cast<int *>(R.s_i64b.p);
+    CK(launch_narrow_i64(d_colptr.p, n_colptr, N + 1, st, &l));
+    CK(launch_narrow_i64(d_rowidx.p, n_rowidx, nnz, st, &l));
+    bump(l);
+    if (int rc = d2h_fast(dc, colptr, n_colptr, (size_t)(N + 1) * 4, st)) return rc;
+    if (nnz)
+      if (int rc = d2h_fast(dc, rowidx, n_rowidx, (size_t)nnz * 4, st)) return rc;
+  } else {
+    bump(l);
+    if (int rc = d2h_fast(dc, colptr, d_colptr.p, (size_t)(N + 1) * 8, st)) return rc;
+    if (nnz)
+      if (int rc = d2h_fast(dc, rowidx, d_rowidx.p, (size_t)nnz * 8, st)) return rc;
+  }
+  if (nnz)
+    if (int rc = d2h_fast(dc, vals, R.s_tmp2.p, (size_t)nnz * 8, st)) return rc;
+  CK(cudaStreamSynchronize(st));
   return ASG_OK;
+}
+
+int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                           int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals) {
+  ASG_TRACE();
+  return basis_fill_csc_common(g, X, M, sp, sdim, atol, dropzeros, row_ptr, colptr, rowidx, vals, false);
+}
+
+int32_t asg_basis_fill_csc32(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                             int32_t dropzeros, const int64_t *row_ptr, int32_t *colptr, int32_t *rowidx, double *vals) {
+  ASG_TRACE();
+  if (g && g->N >= ((int64_t)1 << 31) - 1) return set_err(ASG_EUNSUPPORTED, "N >= 2^31: use asg_basis_fill_csc");
+  return basis_fill_csc_common(g, X, M, sp, sdim, atol, dropzeros, row_ptr, colptr, rowidx, vals, true);
 }
 
 int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t sp, int64_t sdim, double atol,
@@ -1679,44 +1773,20 @@ int32_t asg_basis_dense_device(asg_grid *g, const double *dX, int64_t M, int64_t
   BasisArgs a{};
   a.X = dX; a.M = M; a.sp = sp; a.sd = sdim; a.atol = atol; a.dropzeros = dropzeros; a.mode = 2;
   a.dense = dout; a.ldm = ldm; a.ldn = ldn;
-  // (measured on cfg5, 18.7 GB: memset + scatter 4.20 ms, CSR + one streaming pass 4.81 ms -- the count and fill
-  // passes cost more than the second pass over the output saves; ASG_DENSE_ONE_PASS=1 selects the streaming path)
-  static const bool two_pass = getenv("ASG_DENSE_ONE_PASS") == nullptr;
+  static const bool no_split = getenv("ASG_DENSE_NO_SPLIT") != nullptr;  // experiment knob: one thread per row (round 1)
   CK(cudaEventRecord(dc.ev0, st));
   if (g->path() == ASG_PATH_SUBSPACE) {
+    // the walk only visits supporting nodes: clear first (needs a dense M x N block), then scatter
     const bool rowmajor = (ldn == 1 && ldm >= g->N), colmajor = (ldm == 1 && ldn >= M);
-    if (rowmajor && !two_pass && M < ((int64_t)1 << 31)) {
-      // One streaming pass over the output: the rows are formed in CSR form first (count, scan, fill: at most one
-      // entry per subspace and row, a few per cent of the output's bytes) and k_dense_rows then writes every output
-      // byte exactly once with 16-byte streaming stores.
-      const int64_t cap = M * std::max<int64_t>(g->info.subspaces, 1);  // upper bound of the entries: no host sync
-      const size_t tb = scan_temp_bytes(M + 1);
-      if (int rc = R.s_i64a.reserve((size_t)M + 1)) return rc;
-      if (int rc = R.s_i64b.reserve((size_t)M + 1)) return rc;
-      if (int rc = R.c_CL.reserve((size_t)cap)) return rc;
-      if (int rc = R.s_tmp.reserve((size_t)cap)) return rc;
-      if (int rc = R.s_sorttmp[0].reserve(tb)) return rc;
-      g->ch_n = -1;  // the adapt! scratch is reused
-      BasisArgs c = a;
-      c.mode = 0;
-      c.row_nnz = (unsigned long long *)R.s_i64a.p;
-      CK(cudaMemsetAsync(R.s_i64a.p + M, 0, 8, st));
-      CK(run_basis(g, c, st));
-      CK(exclusive_scan_u64((const unsigned long long *)R.s_i64a.p, R.s_i64b.p, M + 1, R.s_sorttmp[0].p, tb, st));
-      c.mode = 1;
-      c.row_ptr = R.s_i64b.p;
-      c.colidx = R.c_CL.p;
-      c.vals = R.s_tmp.p;
-      CK(run_basis(g, c, st));
-      int64_t l = 0;
-      CK(launch_dense_rows(R.s_i64b.p, R.c_CL.p, R.s_tmp.p, M, g->N, dout, ldm, st, &l));
-      bump(l);
-    } else {
-      // the walk only visits supporting nodes: clear first (needs a dense M x N block), then scatter
-      if (rowmajor) CK(cudaMemset2DAsync(dout, (size_t)ldm * 8, 0, (size_t)g->N * 8, (size_t)M, st));
-      else if (colmajor) CK(cudaMemset2DAsync(dout, (size_t)ldn * 8, 0, (size_t)M * 8, (size_t)g->N, st));
-      else return set_err(ASG_EUNSUPPORTED, "dense basis needs ldn == 1 (row-major) or ldm == 1 (column-major)");
+    if (rowmajor) CK(cudaMemset2DAsync(dout, (size_t)ldm * 8, 0, (size_t)g->N * 8, (size_t)M, st));
+    else if (colmajor) CK(cudaMemset2DAsync(dout, (size_t)ldn * 8, 0, (size_t)M * 8, (size_t)g->N, st));
+    else return set_err(ASG_EUNSUPPORTED, "dense basis needs ldn == 1 (row-major) or ldm == 1 (column-major)");
+    if (no_split) {
       CK(run_basis(g, a, st));
+    } else {
+      int64_t l = 0;
+      CK(launch_basis_dense_split(R.dg, a, R.dg.n_level1, st, &l));
+      bump(l);
     }
   } else {
     CK(run_basis(g, a, st));

@@ -91,6 +91,7 @@ struct DeviceGrid {
   // subspace engine
   const TrieRec *rec[kMaxDimFast];  // per trie level, each with a sentinel record
   uint32_t n_root;                  // records in level 0
+  uint32_t n_level1;                // records in level 1 (0 for D == 1)
   const double *coef;               // dense subspace blocks (zero padded)
   const int32_t *orig;              // slot -> caller's node number, -1 = padding
   const HashEnt *hent;              // hashed subspaces
@@ -252,16 +253,13 @@ cudaError_t csr_to_csc(const long long *row_ptr, const long long *colidx, const 
                        int64_t nnz, uint32_t *keys, uint32_t *keys_alt, uint32_t *ent, uint32_t *perm, uint32_t *rows,
                        void *temp, size_t temp_bytes, long long *colptr, long long *rowidx, double *vout, cudaStream_t st,
                        int64_t *launches);
-// dense basis rows written in one streaming pass from their CSR form (asg_sort.cu)
-size_t scan_temp_bytes(int64_t n);
-cudaError_t exclusive_scan_u64(const unsigned long long *in, long long *out, int64_t n, void *temp, size_t temp_bytes,
-                               cudaStream_t st);
-cudaError_t launch_dense_rows(const long long *row_ptr, const long long *colidx, const double *vals, int64_t M, int64_t N,
-                              double *out, int64_t ldm, cudaStream_t st, int64_t *launches);
+cudaError_t launch_narrow_i64(const long long *in, int *out, int64_t n, cudaStream_t st, int64_t *launches);
 cudaError_t launch_eval_rsg(const DeviceGrid &g, const RsgParams &rp, const EvalArgs &a, cudaStream_t st,
                             int64_t *launches);
 cudaError_t launch_eval_sweep(const DeviceGrid &g, const EvalArgs &a, cudaStream_t st, int64_t *launches);
 cudaError_t launch_basis_subspace(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);
+// dense basis scatter split over the nodes of trie level 1 (n1 of them) instead of one thread per row
+cudaError_t launch_basis_dense_split(const DeviceGrid &g, const BasisArgs &a, uint32_t n1, cudaStream_t st, int64_t *launches);
 cudaError_t launch_basis_sweep(const DeviceGrid &g, const BasisArgs &a, cudaStream_t st, int64_t *launches);
 // node coordinates: li = [n][D] pairs (level, index) as int64x2, Xout element (k,d) at k*sp + d*sd
 cudaError_t launch_nodes_x(int D, const double *lb_dev_or_null, const DeviceGrid &g, const long long *lev,

@@ -83,15 +83,15 @@ cudaError_t launch_eval_block(const DeviceGrid &g, const EvalArgs &a_in, cudaStr
   if (launches) ++*launches;
   e = cudaGetLastError();
   if (e != cudaSuccess || !pair) return e;
-  // follow-up: the second points of the pairs that straddle a cell boundary, one point per thread; their number is
-  // only known on the device, so the launch covers the worst case and surplus CTAs leave at once
+  // follow-up: the second points of the pairs that straddle a cell boundary (about half a point per occupied cell),
+  // two unpaired points per thread; their number is only known on the device, so the launch covers the worst case and
+  // surplus CTAs leave at once
   EvalArgs b = a_in;
   b.perm = left_list;
   b.M_dev = left_count;
   b.M = a.M / 2 + 1;
-  const size_t smem1 = blk_smem_bytes(g, 1, nt);
-  const int64_t need1 = (b.M + nt - 1) / nt;
-  e = blk_launch_nt<kBlkThreads>(g, b, false, masked, false, (int)(need1 < sms ? need1 : sms), smem1, st);
+  const int64_t need1 = (b.M + per_block - 1) / per_block;
+  e = blk_launch_nt<kBlkThreads>(g, b, true, masked, false, (int)(need1 < sms ? need1 : sms), smem, st);
   if (e != cudaSuccess) return e;
   if (launches) ++*launches;
   return cudaGetLastError();

@@ -172,6 +172,51 @@ __global__ void __launch_bounds__(256) k_basis_subspace(const DeviceGrid g, cons
   }
 }
 
+// ---- dense basis rows: the scatter pass split over the subtrees of the level-vector trie --------------------------
+// asg_basis_dense clears the M x N block and scatters one entry per subspace and row into it. With one thread per
+// row the scatter is latency bound -- a thread visits its ~715 subspaces (BASELINE configs[4]) one dependent trie
+// record after the other, 1.6 ms for 50 000 rows -- although it moves almost no data. Here a thread owns one row AND
+// one node of trie level 1 (a pair of levels of dimensions 0 and 1): ~50 times more threads, each with a ~50 times
+// shorter chain. (Measured and rejected on configs[4], 18.7 GB: building the rows in CSR form first and writing every
+// output byte once -- count + fill + row writer 4.7 ms, the same fused into one kernel 5.3 ms against 4.2 ms for
+// memset + scatter: the single-thread walk of a row, ~0.9 ms, cannot hide behind the stores of its own CTA.)
+template <int D>
+__global__ void __launch_bounds__(256) k_basis_dense_split(const DeviceGrid g, const BasisArgs a, uint32_t n1) {
+  static_assert(D >= 3, "two trie levels above the prefix groups");
+  const int64_t total = a.M * (int64_t)n1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / n1;
+    const uint32_t j1 = (uint32_t)(t - m * n1);
+    Points<D, 1> pt;
+    if (!load_point<D, 1>(g, a.X, m, a.sp, a.sd, pt, 0)) continue;  // outside the domain the row stays zero
+    // the level-0 node that owns child j1 (children ranges are consecutive; a handful of nodes)
+    uint32_t j0 = 0;
+    while (j0 + 1 < g.n_root && ld_rec(g.rec[0] + j0 + 1).x <= j1) ++j0;
+    const TrieRec r = ld_rec(g.rec[0] + j0);
+    const int l = (int)(r.y & 0xffu);
+    Prefix<1> pf;
+    pf.P[0] = 1.0;
+    pf.O[0] = 0u;
+    if (l > 1) {
+      double ph;
+      uint32_t cell;
+      hat_cell(pt.x[0][0], pt.q[0][0], (int)((r.y >> 24) & 0x3fu), (r.y >> 30) & 1u, pow2_lm1(l), ph, cell);
+      pf.P[0] = ph;
+      pf.O[0] = cell;
+    }
+    BasisSink<1> sink;
+    sink.mode = 2;
+    sink.atol = a.atol;
+    sink.dropzeros = a.dropzeros;
+    sink.cnt[0] = 0;
+    sink.colidx[0] = nullptr;
+    sink.vals[0] = nullptr;
+    sink.row[0] = a.dense + m * a.ldm;
+    sink.ldn = a.ldn;
+    Walk<D, 1, 1>::run(g, pt, pf, j1, j1 + 1, INT_MAX / 2, sink);
+  }
+}
+
 static int sm_count() {
   static int sms = 0;
   if (!sms) {
@@ -226,6 +271,23 @@ cudaError_t launch_basis_subspace(const DeviceGrid &g, const BasisArgs &a, cudaS
 #define CALL(DD) k_basis_subspace<DD><<<blocks, threads, 0, st>>>(g, a)
   ASG_DISPATCH_D(g.D, CALL)
 #undef CALL
+  if (launches) ++*launches;
+  return cudaGetLastError();
+}
+
+// dense scatter (a.mode == 2, output already cleared), split over the nodes of trie level 1 where the trie has them
+cudaError_t launch_basis_dense_split(const DeviceGrid &g, const BasisArgs &a, uint32_t n1, cudaStream_t st, int64_t *launches) {
+  if (a.M <= 0) return cudaSuccess;
+  if (g.D < 3 || n1 == 0) return launch_basis_subspace(g, a, st, launches);
+  const int64_t need = (a.M * (int64_t)n1 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 64;
+  const int blocks = (int)(need < cap ? need : cap);
+  switch (g.D) {
+#define CASE(DD) case DD: k_basis_dense_split<DD><<<blocks, 256, 0, st>>>(g, a, n1); break;
+    CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12)
+#undef CASE
+    default: return cudaErrorInvalidValue;
+  }
   if (launches) ++*launches;
   return cudaGetLastError();
 }

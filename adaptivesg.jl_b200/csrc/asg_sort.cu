@@ -5,7 +5,6 @@
 // into broadcasts. The points are not moved: the walk reads point perm[j] and writes out[perm[j]].
 // The sort itself is the CUDA toolkit's cub::DeviceRadixSort (plumbing, 1-2 % of the walk's time).
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 
 #include "asg_internal.h"
 
@@ -133,63 +132,17 @@ cudaError_t csr_to_csc(const long long *row_ptr, const long long *colidx, const 
 
 }  // namespace asg
 
-// ---- dense basis rows from their CSR form: one streaming pass over the output ----------------------------------
-// asg_basis_dense used to clear the M x N block (cudaMemset2D) and then scatter ~one entry per subspace and row into
-// it: two passes over 8*N bytes per point, the second one as partial-sector writes. Here every output byte is written
-// exactly once: a CTA owns one row, builds it segment by segment in shared memory (zeros + the row's entries) and
-// streams each segment out with 16-byte st.global.cs stores.
 namespace asg {
-
-size_t scan_temp_bytes(int64_t n) {
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const unsigned long long *)nullptr, (long long *)nullptr, (int)n);
-  return bytes;
+// 64-bit -> 32-bit indices (asg_basis_fill_csc32: half the bytes to bring home for callers whose sparse type holds Int32)
+__global__ void k_narrow_i64(const long long *in, int *out, int64_t n) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) out[k] = (int)in[k];
 }
-cudaError_t exclusive_scan_u64(const unsigned long long *in, long long *out, int64_t n, void *temp, size_t temp_bytes,
-                               cudaStream_t st) {
-  return cub::DeviceScan::ExclusiveSum(temp, temp_bytes, in, out, (int)n, st);
-}
-
-constexpr int kRowSeg = 4096;  // doubles per shared-memory segment (32 KB)
-
-__global__ void __launch_bounds__(256) k_dense_rows(const long long *row_ptr, const long long *colidx, const double *vals,
-                                                    int64_t M, int64_t N, double *out, int64_t ldm) {
-  __shared__ __align__(16) double seg[kRowSeg];
-  for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
-    const long long p0 = row_ptr[m], p1 = row_ptr[m + 1];
-    double *row = out + m * ldm;
-    // rows start 8-byte aligned only: peel to a 16-byte boundary, then whole double2 stores
-    const int64_t head = ((reinterpret_cast<uintptr_t>(row) & 15u) != 0 && N > 0) ? 1 : 0;
-    for (int64_t c0 = 0; c0 < N; c0 += kRowSeg) {
-      const int64_t cn = (N - c0) < kRowSeg ? (N - c0) : kRowSeg;
-      for (int c = threadIdx.x * 2; c < cn; c += 512) *reinterpret_cast<double2 *>(&seg[c]) = make_double2(0.0, 0.0);
-      __syncthreads();
-      for (long long e = p0 + threadIdx.x; e < p1; e += 256) {
-        const long long c = colidx[e] - c0;
-        if (c >= 0 && c < cn) seg[c] = vals[e];
-      }
-      __syncthreads();
-      // segment [c0, c0 + cn) -> row; the 16-byte grid of the ROW decides the pairing
-      const int64_t a0 = (c0 == 0) ? head : ((c0 - head) & 1 ? 1 : 0);  // first index of this segment on the 16-byte grid
-      if (threadIdx.x == 0 && a0 == 1) row[c0] = seg[0];
-      const int64_t npair = (cn - a0) / 2;
-      for (int64_t k = threadIdx.x; k < npair; k += 256) {
-        const double2 v = make_double2(seg[a0 + 2 * k], seg[a0 + 2 * k + 1]);
-        __stcs(reinterpret_cast<double2 *>(row + c0 + a0 + 2 * k), v);
-      }
-      if (threadIdx.x == 0 && ((cn - a0) & 1)) row[c0 + cn - 1] = seg[cn - 1];
-      __syncthreads();
-    }
-  }
-}
-
-cudaError_t launch_dense_rows(const long long *row_ptr, const long long *colidx, const double *vals, int64_t M, int64_t N,
-                              double *out, int64_t ldm, cudaStream_t st, int64_t *launches) {
-  if (M <= 0 || N <= 0) return cudaSuccess;
-  const int64_t cap = 148 * 16;
-  k_dense_rows<<<(int)(M < cap ? M : cap), 256, 0, st>>>(row_ptr, colidx, vals, M, N, out, ldm);
+cudaError_t launch_narrow_i64(const long long *in, int *out, int64_t n, cudaStream_t st, int64_t *launches) {
+  if (n <= 0) return cudaSuccess;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_narrow_i64<<<(int)blocks, 256, 0, st>>>(in, out, n);
   if (launches) ++*launches;
   return cudaGetLastError();
 }
-
 }  // namespace asg

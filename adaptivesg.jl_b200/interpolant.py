@@ -631,13 +631,22 @@ def basis(*args, safe: bool = True, dropzeros: bool = True, atol: float = 1e-16,
     check(lib.asg_basis_count(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(nnz, i64p)))
     ptr = np.zeros(M + 1, dtype=np.int64)
     np.cumsum(nnz, out=ptr[1:])
-    col = np.empty(int(ptr[-1]), dtype=np.int64)
     val = np.empty(int(ptr[-1]), dtype=np.float64)
+    col = np.empty(int(ptr[-1]) if (format == "csr" or int(ptr[-1]) >= 2 ** 31 - 1 or N >= 2 ** 31 - 1) else 0, dtype=np.int64)
     if format == "csr":
         check(lib.asg_basis_fill(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(col, i64p),
                                  _ptr(val, f64p)))
         B = sps.csr_matrix((val, col, ptr), shape=(M, N))
-    else:  # the reference's SparseMatrixCSC: transposed on the device (stable sort of the entries by column)
+    elif int(ptr[-1]) < 2 ** 31 - 1 and N < 2 ** 31 - 1:
+        # the reference's SparseMatrixCSC: transposed on the device (stable sort of the entries by column); scipy holds
+        # 32-bit indices at this size, so ask for them directly (nothing to convert, half the index bytes to copy)
+        i32p = C.POINTER(C.c_int32)
+        cptr = np.empty(N + 1, dtype=np.int32)
+        col = np.empty(int(ptr[-1]), dtype=np.int32)
+        check(lib.asg_basis_fill_csc32(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(cptr, i32p),
+                                       _ptr(col, i32p), _ptr(val, f64p)))
+        B = sps.csc_matrix((val, col, cptr), shape=(M, N))
+    else:
         cptr = np.empty(N + 1, dtype=np.int64)
         check(lib.asg_basis_fill_csc(h, _vp(X), M, D, 1, float(atol), int(dropzeros), _ptr(ptr, i64p), _ptr(cptr, i64p),
                                      _ptr(col, i64p), _ptr(val, f64p)))

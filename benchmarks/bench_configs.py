@@ -35,6 +35,24 @@ def timed(fn, reps=3):
     return min(t)
 
 
+def device_eval_ms(lib, G, X, reps=5):
+    """points resident in HBM: asg_eval_device timed with CUDA events inside the library (median of `reps`)"""
+    import torch
+    dX = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    out = torch.empty(len(X), dtype=torch.float64, device="cuda")
+    h = G._ensure()
+    st = torch.cuda.current_stream().cuda_stream
+    ms = C.c_double()
+    ts = []
+    for k in range(reps + 2):
+        asg._capi.check(lib.asg_eval_device(h, C.c_void_p(dX.data_ptr()), len(X), X.shape[1], 1, -1, C.c_void_p(out.data_ptr()),
+                                            C.c_void_p(st)))
+        asg._capi.check(lib.asg_last_kernel_ms(C.byref(ms)))
+        if k >= 2:
+            ts.append(ms.value)
+    return float(np.median(ts))
+
+
 def main():
     import torch
     asg.init(0)
@@ -68,8 +86,11 @@ def main():
     t_build = time.perf_counter() - t0
     X = rng.random((10_000_000, 2))
     dt = timed(lambda: G.evaluate(X), reps=2)
+    dms = device_eval_ms(lib, G, X)
     print(json.dumps({"config": "cfg2", "nodes": len(G), "train_adapt_s": t_build, "points": len(X),
-                      "eval_ms_host_buffers": dt * 1e3, "points_per_s": len(X) / dt, "info": G.info()}), flush=True)
+                      "eval_ms_host_buffers_pageable": dt * 1e3, "points_per_s_host_buffers": len(X) / dt,
+                      "eval_ms_device_resident": dms, "points_per_s_device_resident": len(X) / (dms * 1e-3),
+                      "info": G.info()}), flush=True)
 
     # ---- cfg4 -------------------------------------------------------------------------------------
     G = asg.SparseGridInterpolant(6)
@@ -120,6 +141,32 @@ def main():
     N = len(G)
     M = 50000
     X = rng.random((M, 4))
+    Xe = rng.random((10_000_000, 4))
+    dms5 = device_eval_ms(lib, G, Xe)
+    del Xe
+    # where the sparse basis spends its time: the two device passes vs. the host side (pageable D2H, scipy)
+    import scipy.sparse as sps
+    h5 = G._ensure()
+    Xc = np.ascontiguousarray(X)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    t0 = time.perf_counter()
+    nnz_row = np.zeros(M, dtype=np.int64)
+    asg._capi.check(lib.asg_basis_count(h5, vp(Xc), M, 4, 1, 1e-16, 1, nnz_row.ctypes.data_as(asg._capi.i64p)))
+    t_count = time.perf_counter() - t0
+    ptr = np.zeros(M + 1, dtype=np.int64)
+    np.cumsum(nnz_row, out=ptr[1:])
+    col = np.empty(int(ptr[-1]), dtype=np.int64)
+    val = np.empty(int(ptr[-1]), dtype=np.float64)
+    cptr = np.empty(N + 1, dtype=np.int64)
+    t0 = time.perf_counter()
+    asg._capi.check(lib.asg_basis_fill_csc(h5, vp(Xc), M, 4, 1, 1e-16, 1, ptr.ctypes.data_as(asg._capi.i64p),
+                                           cptr.ctypes.data_as(asg._capi.i64p), col.ctypes.data_as(asg._capi.i64p),
+                                           val.ctypes.data_as(asg._capi.f64p)))
+    t_fill = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sps.csc_matrix((val, col, cptr), shape=(M, N))
+    t_scipy = time.perf_counter() - t0
+    del col, val
     t_sparse = timed(lambda: asg.basis(X, G), reps=2)
     t_sparse_csr = timed(lambda: asg.basis(X, G, format="csr"), reps=2)   # without the host-side CSR -> CSC transposition
     B = asg.basis(X, G)
@@ -146,7 +193,11 @@ def main():
     k_ms = float(np.median(ts))
     gbs = M * N * 8 / (k_ms * 1e-3) / 1e9
     nnz_dense = int(torch.count_nonzero(out).item())
-    print(json.dumps({"config": "cfg5", "nodes": N, "points": M, "sparse_basis_s": t_sparse, "sparse_basis_csr_s": t_sparse_csr, "nnz": int(B.nnz),
+    print(json.dumps({"config": "cfg5", "nodes": N, "points": M, "eval_1e7_points_device_resident_ms": dms5,
+                      "eval_points_per_s_device_resident": 1e7 / (dms5 * 1e-3),
+                      "sparse_breakdown_s": {"count_call": t_count, "fill_csc_call_incl_576MB_pageable_D2H": t_fill,
+                                             "scipy_csc_matrix": t_scipy},
+                      "sparse_basis_s": t_sparse, "sparse_basis_csr_s": t_sparse_csr, "nnz": int(B.nnz),
                       "nnz_per_row": B.nnz / M, "B_times_C_vs_eval_max_abs": err, "dense_ms": k_ms,
                       "dense_bytes": M * N * 8, "dense_write_GBps": gbs, "hbm_peak_GBps": peaks.get("hbm_gbs"),
                       "dense_frac_of_hbm_peak": gbs / peaks["hbm_gbs"] if "hbm_gbs" in peaks else None,

@@ -226,6 +226,10 @@ int32_t asg_basis_fill(asg_grid *g, const double *X, int64_t M, int64_t sp, int6
  * reference returns (src/class.jl:483-503): colptr[N+1], rowidx / vals [row_ptr[M]], 0-based, rows ascending in a column */
 int32_t asg_basis_fill_csc(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                            int32_t dropzeros, const int64_t *row_ptr, int64_t *colptr, int64_t *rowidx, double *vals);
+/* the same with 32-bit colptr / rowidx (sparse types that hold Int32 indices, e.g. scipy's default: half the index
+ * bytes come home and the caller converts nothing); ASG_EUNSUPPORTED when N or the entry count needs 64 bits */
+int32_t asg_basis_fill_csc32(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
+                             int32_t dropzeros, const int64_t *row_ptr, int32_t *colptr, int32_t *rowidx, double *vals);
 int32_t asg_basis_dense(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim, double atol,
                         int32_t dropzeros, double *out, int64_t ldm, int64_t ldn);
 /* dense variant into a DEVICE buffer (bench: HBM-write roofline without the D2H copy) */

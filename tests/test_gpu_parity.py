@@ -833,7 +833,7 @@ def test_append_without_repacking(asg, oracle):
     assert H.info()["delta_nodes"] > 0                       # none of this packed
     # coefficient updates reach appended nodes
     nd = H.info()["delta_nodes"]
-    idx = np.arange(len(H) - nd, len(H), dtype=np.int64)[::3]
+    idx = np.ascontiguousarray(np.arange(len(H) - nd, len(H), dtype=np.int64)[::3])
     vals = np.ascontiguousarray(rng.standard_normal(len(idx)))
     lib = asg._capi.load()
     asg._capi.check(lib.asg_grid_scatter_coefs(H._ensure(), len(idx), idx.ctypes.data_as(asg._capi.i64p),
