@@ -530,15 +530,25 @@ int stage_points(const double *X, int64_t m0, int64_t cnt, int D, int64_t sp, in
 // the copy-in stream (so that a pageable source, whose cudaMemcpyAsync blocks the issuing thread, still overlaps with
 // the walks). The walk side is GREEDY: whenever the GPU is free it takes EVERY piece that has arrived since the last
 // window as one batch (point ordering + walk), then looks again. The window sizes therefore adapt to the machine by
-// themselves: with one GPU a copy runs ~3x faster than the walk of the same points and the windows grow 0.26 M,
-// 0.8 M, 2.4 M, ... until everything has arrived and the rest goes in one large, sharply ordered batch (PAIR mode);
+// themselves: with one GPU a copy runs ~3x faster than the walk of the same points and the windows grow 0.3 M,
+// 0.9 M, 2.7 M, ... until everything has arrived and the rest goes in one large, sharply ordered batch (PAIR mode);
 // with eight GPUs sharing the host's PCIe fabric (23-36 GB/s each, profiles/r02_pcie_bandwidth_8gpu.json) copy and
 // walk run at about the same rate and the windows stay moderate. Only the first piece's copy, and the walk + D2H copy
 // of the last window -- a short tail split off on purpose -- are not hidden behind other work. Results return on a
 // third stream, one window behind. Batches above pipe_super() points run as consecutive super-batches (device buffers).
 // ASG_PIPE_PIECE / ASG_PIPE_SUPER (points) override the two sizes.
 int64_t pipe_piece() {
-  static const int64_t v = [] { const char *e = getenv("ASG_PIPE_PIECE"); const long long x = e ? atoll(e) : 0; return x > 0 ? (int64_t)x : (int64_t)1 << 18; }();
+  // two full waves of the walk's CTAs (one CTA of 1 024 points per SM): a window of k pieces is 2k full waves, where
+  // 2^18 points were 1.73 waves on 148 SMs -- 14 % of the small windows' time went to the half-empty last wave
+  static const int64_t v = [] {
+    const char *e = getenv("ASG_PIPE_PIECE");
+    const long long x = e ? atoll(e) : 0;
+    if (x > 0) return (int64_t)x;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int64_t)2 * (sms > 0 ? sms : 148) * 1024;
+  }();
   return v;
 }
 int64_t pipe_super() {

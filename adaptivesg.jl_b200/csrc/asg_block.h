@@ -98,9 +98,26 @@ struct __align__(16) BlockRec {
   uint32_t odd;    // stage: 1 if level > 2 (index = 2*cell + 1)
 };
 static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words");
-// suffix code = 8 * S + r: S = 3 the 3-D suffix (r = 0..7); S = 2 the 2-D suffix of a split record (dimension A is
-// the record's stage or at level 1); S = 4..7 deeper suffixes with r = 1..blk_max_r(S)
-ASG_HD constexpr uint32_t blk_code(int S, int r) { return (uint32_t)(8 * S + r); }
+// suffix code of a record: a DENSE numbering of the compiled (S, r) pairs, so that the walk's dispatch is one indexed
+// branch. S = 3 the 3-D suffix (r = 0..7: codes 0..7); S = 2 the 2-D suffix of a split record (dimension A is the
+// record's stage or at level 1; codes 8..15); S = 4.. deeper suffixes with r = 1..blk_max_r(S), numbered on from 16.
+ASG_HD constexpr uint32_t blk_code_base(int S) {
+  uint32_t b = 16;
+  for (int s = 4; s < S; ++s) b += (uint32_t)(blk_max_r(s) > 0 ? blk_max_r(s) : 0);
+  return b;
+}
+ASG_HD constexpr uint32_t blk_code(int S, int r) {
+  return S == 3 ? (uint32_t)r : (S == 2 ? (uint32_t)(8 + r) : blk_code_base(S) + (uint32_t)(r - 1));
+}
+constexpr uint32_t kBlkCodes = blk_code_base(kBlkMaxS + 1);  // number of codes
+ASG_HD inline void blk_decode(uint32_t code, int &S, int &r) {  // host side: packer self-check, persistence
+  if (code < 8) { S = 3; r = (int)code; return; }
+  if (code < 16) { S = 2; r = (int)code - 8; return; }
+  for (int s = 4; s <= kBlkMaxS; ++s)
+    if (code < blk_code_base(s + 1)) { S = s; r = (int)(code - blk_code_base(s)) + 1; return; }
+  S = -1;
+  r = -1;
+}
 constexpr uint32_t kBrNone = 255u;  // stage only (no nodes under this prefix)
 constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later record restarts from it)
 // PAIR mode of the walk (asg_kernels_block.cuh): two neighbours of the cell-key order share the cell of every level

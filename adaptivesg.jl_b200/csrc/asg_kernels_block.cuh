@@ -257,7 +257,7 @@ struct BlkStaged {     // a record after its stage: everything its compiled suff
 // that supports the point, on top of the prefix saved by the parent record (stack slot ra.z).
 template <int R, bool MASKED, int NT>
 __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_t os_t, uint32_t xs_t, uint32_t tbias,
-                                          int rem, BlkStaged<R> &out) {
+                                          int rem, BlkStaged<R> &out, double (&xpre)[R], uint32_t kmax) {
   uint4 ra, rb;  // {cbase, sw, slot, k0} {b, s_hi, lim, odd}
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(ra.x), "=r"(ra.y), "=r"(ra.z), "=r"(ra.w) : "r"(rbase));
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(rb.x), "=r"(rb.y), "=r"(rb.z), "=r"(rb.w) : "r"(rbase));
@@ -267,13 +267,33 @@ __device__ __forceinline__ void blk_stage(uint32_t rbase, uint32_t ps_t, uint32_
   for (int k = 0; k < R; ++k) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Oin[k]) : "r"(oa + k * (NT * 4u)));
   // (keeping the inputs of sibling records -- same parent, same stage dimension -- in registers instead of
   // re-loading them was measured 4 % SLOWER: the eight registers are worth more to the compiled suffix)
-  const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
   double Pin[R], xin[R];
+#ifdef ASG_BLK_PREFETCH_X
+  // the coordinate of the stage dimension was fetched while the previous record's suffix ran (coordinates never change
+  // during a walk): one shared-memory round trip less on the record's critical path. Now fetch the next record's.
+  (void)kmax;
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    Pin[k] = lds_f64(pa + k * (NT * 8u));
+    xin[k] = xpre[k];
+  }
+  {
+    uint32_t k0n;
+    asm volatile("ld.shared.u32 %0, [%1+44];" : "=r"(k0n) : "r"(rbase));  // k0 of the next record (32 + 12)
+    k0n = min(k0n, kmax);  // past the tile's last record: any valid row
+    const uint32_t xn = xs_t + k0n * (R * NT * 8u);
+#pragma unroll
+    for (int k = 0; k < R; ++k) xpre[k] = lds_f64(xn + k * (NT * 8u));
+  }
+#else
+  (void)xpre; (void)kmax;
+  const uint32_t xa = xs_t + ra.w * (R * NT * 8u);
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     Pin[k] = lds_f64(pa + k * (NT * 8u));
     xin[k] = lds_f64(xa + k * (NT * 8u));
   }
+#endif
   const double s = __hiloint2double((int)rb.y, 0);                            // 2^(l-1), or 0 for the root record
   const double s2b = __hiloint2double((int)((rb.x << 20) + 0x3ff00000u), 0);  // 2^b
 #pragma unroll
@@ -314,19 +334,18 @@ __device__ __forceinline__ void blk_record(const BlkPoint<R, PAIR> &pt, const Bl
 // above kBlkTab) only for the small budgets such a prefix can leave on the grids that take PAIR mode (kBlkPairMaxR).
 template <int R, bool MASKED, bool PAIR, bool SH>
 __device__ __forceinline__ void blk_dispatch(const BlkPoint<R, PAIR> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
+  // (pairs this build does not compile -- RS above blk_max_r(S) -- get labels outside the code range)
 #define BLK_CASE(S, RS)                                                                                      \
-  case blk_code(S, RS):                                                                                      \
+  case ((S <= 3 || RS <= blk_max_r(S)) ? blk_code(S, RS) : 160u + 8u * S + RS):                              \
     if constexpr ((S <= 3 || RS <= blk_max_r(S)) && (!PAIR || SH || RS <= kBlkPairMaxR))                     \
       blk_record<S, RS, R, MASKED, PAIR, SH>(pt, st, rem, acc);                                              \
     break;
-  // half of all prefix vectors of a regular grid spend the whole budget (r = 0), a quarter leave r = 1:
-  // test those first, the compiler's balanced compare tree would spend 4-5 branches on each
+  // a quarter of the records of a regular grid are single terms (3-D suffix, r = 0): test that first; every other
+  // compiled suffix goes through ONE indexed branch (the codes are dense, asg_block.h)
   const uint32_t code = st.sw & 0xffu;
   if (code == blk_code(3, 0)) blk_record<3, 0, R, MASKED, PAIR, SH>(pt, st, rem, acc);
-  else if (code == blk_code(3, 1)) blk_record<3, 1, R, MASKED, PAIR, SH>(pt, st, rem, acc);
-  else if (code == blk_code(3, 2)) blk_record<3, 2, R, MASKED, PAIR, SH>(pt, st, rem, acc);
   else switch (code) {
-    BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
+    BLK_CASE(3, 1) BLK_CASE(3, 2) BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
     BLK_CASE(2, 0) BLK_CASE(2, 1) BLK_CASE(2, 2) BLK_CASE(2, 3) BLK_CASE(2, 4) BLK_CASE(2, 5) BLK_CASE(2, 6) BLK_CASE(2, 7)
     BLK_CASE(4, 1) BLK_CASE(4, 2) BLK_CASE(4, 3) BLK_CASE(4, 4) BLK_CASE(4, 5)
     BLK_CASE(5, 1) BLK_CASE(5, 2) BLK_CASE(5, 3) BLK_CASE(5, 4)
@@ -469,9 +488,19 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       pin_u32(ps_t);
       pin_u32(os_t);
       const uint32_t rend = rbase + (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
+      double xpre[R];
+#ifdef ASG_BLK_PREFETCH_X
+      {
+        uint32_t k0f;
+        asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(k0f) : "r"(rbase));  // k0 of the tile's first record
+        const uint32_t xf = xs_t + min(k0f, (uint32_t)(D - 1)) * (R * NT * 8u);
+#pragma unroll
+        for (int k = 0; k < R; ++k) xpre[k] = lds_f64(xf + k * (NT * 8u));
+      }
+#endif
       for (; rbase < rend; rbase += (uint32_t)sizeof(BlockRec)) {
         BlkStaged<R> st;
-        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, st);
+        blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, st, xpre, (uint32_t)(D - 1));
         if constexpr (PAIR) {
           // warp-uniform: every level of the record's prefix is <= kBlkTab, the pair shares the prefix position
           if (st.sw & kBrShared) blk_dispatch<R, MASKED, true, true>(pt, st, a.rem, acc);

@@ -464,7 +464,9 @@ double block_walk_host(int D, const PackResult &pk, const double *x01, int rem) 
     if (q.sw & kBrSave) { P[q.slot + 1] = cur; O[q.slot + 1] = cO; }
     const uint32_t code = q.sw & 0xffu;
     if (code == kBrNone) continue;
-    const int S = (int)(code >> 3), rs = (int)(code & 7u);
+    int S, rs;
+    blk_decode(code, S, rs);
+    if (S < 2) return std::nan("");
     const int reff = std::min(rs, rem - used);
     if ((uint64_t)q.cbase + (cO + 1) * t_size(S, rs) > pk.bcoef.size()) return std::nan("");  // chunk outside the storage
     const double *chunk = pk.bcoef.data() + q.cbase + cO * t_size(S, rs);

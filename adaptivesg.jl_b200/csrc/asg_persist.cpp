@@ -33,7 +33,7 @@ uint64_t checksum(const unsigned char *p, size_t n) {
 }
 
 uint64_t layout_fingerprint() {  // everything a blob's bytes depend on besides the grid itself
-  const uint32_t c[] = {2u /* format version */, (uint32_t)kBlkPairLevel, (uint32_t)kBlkPairMaxR, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
+  const uint32_t c[] = {3u /* format version */, kBlkCodes, (uint32_t)kBlkPairLevel, (uint32_t)kBlkPairMaxR, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
                         (uint32_t)sizeof(StreamTile), (uint32_t)sizeof(BlockTile), (uint32_t)sizeof(HashEnt),
                         (uint32_t)sizeof(SweepDim), (uint32_t)sizeof(RsgParams), (uint32_t)kLeafTable, (uint32_t)kTileCoefs,
                         (uint32_t)kTileRecs, (uint32_t)kBlkTileCoefsMax, (uint32_t)kBlkTileRecs, (uint32_t)kBlkMaxS,
@@ -180,7 +180,8 @@ int pack_deserialize(const unsigned char *buf, size_t bytes, int D, const double
         if (b.slot + (save ? 1u : 0u) >= (uint32_t)pk.blk_slots || b.k0 >= (uint32_t)D || b.b > 24u || b.lim != (1u << b.b) - 1u)
           return bad("BLOCK record stage");
         if (code != kBrNone) {
-          const int S = (int)(code >> 3), r = (int)(code & 7u);
+          int S, r;
+          blk_decode(code, S, r);
           if (S < 2 || S > kBlkMaxS || (S > 3 && r > blk_max_r(S)) || b.cbase < t.c0 || b.cbase >= t.c1) return bad("BLOCK record suffix");
         }
       }

@@ -6,6 +6,8 @@
 // The sort itself is the CUDA toolkit's cub::DeviceRadixSort (plumbing, 1-2 % of the walk's time).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstdlib>
+
 #include "asg_internal.h"
 
 namespace asg {
@@ -13,7 +15,7 @@ namespace asg {
 // key = bit planes of the unit-cube coordinates, most significant plane first: [bit 1 of every dimension]
 // [bit 2 of every dimension] ...  (`planes` planes of min(D, 32/planes...) bits, 32 bits in total at most).
 __global__ void k_point_keys(const DeviceGrid g, const double *X, int64_t M, int64_t sp, int64_t sd, int planes,
-                             uint32_t *keys, uint32_t *idx) {
+                             uint32_t *keys, uint32_t *idx, int suffix_first) {
   const int D = g.D;
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
     uint32_t key = 0u;
@@ -22,7 +24,20 @@ __global__ void k_point_keys(const DeviceGrid g, const double *X, int64_t M, int
       const double u = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(X[m * sp + d * sd], g.lb[d]), g.width[d]));  // scale()
       inside = inside && (u >= 0.0) && (u <= 1.0);
       const uint32_t q = u < 1.0 ? (uint32_t)(u * 256.0) : 255u;  // top 8 bits of the coordinate
-      if (d < 32)
+      if (suffix_first && D >= 4) {
+        // experiment (ASG_SORT_KEY=suffix): the three compiled dimensions first, `planes` bits each, then the bit
+        // planes of the prefix dimensions
+        const int K = D - 3;
+        if (d >= K) {
+          const int pos = 32 - planes * (D - d);  // C on top, then B, then A
+          if (pos >= 0) key |= (q >> (8 - planes)) << pos;
+        } else {
+          for (int p = 0; p < planes; ++p) {
+            const int pos = 32 - 3 * planes - (p + 1) * K + (K - 1 - d);
+            if (pos >= 0 && pos < 32) key |= ((q >> (7 - p)) & 1u) << pos;
+          }
+        }
+      } else if (d < 32)
         for (int p = 0; p < planes; ++p) {
           const int pos = (planes - 1 - p) * D + (D - 1 - d);  // plane p occupies bits [(planes-1-p)*D, +D)
           if (pos < 32) key |= ((q >> (7 - p)) & 1u) << pos;
@@ -49,7 +64,8 @@ cudaError_t sort_points(const DeviceGrid &g, const double *X, int64_t M, int64_t
   if (planes > 8) planes = 8;
   int64_t blocks = (M + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_point_keys<<<(int)blocks, 256, 0, st>>>(g, X, M, sp, sd, planes, keys, idx);
+  const char *kenv = getenv("ASG_SORT_KEY");
+  k_point_keys<<<(int)blocks, 256, 0, st>>>(g, X, M, sp, sd, planes, keys, idx, (kenv && kenv[0] == 's') ? 1 : 0);
   if (launches) ++*launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -503,6 +503,21 @@ def main():
                "parity_vs_long_double_oracle": {"points": int(ns), "max_abs_err": float(err.max()),
                                                 "tolerance": "1e-12 rel | 1e-14 * max(1, sum|c*phi|) abs", "asserted": True}}
 
+    # a second CPU row from the reference ITSELF, if somebody has run tests/golden/dump_reference.jl (Julia >= 1.9): its
+    # header carries Threads.nthreads() and the wall time of G.(points) on cfg1 (737 nodes) -- another grid than the
+    # headline's, so it is reported next to cpu_baseline, not instead of it
+    if cpu is not None:
+        dump = os.path.join(ROOT, "tests", "golden", "julia_cfg1.bin")
+        if os.path.exists(dump):
+            import struct
+            with open(dump, "rb") as fh:
+                hd = fh.read(56)
+            Dj, Nj, Mj, nth = struct.unpack_from("<4q", hd, 0)
+            wt, wa, we = struct.unpack_from("<3d", hd, 32)
+            cpu["julia_reference_cfg1"] = {"value": Mj / we if we > 0 else None, "unit": "points/s", "threads": int(nth),
+                                           "nodes": int(Nj), "points": int(Mj), "train_s": wt, "kind": "reference",
+                                           "note": "the unmodified reference's G.(points) on cfg1 (D = 3, 737 nodes)"}
+
     line = {
         "metric": "interpolant evaluations per second", "value": value, "unit": "points/s", "n_gpus": world,
         "steps": K, "warmup": Wd, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
