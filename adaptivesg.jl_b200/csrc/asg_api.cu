@@ -459,7 +459,7 @@ int run_eval(asg_grid *g, int r, const EvalArgs &a_in, cudaStream_t st, int slot
     }
     uint32_t *left = nullptr, *leftcnt = nullptr;
     if (sorted && block_pair_mode(R.dg, a.M, true)) {
-      if (int rc = R.s_left[slot].reserve((size_t)a.M / 2 + 2)) return rc;
+      if (int rc = R.s_left[slot].reserve((size_t)a.M + 2)) return rc;  // (groups of four: up to 3/4 of the points)
       if (int rc = R.s_leftcnt[slot].reserve(4)) return rc;
       left = R.s_left[slot].p;
       leftcnt = R.s_leftcnt[slot].p;
@@ -585,7 +585,7 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
     if (int rc = R.s_perm[0].reserve((size_t)cnt)) return rc;
     if (int rc = R.s_sorttmp[0].reserve(sort_points_temp_bytes(cnt))) return rc;
     if (block_pair_mode(R.dg, cnt, true)) {
-      if (int rc = R.s_left[0].reserve((size_t)cnt / 2 + 2)) return rc;
+      if (int rc = R.s_left[0].reserve((size_t)cnt + 2)) return rc;
       if (int rc = R.s_leftcnt[0].reserve(4)) return rc;
     }
   }

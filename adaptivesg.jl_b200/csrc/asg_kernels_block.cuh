@@ -25,6 +25,8 @@
 namespace asg {
 
 constexpr int kBlkThreads = 512;  // default CTA size (384 threads x 168 registers was measured 6 % slower)
+// threads of the CTA as a function of the points per thread: a CTA always owns 1 024 points at R >= 2
+__host__ __device__ constexpr int blk_nt(int R) { return R == 4 ? 256 : kBlkThreads; }
 constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulated in registers
 // PAIR mode (two points per thread, large ordered batches): the two points of a thread are NEIGHBOURS in the cell-key
 // order and share the cell of every level <= kBlkTab in EVERY dimension (checked per thread; the second point of a pair
@@ -58,7 +60,7 @@ struct BlkPoint {
 template <int R, bool PAIR>
 __device__ __forceinline__ double blk_x_rare(const BlkPoint<R, PAIR> &pt, int which, int k) {
   double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (kBlkThreads * 8))));
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(pt.xsBC + (uint32_t)((which * R + k) * (blk_nt(R) * 8))));
   return v;
 }
 __device__ __forceinline__ uint32_t blk_key(double v) {  // floor(v * 2^30), clamped for v == 1 (exact)
@@ -372,8 +374,8 @@ __device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm,
 
 // registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
 template <int R, bool MASKED, int NT, bool PAIR>
-__global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid g, const EvalArgs a) {
-  static_assert(!PAIR || R == 2, "PAIR mode pairs the two points of a thread");
+__global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_block(const DeviceGrid g, const EvalArgs a) {
+  static_assert(!PAIR || R >= 2, "PAIR mode shares loads between the points of a thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BlkSmem &sm = *reinterpret_cast<BlkSmem *>(smem_raw);
   const int D = g.D;
@@ -408,14 +410,14 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < M; base += stride) {
     BlkPoint<R, PAIR> pt;
     pt.xsBC = xs_t + (uint32_t)((K + 1) * R * NT * 8);
-    static_assert(NT == kBlkThreads, "blk_x_rare assumes the default CTA size");
+    static_assert(NT == blk_nt(R), "blk_x_rare derives the CTA size from R");
     // flags: bit k: point k lies in the domain; bit 8 + k: point k's result is stored by this launch
     uint32_t flags = ((1u << R) - 1u) << 8;
     uint32_t code2[R];     // PAIR: the cells of level <= kBlkTab of every dimension (2 bits each)
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      // PAIR: a thread owns two NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
-      const int64_t j = PAIR ? base + 2 * (int64_t)tid + k : base + (int64_t)k * NT + tid;
+      // PAIR: a thread owns R NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
+      const int64_t j = PAIR ? base + R * (int64_t)tid + k : base + (int64_t)k * NT + tid;
       const int64_t jj = j < M ? j : M - 1;  // tail lanes redo the last point, never store
       if (j >= M) flags &= ~(0x100u << k);
       const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
@@ -436,14 +438,17 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
       code2[k] = c2;
     }
     if constexpr (PAIR) {
-      if (code2[1] != code2[0]) {
-        // not in one cell: this launch evaluates point 0 twice, the follow-up launch takes point 1
-        if (flags & 0x200u) {
-          const int64_t j1 = base + 2 * (int64_t)tid + 1;
-          a.left_list[atomicAdd(a.left_count, 1u)] = a.perm ? a.perm[j1] : (uint32_t)j1;
+#pragma unroll
+      for (int k = 1; k < R; ++k) {
+        if (code2[k] != code2[0]) {
+          // not in point 0's cell: this launch evaluates point 0 in its place, the follow-up launch takes point k
+          if (flags & (0x100u << k)) {
+            const int64_t jk = base + R * (int64_t)tid + k;
+            a.left_list[atomicAdd(a.left_count, 1u)] = a.perm ? a.perm[jk] : (uint32_t)jk;
+          }
+          flags = (flags & ~((0x100u | 1u) << k)) | ((flags & 1u) << k);
+          for (int d = 0; d < D; ++d) xs[(d * R + k) * NT + tid] = xs[(d * R + 0) * NT + tid];
         }
-        flags = (flags & 0x100u) | ((flags & 1u) * 3u);
-        for (int d = 0; d < D; ++d) xs[(d * R + 1) * NT + tid] = xs[(d * R + 0) * NT + tid];
       }
     }
 #pragma unroll
@@ -515,7 +520,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : 168) k_eval_block(const DeviceGrid
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       if ((flags >> (8 + k)) & 1u) {
-        const int64_t j = PAIR ? base + 2 * (int64_t)tid + k : base + (int64_t)k * NT + tid;
+        const int64_t j = PAIR ? base + R * (int64_t)tid + k : base + (int64_t)k * NT + tid;
         const int64_t mm = a.perm ? (int64_t)a.perm[j] : j;
         const double v = ((flags >> k) & 1u) ? acc[k] : 0.0;
         a.out[mm] = a.fvals ? (a.fvals[mm] - v) : v;

@@ -177,9 +177,12 @@ __global__ void __launch_bounds__(256) k_basis_subspace(const DeviceGrid g, cons
 // row the scatter is latency bound -- a thread visits its ~715 subspaces (BASELINE configs[4]) one dependent trie
 // record after the other, 1.6 ms for 50 000 rows -- although it moves almost no data. Here a thread owns one row AND
 // one node of trie level 1 (a pair of levels of dimensions 0 and 1): ~50 times more threads, each with a ~50 times
-// shorter chain. (Measured and rejected on configs[4], 18.7 GB: building the rows in CSR form first and writing every
-// output byte once -- count + fill + row writer 4.7 ms, the same fused into one kernel 5.3 ms against 4.2 ms for
-// memset + scatter: the single-thread walk of a row, ~0.9 ms, cannot hide behind the stores of its own CTA.)
+// shorter chain. What is left of the scatter (1.4 ms) is the memory system's handling of 3.6e7 scattered 8-byte writes
+// into freshly cleared lines. (Measured and rejected on configs[4], 18.7 GB, against 3.95 ms for memset + this scatter:
+// rows built in CSR form first and written once by a row-streaming kernel -- count + fill + writer 4.7 ms; the same
+// fused into one kernel 5.3 ms; per-row strips filled by this split walk with atomic appends (0.92 ms) + a writer that
+// looks every column up in a shared-memory bitmap (4.0 ms) or assembles 32 KB segments in shared memory (3.3 ms).
+// cudaMemset2D itself runs at 7.4 TB/s; none of the hand-written row writers came close to it.)
 template <int D>
 __global__ void __launch_bounds__(256) k_basis_dense_split(const DeviceGrid g, const BasisArgs a, uint32_t n1) {
   static_assert(D >= 3, "two trie levels above the prefix groups");
