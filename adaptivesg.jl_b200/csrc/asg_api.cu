@@ -320,6 +320,7 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
       dg.blk_slots = pk.blk_slots;
       dg.blk_tile_coefs = pk.blk_tile_coefs;
       dg.blk_pair_ok = pk.blk_pair_ok ? 1 : 0;
+      dg.blk_wide = pk.blk_wide ? 1 : 0;
     }
   }
   CK(cudaStreamSynchronize(st));
@@ -382,7 +383,7 @@ int install_pack(asg_grid *g, PackResult &pk) {
   I.block_records = g->blk_ok ? (int64_t)pk.brec.size() : 0;
   I.block_tiles = g->blk_ok ? (int64_t)pk.btiles.size() : 0;
   I.block_stack = g->blk_ok ? pk.blk_slots : 0;
-  I.block_pair = (g->blk_ok && pk.blk_pair_ok) ? 1 : 0;
+  I.block_pair = (g->blk_ok && pk.blk_pair_ok && !pk.blk_wide) ? 1 : 0;
   I.packs = g->packs;
   I.delta_nodes = 0;
   if (g->blk_ok) I.device_bytes += (int64_t)(R.d_bcoef.bytes() + R.d_brec.bytes() + R.d_btiles.bytes());
@@ -1877,7 +1878,7 @@ int32_t asg_pack_info(int32_t D, int64_t N, const int64_t *levels, const int64_t
   info->block_records = info->block ? (int64_t)pk.brec.size() : 0;
   info->block_tiles = info->block ? (int64_t)pk.btiles.size() : 0;
   info->block_stack = info->block ? pk.blk_slots : 0;
-  info->block_pair = (info->block && pk.blk_pair_ok) ? 1 : 0;
+  info->block_pair = (info->block && pk.blk_pair_ok && !pk.blk_wide) ? 1 : 0;
   if (!pk.canonical) t_err = pk.why;
   else if (!pk.blk_ok) t_err = "no BLOCK layout: " + pk.blk_why;
   return ASG_OK;

@@ -36,7 +36,7 @@
 
 namespace asg {
 
-constexpr int kBlkMaxBudget = 7;     // suffix budget r <= 7  <=>  suffix levels <= 8 (register tables)
+constexpr int kBlkMaxBudget = 9;     // suffix budget r <= 9  <=>  suffix levels <= 10 (levels above 4 are formed on the fly)
 // doubles per shared-memory coefficient tile: the packer takes the largest candidate whose walk (two buffers of it,
 // the records, the coordinates and the prefix stack of 1024 points) still fits the 227 KB of an SM
 constexpr int kBlkTileCandidates[] = {6144, 4608, 3072, 2048, 1024};
@@ -64,6 +64,7 @@ ASG_HD constexpr uint32_t blk_size2(int r) { return blk_size(2, r); }           
 ASG_HD constexpr uint32_t blk_offA(int lA, int r) { return blk_off(3, lA, r); }    // 3-D chunk: start of level lA of A
 ASG_HD constexpr uint32_t blk_size3(int r) { return blk_size(3, r); }              // 1, 7, 25, 69, 177, 441, 1073, 2561
 static_assert(blk_size2(7) == 705 && blk_size3(7) == 2561 && blk_n1(7) == 129, "suffix block sizes");
+static_assert(blk_n1(9) == 513 && blk_size2(9) <= (uint32_t)kBlkTileCoefsMax, "a 2-D block of the largest budget fits a tile");
 // Deeper compiled suffixes for prefixes that leave little budget: half of the prefix vectors of a regular grid
 // leave r = 0 (one term), a quarter r = 1. Where a SHORTER prefix (S = 4, 5, 6 compiled dimensions) still has a
 // small budget, ONE record with a compiled S-dimensional suffix replaces all the records below it.
@@ -98,21 +99,21 @@ struct __align__(16) BlockRec {
   uint32_t odd;    // stage: 1 if level > 2 (index = 2*cell + 1)
 };
 static_assert(sizeof(BlockRec) == 32, "BlockRec is fetched as two 16-byte words");
-// suffix code of a record: a DENSE numbering of the compiled (S, r) pairs, so that the walk's dispatch is one indexed
-// branch. S = 3 the 3-D suffix (r = 0..7: codes 0..7); S = 2 the 2-D suffix of a split record (dimension A is the
-// record's stage or at level 1; codes 8..15); S = 4.. deeper suffixes with r = 1..blk_max_r(S), numbered on from 16.
+// suffix code of a record: a DENSE numbering of the compiled (S, r) pairs. S = 3 the 3-D suffix (r = 0..kBlkMaxBudget);
+// S = 2 the 2-D suffix of a split record (dimension A is the record's stage or at level 1), numbered after them;
+// S = 4.. deeper suffixes with r = 1..blk_max_r(S), numbered on from 2 * (kBlkMaxBudget + 1).
 ASG_HD constexpr uint32_t blk_code_base(int S) {
-  uint32_t b = 16;
+  uint32_t b = 2u * (kBlkMaxBudget + 1);
   for (int s = 4; s < S; ++s) b += (uint32_t)(blk_max_r(s) > 0 ? blk_max_r(s) : 0);
   return b;
 }
 ASG_HD constexpr uint32_t blk_code(int S, int r) {
-  return S == 3 ? (uint32_t)r : (S == 2 ? (uint32_t)(8 + r) : blk_code_base(S) + (uint32_t)(r - 1));
+  return S == 3 ? (uint32_t)r : (S == 2 ? (uint32_t)(kBlkMaxBudget + 1 + r) : blk_code_base(S) + (uint32_t)(r - 1));
 }
 constexpr uint32_t kBlkCodes = blk_code_base(kBlkMaxS + 1);  // number of codes
 ASG_HD inline void blk_decode(uint32_t code, int &S, int &r) {  // host side: packer self-check, persistence
-  if (code < 8) { S = 3; r = (int)code; return; }
-  if (code < 16) { S = 2; r = (int)code - 8; return; }
+  if (code <= (uint32_t)kBlkMaxBudget) { S = 3; r = (int)code; return; }
+  if (code < 2u * (kBlkMaxBudget + 1)) { S = 2; r = (int)code - (kBlkMaxBudget + 1); return; }
   for (int s = 4; s <= kBlkMaxS; ++s)
     if (code < blk_code_base(s + 1)) { S = s; r = (int)(code - blk_code_base(s)) + 1; return; }
   S = -1;
@@ -123,7 +124,7 @@ constexpr uint32_t kBrSave = 1u << 8;    // save the result in slot + 1 (a later
 // PAIR mode of the walk (asg_kernels_block.cuh): two neighbours of the cell-key order share the cell of every level
 // <= kBlkPairLevel in every dimension. A record whose prefix stages all have such levels is flagged kBrShared: the
 // pair has ONE prefix position, so its chunk is read through one address. A grid takes PAIR mode when every other
-// record leaves a suffix budget <= kBlkPairMaxR (always true while budgets are <= 7: a level above 4 spends >= 4).
+// record leaves a suffix budget <= kBlkPairMaxR (always true while total budgets are <= 7: a level above 4 spends >= 4).
 constexpr int kBlkPairLevel = 4;
 constexpr int kBlkPairMaxR = 3;
 constexpr uint32_t kBrShared = 1u << 9;

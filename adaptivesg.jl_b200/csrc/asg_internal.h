@@ -107,6 +107,7 @@ struct DeviceGrid {
   int blk_slots;                    // saved prefix slots the walk needs (<= kBlkMaxSlots)
   int blk_tile_coefs;               // doubles per coefficient tile buffer (chosen by the packer)
   int blk_pair_ok;                  // the record set admits PAIR mode (asg_block.h)
+  int blk_wide;                     // some record has a suffix budget above 7: the WIDE kernels walk this grid
   // sweep engine (caller's node order)
   int64_t N;
   const SweepDim *sw;       // [N][D]
@@ -154,6 +155,7 @@ struct PackResult {
   int blk_slots = 0;
   int blk_tile_coefs = 0;             // coefficient tile size the tiles were cut for
   bool blk_pair_ok = false;           // every record without kBrShared has a budget <= kBlkPairMaxR
+  bool blk_wide = false;              // some record has a suffix budget above 7
   // sweep engine
   std::vector<SweepDim> sw;
   std::vector<uint64_t> sw_low;

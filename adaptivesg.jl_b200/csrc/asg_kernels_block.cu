@@ -28,19 +28,24 @@ static int blk_threads() { return kBlkThreads; }
 
 bool block_kernel_fits(const DeviceGrid &g) { return g.n_btiles > 0 && blk_smem_bytes(g, 1, blk_threads()) <= 227 * 1024; }
 
-extern template cudaError_t blk_launch<1, false, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<1, true, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, false, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, true, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, false, kBlkThreads, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
-extern template cudaError_t blk_launch<2, true, kBlkThreads, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+#define ASG_BLK_EXTERN(R, M, P, W) \
+  extern template cudaError_t blk_launch<R, M, kBlkThreads, P, W>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+ASG_BLK_EXTERN(1, false, false, false) ASG_BLK_EXTERN(1, true, false, false) ASG_BLK_EXTERN(2, false, false, false)
+ASG_BLK_EXTERN(2, true, false, false) ASG_BLK_EXTERN(2, false, true, false) ASG_BLK_EXTERN(2, true, true, false)
+ASG_BLK_EXTERN(1, false, false, true) ASG_BLK_EXTERN(1, true, false, true) ASG_BLK_EXTERN(2, false, false, true)
+ASG_BLK_EXTERN(2, true, false, true)
+#undef ASG_BLK_EXTERN
 
 template <int NT>
 static cudaError_t blk_launch_nt(const DeviceGrid &g, const EvalArgs &a, bool two, bool masked, bool pair, int blocks, size_t smem,
                                  cudaStream_t st) {
-  if (two && pair) return masked ? blk_launch<2, true, NT, true>(g, a, blocks, smem, st) : blk_launch<2, false, NT, true>(g, a, blocks, smem, st);
-  if (two) return masked ? blk_launch<2, true, NT, false>(g, a, blocks, smem, st) : blk_launch<2, false, NT, false>(g, a, blocks, smem, st);
-  return masked ? blk_launch<1, true, NT, false>(g, a, blocks, smem, st) : blk_launch<1, false, NT, false>(g, a, blocks, smem, st);
+  if (g.blk_wide) {  // suffix budgets 8 / 9: the WIDE instantiations (never paired)
+    if (two) return masked ? blk_launch<2, true, NT, false, true>(g, a, blocks, smem, st) : blk_launch<2, false, NT, false, true>(g, a, blocks, smem, st);
+    return masked ? blk_launch<1, true, NT, false, true>(g, a, blocks, smem, st) : blk_launch<1, false, NT, false, true>(g, a, blocks, smem, st);
+  }
+  if (two && pair) return masked ? blk_launch<2, true, NT, true, false>(g, a, blocks, smem, st) : blk_launch<2, false, NT, true, false>(g, a, blocks, smem, st);
+  if (two) return masked ? blk_launch<2, true, NT, false, false>(g, a, blocks, smem, st) : blk_launch<2, false, NT, false, false>(g, a, blocks, smem, st);
+  return masked ? blk_launch<1, true, NT, false, false>(g, a, blocks, smem, st) : blk_launch<1, false, NT, false, false>(g, a, blocks, smem, st);
 }
 
 // PAIR mode pays when most neighbours of the cell-key order share their 2-bit cells. Measured on the D = 10
@@ -51,7 +56,7 @@ static double pair_min_per_cell() {  // read per call: the tests switch it betwe
   return e ? atof(e) : 5.0;
 }
 bool block_pair_mode(const DeviceGrid &g, int64_t M, bool sorted) {
-  if (!sorted || !g.blk_pair_ok || g.D > 15 || pair_min_per_cell() <= 0.0) return false;
+  if (!sorted || !g.blk_pair_ok || g.blk_wide || g.D > 15 || pair_min_per_cell() <= 0.0) return false;
   if (M <= (int64_t)blk_sm_count() * blk_threads() || blk_smem_bytes(g, 2, blk_threads()) > 227 * 1024) return false;
   return (double)M >= pair_min_per_cell() * std::ldexp(1.0, 2 * g.D);
 }

@@ -33,6 +33,7 @@ constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulate
 // that does not is evaluated by a follow-up launch). Wherever all levels on the path to a coefficient are <= kBlkTab
 // the two points read the SAME coefficient: one address, one LDS.64, two DFMA ("SH" below). 16 588 of the 19 448
 // terms of the D = 10 benchmark grid are of that kind.
+static_assert(kBlkMaxBudget == 9, "the dispatch lists the suffix budgets 0..9");
 static_assert(kBlkTab == kBlkPairLevel, "the packer flags shared records with the level the tables cover");
 
 struct __align__(16) BlkSmem {
@@ -334,12 +335,17 @@ __device__ __forceinline__ void blk_record(const BlkPoint<R, PAIR> &pt, const Bl
 
 // the compiled suffix of a staged record, chosen by its code. PAIR kernels compile the unshared form (a prefix level
 // above kBlkTab) only for the small budgets such a prefix can leave on the grids that take PAIR mode (kBlkPairMaxR).
-template <int R, bool MASKED, bool PAIR, bool SH>
+// WIDE kernels additionally compile the suffix budgets 8 and 9 (levels up to 10, e.g. BASELINE configs[4]: D = 4,
+// depth 10); they are separate instantiations because the larger bodies cost the common ones registers (the D = 10
+// benchmark grid walked 4.5 % slower with them in one kernel).
+template <int R, bool MASKED, bool PAIR, bool SH, bool WIDE>
 __device__ __forceinline__ void blk_dispatch(const BlkPoint<R, PAIR> &pt, const BlkStaged<R> &st, int rem, double (&acc)[R]) {
-  // (pairs this build does not compile -- RS above blk_max_r(S) -- get labels outside the code range)
+  // (pairs this build does not compile -- RS above blk_max_r(S), 3-D chunks no tile can hold -- get labels outside
+  // the code range)
 #define BLK_CASE(S, RS)                                                                                      \
-  case ((S <= 3 || RS <= blk_max_r(S)) ? blk_code(S, RS) : 160u + 8u * S + RS):                              \
-    if constexpr ((S <= 3 || RS <= blk_max_r(S)) && (!PAIR || SH || RS <= kBlkPairMaxR))                     \
+  case ((S <= 3 || RS <= blk_max_r(S)) ? blk_code(S, RS) : 160u + 10u * S + RS):                             \
+    if constexpr ((S <= 3 || RS <= blk_max_r(S)) && (!PAIR || SH || RS <= kBlkPairMaxR) &&                   \
+                  (S != 3 || blk_size(3, RS) + 2u <= (uint32_t)kBlkTileCoefsMax) && (WIDE || RS <= 7))       \
       blk_record<S, RS, R, MASKED, PAIR, SH>(pt, st, rem, acc);                                              \
     break;
   // a quarter of the records of a regular grid are single terms (3-D suffix, r = 0): test that first; every other
@@ -347,8 +353,10 @@ __device__ __forceinline__ void blk_dispatch(const BlkPoint<R, PAIR> &pt, const 
   const uint32_t code = st.sw & 0xffu;
   if (code == blk_code(3, 0)) blk_record<3, 0, R, MASKED, PAIR, SH>(pt, st, rem, acc);
   else switch (code) {
-    BLK_CASE(3, 1) BLK_CASE(3, 2) BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7)
+    BLK_CASE(3, 1) BLK_CASE(3, 2) BLK_CASE(3, 3) BLK_CASE(3, 4) BLK_CASE(3, 5) BLK_CASE(3, 6) BLK_CASE(3, 7) BLK_CASE(3, 8)
+    BLK_CASE(3, 9)
     BLK_CASE(2, 0) BLK_CASE(2, 1) BLK_CASE(2, 2) BLK_CASE(2, 3) BLK_CASE(2, 4) BLK_CASE(2, 5) BLK_CASE(2, 6) BLK_CASE(2, 7)
+    BLK_CASE(2, 8) BLK_CASE(2, 9)
     BLK_CASE(4, 1) BLK_CASE(4, 2) BLK_CASE(4, 3) BLK_CASE(4, 4) BLK_CASE(4, 5)
     BLK_CASE(5, 1) BLK_CASE(5, 2) BLK_CASE(5, 3) BLK_CASE(5, 4)
     BLK_CASE(6, 1) BLK_CASE(6, 2) BLK_CASE(6, 3) BLK_CASE(6, 4)
@@ -373,8 +381,9 @@ __device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm,
 }
 
 // registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
-template <int R, bool MASKED, int NT, bool PAIR>
+template <int R, bool MASKED, int NT, bool PAIR, bool WIDE>
 __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_block(const DeviceGrid g, const EvalArgs a) {
+  static_assert(!(PAIR && WIDE), "grids with suffix budgets above 7 do not take PAIR mode");
   static_assert(!PAIR || R >= 2, "PAIR mode shares loads between the points of a thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BlkSmem &sm = *reinterpret_cast<BlkSmem *>(smem_raw);
@@ -508,10 +517,10 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
         blk_stage<R, MASKED, NT>(rbase, ps_t, os_t, xs_t, tbias, a.rem, st, xpre, (uint32_t)(D - 1));
         if constexpr (PAIR) {
           // warp-uniform: every level of the record's prefix is <= kBlkTab, the pair shares the prefix position
-          if (st.sw & kBrShared) blk_dispatch<R, MASKED, true, true>(pt, st, a.rem, acc);
-          else blk_dispatch<R, MASKED, true, false>(pt, st, a.rem, acc);
+          if (st.sw & kBrShared) blk_dispatch<R, MASKED, true, true, false>(pt, st, a.rem, acc);
+          else blk_dispatch<R, MASKED, true, false, false>(pt, st, a.rem, acc);
         } else {
-          blk_dispatch<R, MASKED, false, false>(pt, st, a.rem, acc);
+          blk_dispatch<R, MASKED, false, false, WIDE>(pt, st, a.rem, acc);
         }
       }
       __syncthreads();  // every warp is done with buffer `buf`
@@ -531,13 +540,13 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
 
 // One launch function per (points per thread, masked, paired) variant; each is instantiated in its own translation
 // unit (asg_kernels_block_r{1,2,2p}{,m}.cu) so that the large kernels compile in parallel.
-template <int R, bool MASKED, int NT, bool PAIR>
+template <int R, bool MASKED, int NT, bool PAIR, bool WIDE>
 cudaError_t blk_launch(const DeviceGrid &g, const EvalArgs &a, int blocks, size_t smem, cudaStream_t st) {
   // one instantiation serves every grid: raise its dynamic shared-memory limit once per device to the device maximum
   static std::atomic<unsigned> limit_set{0};
-  const cudaError_t e = smem_limit_once(k_eval_block<R, MASKED, NT, PAIR>, 227 * 1024, limit_set);
+  const cudaError_t e = smem_limit_once(k_eval_block<R, MASKED, NT, PAIR, WIDE>, 227 * 1024, limit_set);
   if (e != cudaSuccess) return e;
-  k_eval_block<R, MASKED, NT, PAIR><<<blocks, NT, smem, st>>>(g, a);
+  k_eval_block<R, MASKED, NT, PAIR, WIDE><<<blocks, NT, smem, st>>>(g, a);
   return cudaSuccess;
 }
 

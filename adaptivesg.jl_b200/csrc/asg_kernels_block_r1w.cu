@@ -1,0 +1,6 @@
+// asg_kernels_block_r1w.cu -- the BLOCK walk with 1 point per thread, unmasked, WIDE (suffix budgets 8 and 9 compiled in) (see asg_kernels_block.cuh)
+#include "asg_kernels_block.cuh"
+
+namespace asg {
+template cudaError_t blk_launch<1, false, kBlkThreads, false, true>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+}  // namespace asg

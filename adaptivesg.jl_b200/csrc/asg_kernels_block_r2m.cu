@@ -2,5 +2,5 @@
 #include "asg_kernels_block.cuh"
 
 namespace asg {
-template cudaError_t blk_launch<2, true, kBlkThreads, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
+template cudaError_t blk_launch<2, true, kBlkThreads, false, false>(const DeviceGrid &, const EvalArgs &, int, size_t, cudaStream_t);
 }  // namespace asg

@@ -156,7 +156,7 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
         pr = &pre.emplace(cur, -1).first->second;
       }
       const int eS = (L[K] - 1) + (L[K + 1] - 1) + (L[K + 2] - 1);
-      if (eS > kBlkMaxBudget) return no("suffix budget > 7");
+      if (eS > kBlkMaxBudget) return no("suffix budget > 9");
       *pr = std::max(*pr, eS);
     }
   }
@@ -324,6 +324,7 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     q.sw = (save ? kBrSave : 0u) | ((uint32_t)used << kBrUsedShift);
   };
   out.blk_pair_ok = true;
+  out.blk_wide = false;
   for (auto &kv : recs) {
     const Key &p = kv.first;
     const Rec &I = kv.second;
@@ -342,6 +343,7 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     } else if (!I.split) {
       q.sw |= blk_code(I.S, I.r);
       if (!shared && I.r > kBlkPairMaxR) out.blk_pair_ok = false;
+      if (I.r > 7) out.blk_wide = true;
       q.cbase = I.cbase;
       out.brec.push_back(q);
       lo.push_back(I.cbase);
@@ -355,6 +357,7 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
         }
         if (shared && lA <= kBlkPairLevel) s.sw |= kBrShared;
         else if (rA > kBlkPairMaxR) out.blk_pair_ok = false;
+        if (rA > 7) out.blk_wide = true;
         s.sw |= blk_code(2, rA);
         s.cbase = I.cbaseA[lA - 1];
         out.brec.push_back(s);

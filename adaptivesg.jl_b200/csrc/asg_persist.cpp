@@ -33,7 +33,7 @@ uint64_t checksum(const unsigned char *p, size_t n) {
 }
 
 uint64_t layout_fingerprint() {  // everything a blob's bytes depend on besides the grid itself
-  const uint32_t c[] = {3u /* format version */, kBlkCodes, (uint32_t)kBlkPairLevel, (uint32_t)kBlkPairMaxR, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
+  const uint32_t c[] = {5u /* format version */, kBlkCodes, (uint32_t)kBlkMaxBudget, (uint32_t)kBlkPairLevel, (uint32_t)kBlkPairMaxR, (uint32_t)sizeof(TrieRec), (uint32_t)sizeof(GroupRec), (uint32_t)sizeof(BlockRec),
                         (uint32_t)sizeof(StreamTile), (uint32_t)sizeof(BlockTile), (uint32_t)sizeof(HashEnt),
                         (uint32_t)sizeof(SweepDim), (uint32_t)sizeof(RsgParams), (uint32_t)kLeafTable, (uint32_t)kTileCoefs,
                         (uint32_t)kTileRecs, (uint32_t)kBlkTileCoefsMax, (uint32_t)kBlkTileRecs, (uint32_t)kBlkMaxS,
@@ -91,7 +91,7 @@ void fields(IO &io, PK &pk) {  // one list for both directions
   io.vec(pk.coef); io.pod(pk.coef_pad); io.vec(pk.orig); io.vec(pk.hent); io.vec(pk.horig); io.vec(pk.slot_of_node);
   io.vec(pk.grp); io.vec(pk.tiles); io.pod(pk.regular); io.pod(pk.rp);
   io.pod(pk.blk_ok); io.str(pk.blk_why); io.vec(pk.bcoef); io.vec(pk.brec); io.vec(pk.btiles); io.vec(pk.bslot_of_node);
-  io.pod(pk.blk_slots); io.pod(pk.blk_tile_coefs); io.pod(pk.blk_pair_ok); io.vec(pk.sw); io.vec(pk.sw_low); io.vec(pk.depth);
+  io.pod(pk.blk_slots); io.pod(pk.blk_tile_coefs); io.pod(pk.blk_pair_ok); io.pod(pk.blk_wide); io.vec(pk.sw); io.vec(pk.sw_low); io.vec(pk.depth);
 }
 
 }  // namespace

@@ -114,6 +114,19 @@ def test_cfg5_basis_against_oracle(asg, oracle):
     rng = np.random.default_rng(5)
     OG.coefs = rng.standard_normal(len(OG))
     G = _mirror(asg, OG)
+    # evaluation of this grid takes the BLOCK walk since round 2 (suffix budgets up to 9 = levels up to 10)
+    assert G.info()["block"] == 1
+    Xe = np.vstack([rng.random((4000, 4)), rng.integers(0, 1025, size=(500, 4)) / 1024.0])
+    Xe[::97, 1] = 1.0 + 1e-12
+    we, se = OG.evaluate(Xe, return_abssum=True)
+    for path in ("block", "stream", "sweep"):
+        G.set_path(path)
+        assert_close(G.evaluate(Xe), we, se, f"cfg5 evaluation, {path}")
+        assert_close(G.evaluate(Xe, max_depth=7), OG.evaluate(Xe, max_depth=7), se, f"cfg5 evaluation, depth <= 7, {path}")
+    G.set_path("auto")
+    big = rng.random((300000, 4))                                   # two points per thread, ordered batch
+    yb = G.evaluate(big)
+    assert_close(yb[:3000], OG.evaluate(big[:3000]), None, "cfg5 large batch")
     X = rng.random((200, 4))
     X[:20] = rng.integers(0, 513, size=(20, 4)) / 512.0             # knots: extra supporting nodes with value 0 drop out
     B = asg.basis(X, G).toarray()

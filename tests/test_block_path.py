@@ -49,8 +49,13 @@ def test_block_layout_regular_grids(asg):
     asg.rsg(G, 7, 5)
     rc, info, msg = _pack_info(asg, G.levels, G.indices)
     assert rc == 0 and info["block"] == 1 and info["block_records"] == 1 and info["block_slots"] == 1073, msg  # caps: padding
-    # outside the layout's limits: D < 3, suffix levels > 8
-    for D, depth in [(2, 5), (4, 10)]:
+    # BASELINE configs[4] (D = 4, depth 10): suffix budgets up to 9 since round 2 (the WIDE kernels), never paired
+    G = asg.SparseGridInterpolant(4)
+    asg.rsg(G, 10, 10)
+    rc, info, msg = _pack_info(asg, G.levels, G.indices)
+    assert rc == 0 and info["block"] == 1 and info["block_slots"] == 46721 and info["block_pair"] == 0, msg
+    # outside the layout's limits: D < 3, suffix levels > 10
+    for D, depth in [(2, 5), (4, 12)]:
         G = asg.SparseGridInterpolant(D)
         asg.rsg(G, depth, depth)
         rc, info, msg = _pack_info(asg, G.levels, G.indices)
@@ -101,7 +106,8 @@ def _grids(oracle):
     out = []
     for D, depth, ml, keepfrac, unit in [(3, 8, 8, 1.0, False), (3, 7, (5, 6, 4), 0.8, True), (4, 7, 7, 1.0, True), (10, 5, 5, 1.0, True), (6, 6, (4, 5, 6, 3, 6, 6), 1.0, False),
                                          (5, 6, 6, 0.9, False), (7, 4, 4, 0.7, True), (4, 8, 8, 1.0, False),
-                                         (12, 3, 3, 1.0, True)]:
+                                         (12, 3, 3, 1.0, True),
+                                         (3, 10, 10, 1.0, True), (4, 10, 10, 1.0, False)]:   # suffix budgets 8 and 9 (levels up to 10)
         lb = np.zeros(D) if unit else -rng.random(D)
         ub = np.ones(D) if unit else 1.0 + rng.random(D)
         OG = oracle.OracleGrid(D, lb=lb, ub=ub)
