@@ -853,3 +853,57 @@ def test_append_without_repacking(asg, oracle):
                                         np.array([[0, 1]], dtype=np.int64).ctypes.data_as(asg._capi.i64p), 2, 1,
                                         np.array([0.5]).ctypes.data_as(asg._capi.f64p)))
     assert H.info()["packs"] == p1 + 1 and H.info()["canonical"] == 0      # a repeated node: the sweep engine takes over
+
+
+def test_fuzz_engines_against_oracle(asg, oracle):
+    """benchmarks/fuzz_paths.py compares the engines with each other (good at layout bugs, blind to a shared misreading
+    of the reference); this is the same kind of random grid -- dimension, depth, level caps, node subsets, domains,
+    adapt!-grown -- with every engine compared to the ORACLE's long-double sum, unmasked and depth-masked."""
+    rng = np.random.default_rng(20261020)
+    done = 0
+    for t in range(60):
+        D = int(rng.integers(1, 11))
+        depth = int(rng.integers(2, {1: 11, 2: 10, 3: 9, 4: 8}.get(D, 6 if D <= 7 else 5)))
+        caps = tuple(int(v) for v in rng.integers(2, depth + 2, size=D)) if rng.random() < 0.5 else depth
+        lb = np.zeros(D) if rng.random() < 0.4 else -rng.random(D) * 3
+        ub = np.ones(D) if rng.random() < 0.4 else lb + 0.5 + rng.random(D) * 4
+        OG = oracle.OracleGrid(D, lb=lb, ub=ub)
+        OG.rsg(depth, caps)
+        if len(OG) > 60000:
+            continue
+        mode = rng.choice(["full", "subset", "adapt"])
+        if mode == "subset":
+            keep = rng.random(len(OG)) < rng.choice([0.97, 0.8, 0.5])
+            keep[0] = True
+            OG.levels, OG.indices, OG.depths = OG.levels[keep], OG.indices[keep], OG.depths[keep]
+        OG.coefs = rng.standard_normal(len(OG.levels)) * 2.0 ** (-rng.random() * OG.depths)
+        OG.fvals = np.zeros(len(OG.levels))
+        G = _mirror(asg, OG)
+        if mode == "adapt" and D <= 4 and len(OG) < 3000:
+            c = rng.random(D)
+            f = lambda x, lb=lb, ub=ub, c=c: float(np.exp(-np.sum(((np.asarray(x) - lb) / (ub - lb) - c) ** 2) * 8.0))
+            tol = 10.0 ** -int(rng.integers(2, 4))
+            extra = int(rng.integers(1, 3))
+            OG.train(f, depth, caps)
+            OG.adapt(f, depth + extra, tol=tol)
+            G = asg.SparseGridInterpolant(D, lb=lb, ub=ub)
+            asg.train(G, f, depth, caps)
+            asg.adapt(G, f, depth + extra, tol=tol, verbose=False)
+            assert len(G) == len(OG), (t, D, depth)
+            OG.levels, OG.indices, OG.depths, OG.coefs, OG.fvals = G.levels, G.indices, G.depths, G.coefs, G.fvals
+        M = 400
+        u = rng.random((M, D))
+        u[rng.random((M, D)) < 0.05] = rng.integers(0, 65) / 64.0          # knots
+        u[::37, rng.integers(0, D)] = rng.choice([1.0, 0.0, 1.25, -0.5, np.nan])
+        X = lb + (ub - lb) * u
+        L = int(rng.integers(1, int(OG.depths.max()) + 1))
+        want, sc = OG.evaluate(X, return_abssum=True)
+        wantm = OG.evaluate(X, max_depth=L)
+        info = G.info()
+        paths = ["sweep"] + (["stream", "trie"] + (["block"] if info["block"] else []) if info["canonical"] else [])
+        for p in paths:
+            G.set_path(p)
+            assert_close(G.evaluate(X), want, sc, f"grid {t} D={D} depth={depth} {mode} {p}")
+            assert_close(G.evaluate(X, max_depth=L), wantm, sc, f"grid {t} D={D} depth={depth} {mode} {p} depth<={L}")
+        done += 1
+    assert done >= 40
