@@ -682,7 +682,8 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
 int eval_host_dev(asg_grid *g, int r, const double *X, int64_t M, int64_t sp, int64_t sdim, const double *fvals,
                   int64_t max_depth, double *out) {
   if (int rc = use_dev(r)) return rc;
-  const int64_t S = pipe_super();
+  // a super-batch keeps its points on the device: at most pipe_super() points and at most 8 GiB of coordinates
+  const int64_t S = std::max<int64_t>(pipe_piece(), std::min<int64_t>(pipe_super(), ((int64_t)8 << 30) / (8 * (int64_t)g->D)));
   for (int64_t m0 = 0; m0 < M; m0 += S) {
     const int64_t cnt = std::min(S, M - m0);
     if (int rc = eval_super(g, r, X + m0 * sp, cnt, sp, sdim, fvals ? fvals + m0 : nullptr, max_depth, out + m0)) return rc;
