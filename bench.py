@@ -360,6 +360,10 @@ def main():
     value = M_total / (ms_per_step * 1e-3)
     checksum = float(out.sum().item())
     del full
+    # a sample of THE BENCHMARKED LAUNCH itself (points and results of the timed, device-resident, paired walk) for the
+    # oracle comparison below
+    sidx = torch.randint(0, M, (1000,), device=dev, generator=gen)
+    X_sample, y_sample = X[sidx].cpu().numpy(), out[sidx].cpu().numpy()
 
     # ---- e2e: the public API with pinned host buffers (H2D and D2H inside the timed region) ------
     e2e = None
@@ -495,12 +499,22 @@ def main():
         if not np.all(okp):
             raise SystemExit(f"PARITY FAILURE on the benchmarked grid: {np.count_nonzero(~okp)} of {ns} points out of "
                              f"tolerance, worst error {float(err.max()):.3e}")
+        # ... and of the timed launch itself: 1 000 points drawn from the device-resident batch with the results the
+        # benchmarked (ordered, paired) walk wrote for them
+        want2, sc2 = OG.evaluate(X_sample, return_abssum=True)
+        err2 = np.abs(y_sample - want2)
+        ok2 = (err2 <= 1e-12 * np.abs(want2)) | (err2 <= 1e-14 * np.maximum(1.0, sc2))
+        if not np.all(ok2):
+            raise SystemExit(f"PARITY FAILURE in the benchmarked launch: {np.count_nonzero(~ok2)} of {len(want2)} sampled points "
+                             f"out of tolerance, worst error {float(err2.max()):.3e}")
         cpu = {"value": rate, "unit": "points/s", "cores": cores, "kind": "port",
                "sample": f"{n} of {M_total} points in {sec:.1f} s, restated reference algorithm "
                          "(src/class.jl:635-642), -O2 OpenMP over points (generous to the reference: Julia's broadcast "
                          "also allocates N doubles per point)",
                "max_abs_diff_vs_gpu": float(np.max(np.abs(ygpu - ycpu))),
                "parity_vs_long_double_oracle": {"points": int(ns), "max_abs_err": float(err.max()),
+                                                "timed_launch_sample_points": int(len(want2)),
+                                                "timed_launch_sample_max_abs_err": float(err2.max()),
                                                 "tolerance": "1e-12 rel | 1e-14 * max(1, sum|c*phi|) abs", "asserted": True}}
 
     # a second CPU row from the reference ITSELF, if somebody has run tests/golden/dump_reference.jl (Julia >= 1.9): its
