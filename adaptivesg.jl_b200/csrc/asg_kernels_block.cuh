@@ -24,7 +24,10 @@
 
 namespace asg {
 
-constexpr int kBlkThreads = 512;  // default CTA size (384 threads x 168 registers was measured 6 % slower)
+#ifndef ASG_BLK_THREADS
+#define ASG_BLK_THREADS 512  // build knob: 384 gives 168 registers per thread (3 warps per sub-partition); see DESIGN.md section 8
+#endif
+constexpr int kBlkThreads = ASG_BLK_THREADS;  // CTA size of the walk
 // threads of the CTA as a function of the points per thread: a CTA always owns 1 024 points at R >= 2
 __host__ __device__ constexpr int blk_nt(int R) { return R == 4 ? 256 : kBlkThreads; }
 constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulated in registers
