@@ -122,35 +122,54 @@ cudaError_t launch_scatter_hash(HashEnt *dst, const long long *slots, const doub
   return cudaGetLastError();
 }
 
-// In-place ascending sort of every CSR row by column index: one CTA per row, bitonic network over the
-// row padded (virtually) to a power of two. Rows are short (one entry per subspace at most).
+// In-place ascending sort of every CSR row by column index: one CTA per row, bitonic network over the row padded
+// (virtually) to a power of two. Rows are short (one entry per subspace at most): rows of up to kSortRowsSmem entries
+// are sorted in shared memory (round 1 sorted every row in global memory: 6.9 ms for the 5e4 x 715 entries of BASELINE
+// configs[4], eight times the fill pass that produced them).
+constexpr int kSortRowsSmem = 2048;
+
+template <class KeyArr, class ValArr>
+__device__ __forceinline__ void bitonic_rows(KeyArr c, ValArr v, long long n) {
+  long long np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  // all-ascending form of the network (first step of each merge mirrors with i ^ (k-1)): every comparator puts the
+  // smaller key at the smaller index, so the virtual +inf padding at positions >= n never moves and comparators
+  // touching it can simply be skipped.
+  for (long long k = 2; k <= np2; k <<= 1) {
+    for (long long j = k >> 1; j > 0; j >>= 1) {
+      const long long mask = (j == (k >> 1)) ? (k - 1) : j;
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long ixj = i ^ mask;
+        if (ixj > i && ixj < n) {
+          const long long a = c[i], b = c[ixj];
+          if (a > b) {
+            c[i] = b; c[ixj] = a;
+            const double t = v[i]; v[i] = v[ixj]; v[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void k_sort_rows(const long long *row_ptr, long long *colidx, double *vals, int64_t M) {
+  __shared__ long long sc[kSortRowsSmem];
+  __shared__ double sv[kSortRowsSmem];
   for (int64_t m = blockIdx.x; m < M; m += gridDim.x) {
     const long long p0 = row_ptr[m];
     const long long n = row_ptr[m + 1] - p0;
     if (n < 2) continue;
-    long long np2 = 1;
-    while (np2 < n) np2 <<= 1;
     long long *c = colidx + p0;
     double *v = vals + p0;
-    // all-ascending form of the network (first step of each merge mirrors with i ^ (k-1)): every
-    // comparator puts the smaller key at the smaller index, so the virtual +inf padding at
-    // positions >= n never moves and comparators touching it can simply be skipped.
-    for (long long k = 2; k <= np2; k <<= 1) {
-      for (long long j = k >> 1; j > 0; j >>= 1) {
-        const long long mask = (j == (k >> 1)) ? (k - 1) : j;
-        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-          const long long ixj = i ^ mask;
-          if (ixj > i && ixj < n) {
-            const long long a = c[i], b = c[ixj];
-            if (a > b) {
-              c[i] = b; c[ixj] = a;
-              const double t = v[i]; v[i] = v[ixj]; v[ixj] = t;
-            }
-          }
-        }
-        __syncthreads();
-      }
+    if (n <= kSortRowsSmem) {
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) { sc[i] = c[i]; sv[i] = v[i]; }
+      __syncthreads();
+      bitonic_rows(sc, sv, n);
+      for (long long i = threadIdx.x; i < n; i += blockDim.x) { c[i] = sc[i]; v[i] = sv[i]; }
+      __syncthreads();
+    } else {
+      bitonic_rows(c, v, n);
     }
   }
 }
