@@ -85,8 +85,8 @@ def test_cfg3_full_size_against_oracle(asg, cfg3):
         al = G.surplus(X, f, max_depth=L)
         assert_close(al[sub], f[sub] - wm, scm + np.abs(f[sub]), f"cfg3 full size, surplus depth <= {L}")
     assert np.array_equal(G.evaluate(X, max_depth=8), y)            # depth 8 is the whole grid
-    # PAIR mode of the walk (neighbours of the cell-key order share their coefficient loads; default from ~8 points per
-    # 2-bit cell on, i.e. 8.4e6 points for D = 10): forced on here, where most pairs straddle a cell boundary and go to
+    # PAIR mode of the walk (neighbours of the cell-key order share their coefficient loads; default from 5 points per
+    # 2-bit cell on, i.e. 5.2e6 points for D = 10): forced on here, where most pairs straddle a cell boundary and go to
     # the follow-up launch -- the sums do not depend on the mode, bit for bit
     import os
     os.environ["ASG_BLOCK_PAIR"] = "1e-9"
