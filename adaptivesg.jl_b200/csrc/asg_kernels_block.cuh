@@ -426,6 +426,10 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
     // flags: bit k: point k lies in the domain; bit 8 + k: point k's result is stored by this launch
     uint32_t flags = ((1u << R) - 1u) << 8;
     uint32_t code2[R];     // PAIR: the cells of level <= kBlkTab of every dimension (2 bits each)
+    // The raw coordinates travel global -> shared as asynchronous 8-byte copies, ALL of a thread's R x D in flight at
+    // once (the rows of an ordered batch are a random gather; loaded one by one in front of scale()'s divide they cost
+    // one DRAM latency per coordinate -- 4.6 % of the kernel's time in the round-2 profile). Each thread then
+    // transforms its own column in place; a thread reads only what it copied itself, so no barrier is needed.
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       // PAIR: a thread owns R NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
@@ -433,10 +437,17 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
       const int64_t jj = j < M ? j : M - 1;  // tail lanes redo the last point, never store
       if (j >= M) flags &= ~(0x100u << k);
       const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
+      const double *row = a.X + mm * a.sp;
+      for (int d = 0; d < D; ++d)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_t + (uint32_t)((d * R + k) * NT) * 8u), "l"(row + d * a.sd) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
       bool in = true;
       uint32_t c2 = 0u;
       for (int d = 0; d < D; ++d) {
-        const double xd = a.X[mm * a.sp + d * a.sd];
+        const double xd = xs[(d * R + k) * NT + tid];
         const double u = __dadd_rn(0.0, __ddiv_rn(__dsub_rn(xd, g.lb[d]), g.width[d]));  // scale(), src/math.jl:308
         in = in && (u >= 0.0) && (u <= 1.0);                                             // NaN fails both
         xs[(d * R + k) * NT + tid] = u;
