@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libasg_cuda.so")
+# ASG_CUDA_LIB: another build of the library (A/B measurements of kernel variants on one machine)
+LIB_PATH = os.environ.get("ASG_CUDA_LIB") or os.path.join(_HERE, "lib", "libasg_cuda.so")
 
 ASG_OK = 0
 ASG_EINVAL = -1

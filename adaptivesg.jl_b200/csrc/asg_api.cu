@@ -243,6 +243,8 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
   DeviceGrid &dg = R.dg;
   dg = DeviceGrid{};
   dg.D = D;
+  std::vector<BlockRec> blk_drec;    // live until the stream is drained at the end of the function
+  std::vector<BlockTile> blk_dtiles;
   for (int d = 0; d < D; ++d) {
     dg.lb[d] = g->lb[d];
     volatile double w = g->ub[d] - g->lb[d];  // (from_ub .- from_lb), src/math.jl:308
@@ -307,15 +309,31 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
     dg.horig = R.d_horig.p;
     if (pk.blk_ok) {
       if (int rc = R.d_bcoef.reserve(pk.bcoef.size())) return rc;
-      if (int rc = R.d_brec.reserve(pk.brec.size())) return rc;
-      if (int rc = R.d_btiles.reserve(pk.btiles.size())) return rc;
+      // device record stream: a header record in front of every tile (blk_tile_header, asg_block.h)
+      const size_t ntl = pk.btiles.size();
+      std::vector<uint32_t> at(ntl);
+      uint32_t pos = 0;
+      for (size_t t = 0; t < ntl; ++t) {
+        at[t] = pos;
+        pos += 1u + (pk.btiles[t].r1 - pk.btiles[t].r0);
+      }
+      blk_drec.resize(pos);
+      blk_dtiles.resize(ntl);
+      for (size_t t = 0; t < ntl; ++t) {
+        const BlockTile &tl = pk.btiles[t];
+        blk_drec[at[t]] = blk_tile_header(tl, t + 2 < ntl ? &pk.btiles[t + 2] : nullptr, t + 2 < ntl ? at[t + 2] : 0u);
+        std::copy(pk.brec.begin() + tl.r0, pk.brec.begin() + tl.r1, blk_drec.begin() + at[t] + 1);
+        blk_dtiles[t] = BlockTile{at[t], at[t] + 1u + (tl.r1 - tl.r0), tl.c0, tl.c1};
+      }
+      if (int rc = R.d_brec.reserve(blk_drec.size())) return rc;
+      if (int rc = R.d_btiles.reserve(blk_dtiles.size())) return rc;
       CK(cudaMemcpyAsync(R.d_bcoef.p, pk.bcoef.data(), pk.bcoef.size() * 8, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(R.d_brec.p, pk.brec.data(), pk.brec.size() * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(R.d_btiles.p, pk.btiles.data(), pk.btiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_brec.p, blk_drec.data(), blk_drec.size() * sizeof(BlockRec), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(R.d_btiles.p, blk_dtiles.data(), blk_dtiles.size() * sizeof(BlockTile), cudaMemcpyHostToDevice, st));
       dg.bcoef = R.d_bcoef.p;
       dg.brec = R.d_brec.p;
       dg.btiles = R.d_btiles.p;
-      dg.n_brec = (uint32_t)pk.brec.size();
+      dg.n_brec = (uint32_t)blk_drec.size();
       dg.n_btiles = (uint32_t)pk.btiles.size();
       dg.blk_slots = pk.blk_slots;
       dg.blk_tile_coefs = pk.blk_tile_coefs;

@@ -133,5 +133,21 @@ constexpr int kBrUsedShift = 16;         // used = sum(l-1) over the prefix (S2:
 struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)
   uint32_t r0, r1, c0, c1;
 };
+// DEVICE copy of the record stream: every tile's records are preceded by a HEADER record, so that the kernel learns
+// a tile's extent -- and the extent of the tile after next, which it has to request -- from the shared-memory copy of
+// the tile itself instead of a table in global memory. `at[t]` is the device index of tile t's header; the device tile
+// table counts the header in [r0, r1).
+inline BlockRec blk_tile_header(const BlockTile &t, const BlockTile *next2, uint32_t next2_at) {
+  BlockRec h{};
+  h.cbase = t.c0;        // first coefficient slot of the tile
+  h.sw = t.r1 - t.r0;    // records behind the header
+  if (next2) {
+    h.b = next2_at;                                                  // device index of the header of tile t + 2
+    h.s_hi = (1u + next2->r1 - next2->r0) * (uint32_t)sizeof(BlockRec);  // its bytes, header included
+    h.lim = next2->c0;                                               // its coefficient slots
+    h.odd = next2->c1 - next2->c0;
+  }
+  return h;
+}
 
 }  // namespace asg

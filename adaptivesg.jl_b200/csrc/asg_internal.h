@@ -101,8 +101,8 @@ struct DeviceGrid {
   uint32_t n_grp, n_tiles;
   // BLOCK layout (asg_block.h): present when the grid is (nearly) regular in its last three dimensions
   const double *bcoef;
-  const BlockRec *brec;
-  const BlockTile *btiles;
+  const BlockRec *brec;      // device record stream: a header record in front of every tile (blk_tile_header)
+  const BlockTile *btiles;   // [r0, r1) counts the header
   uint32_t n_brec, n_btiles;
   int blk_slots;                    // saved prefix slots the walk needs (<= kBlkMaxSlots)
   int blk_tile_coefs;               // doubles per coefficient tile buffer (chosen by the packer)

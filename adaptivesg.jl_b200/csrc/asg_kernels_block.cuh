@@ -40,8 +40,11 @@ static_assert(kBlkMaxBudget == 9, "the dispatch lists the suffix budgets 0..9");
 static_assert(kBlkTab == kBlkPairLevel, "the packer flags shared records with the level the tables cover");
 
 struct __align__(16) BlkSmem {
-  BlockRec rec[2][kBlkTileRecs];
+  BlockRec rec[2][kBlkTileRecs + 1];  // a tile's header record (blk_tile_header, asg_block.h) + its records
   unsigned long long bar[2];
+  unsigned done[2];  // warps that have left the tile in buffer b (wraps at the warp count: the last one out refills it)
+  unsigned pad_[2];
+  BlockTile first[2];  // tiles 0 and 1, which open every batch
   // followed by  double coef[2][tile_coefs]  (the two coefficient tile buffers; size chosen by the packer),
   //              double xs[D][R][threads]  (unit-cube coordinates of every dimension),
   //              double Ps[slots][R][threads], uint32_t Os[slots][R][threads]  (saved prefixes)
@@ -370,17 +373,20 @@ __device__ __forceinline__ void blk_dispatch(const BlkPoint<R, PAIR> &pt, const 
 #undef BLK_CASE
 }
 
-// producer side (one thread): start the copies of tile t into buffer `buf`
-__device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm, uint32_t t, int buf) {
-  const BlockTile tl = g.btiles[t];
-  const uint32_t rbytes = (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
-  const uint32_t cbytes = (tl.c1 - tl.c0) * 8u;
+// producer side (one thread): start the copies of a tile -- rbytes of records from device record r0 on (header first),
+// cc coefficient slots from c0 on -- into buffer `buf`
+__device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm, uint32_t r0, uint32_t rbytes, uint32_t c0,
+                                               uint32_t cc, int buf) {
+  const uint32_t cbytes = cc * 8u;
   // the buffer was last read through the generic proxy: order those reads before the async-proxy writes
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(&sm.bar[buf], rbytes + cbytes);
-  tma_load_1d(sm.rec[buf], g.brec + tl.r0, rbytes, &sm.bar[buf]);
+  tma_load_1d(sm.rec[buf], g.brec + r0, rbytes, &sm.bar[buf]);
   if (cbytes)
-    tma_load_1d(reinterpret_cast<double *>(&sm + 1) + (size_t)buf * g.blk_tile_coefs, g.bcoef + tl.c0, cbytes, &sm.bar[buf]);
+    tma_load_1d(reinterpret_cast<double *>(&sm + 1) + (size_t)buf * g.blk_tile_coefs, g.bcoef + c0, cbytes, &sm.bar[buf]);
+}
+__device__ __forceinline__ void blk_issue_tile(const DeviceGrid &g, BlkSmem &sm, const BlockTile tl, int buf) {
+  blk_issue_tile(g, sm, tl.r0, (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec), tl.c0, tl.c1 - tl.c0, buf);
 }
 
 // registers per thread: the whole file for one CTA per SM (65536 / threads, in units of 8)
@@ -409,6 +415,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
   if (tid == 0) {
     mbar_init(&sm.bar[0], 1);
     mbar_init(&sm.bar[1], 1);
+    sm.done[0] = sm.done[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 #pragma unroll
@@ -416,6 +423,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
     Ps[k * NT + tid] = 1.0;
     Os[k * NT + tid] = 0u;
   }
+  if (tid < 2u && tid < ntiles) sm.first[tid] = g.btiles[tid];
   __syncthreads();
   uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
 
@@ -496,8 +504,8 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
       }
     }
     if (tid == 0) {
-      blk_issue_tile(g, sm, 0, 0);
-      if (ntiles > 1) blk_issue_tile(g, sm, 1, 1);
+      blk_issue_tile(g, sm, sm.first[0], 0);
+      if (ntiles > 1) blk_issue_tile(g, sm, sm.first[1], 1);
     }
     double acc[R];
 #pragma unroll
@@ -505,17 +513,22 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
 
     for (uint32_t t = 0; t < ntiles; ++t) {
       const int buf = (int)(t & 1u);
-      const BlockTile tl = g.btiles[t];
       mbar_wait(&sm.bar[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
-      uint32_t rbase = smem_u32(sm.rec[buf]);
-      uint32_t tbias = smem_u32(coefbuf + (size_t)buf * g.blk_tile_coefs) - tl.c0 * 8u;  // shared byte address of coefficient slot 0
+      // the tile's header record came in with the tile: first coefficient slot and number of records (the tile table in
+      // global memory cost an L2 round trip in front of each of the 182 tiles of the benchmark grid: 3.7 % of the
+      // stall samples of the round-2 profile)
+      const uint32_t hbase = smem_u32(sm.rec[buf]);
+      uint32_t tl_c0, tl_nrec;
+      asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(tl_c0), "=r"(tl_nrec) : "r"(hbase));
+      uint32_t rbase = hbase + (uint32_t)sizeof(BlockRec);
+      uint32_t tbias = smem_u32(coefbuf + (size_t)buf * g.blk_tile_coefs) - tl_c0 * 8u;  // shared byte address of coefficient slot 0
       pin_u32(rbase);
       pin_u32(tbias);
       pin_u32(xs_t);  // keep the three column addresses in registers: ptxas would re-derive them per record
       pin_u32(ps_t);
       pin_u32(os_t);
-      const uint32_t rend = rbase + (tl.r1 - tl.r0) * (uint32_t)sizeof(BlockRec);
+      const uint32_t rend = rbase + tl_nrec * (uint32_t)sizeof(BlockRec);
       double xpre[R];
 #ifdef ASG_BLK_PREFETCH_X
       {
@@ -537,9 +550,21 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
           blk_dispatch<R, MASKED, false, false, WIDE>(pt, st, a.rem, acc);
         }
       }
-      __syncthreads();  // every warp is done with buffer `buf`
-      if (tid == 0 && t + 2 < ntiles) blk_issue_tile(g, sm, t + 2, buf);
+      // No CTA-wide barrier per tile (182 per batch on the benchmark grid, 2.4 % of the stall samples): every warp
+      // counts itself out of the buffer and goes on to the next tile; the LAST one out starts the refill. The warps
+      // drift at most two tiles apart (a refill needs all of them).
+      __syncwarp();
+      if ((tid & 31u) == 0u) {
+        __threadfence_block();  // the warp's reads of the buffer are done before it is counted out
+        if (atomicInc(&sm.done[buf], (unsigned)(NT / 32 - 1)) == (unsigned)(NT / 32 - 1) && t + 2 < ntiles) {
+          __threadfence_block();
+          uint32_t nr0, nrb, nc0, ncc;  // the header also names the tile after next
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(nr0), "=r"(nrb), "=r"(nc0), "=r"(ncc) : "r"(hbase));
+          blk_issue_tile(g, sm, nr0, nrb, nc0, ncc, buf);
+        }
+      }
     }
+    __syncthreads();  // both buffers are free again before the next batch's first tiles are issued
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       if ((flags >> (8 + k)) & 1u) {
