@@ -426,6 +426,11 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
   if (tid < 2u && tid < ntiles) sm.first[tid] = g.btiles[tid];
   __syncthreads();
   uint32_t phases = 0u;  // bit b: parity the next wait on buffer b expects
+  // row-wise fetch of the points (see the loader below): lane = row_sub * D + row_d fetches coordinate row_d of the
+  // row_sub-th of the 32 / D points one instruction covers
+  const uint32_t row_ppi = 32u / (uint32_t)D;
+  const uint32_t row_sub = (tid & 31u) / (uint32_t)D, row_d = (tid & 31u) - row_sub * (uint32_t)D;
+  const uint32_t xs_w = xs_t - (tid & 31u) * 8u;  // column of lane 0 of this warp
 
   for (int64_t base = (int64_t)blockIdx.x * tile_pts; base < M; base += stride) {
     BlkPoint<R, PAIR> pt;
@@ -434,22 +439,48 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
     // flags: bit k: point k lies in the domain; bit 8 + k: point k's result is stored by this launch
     uint32_t flags = ((1u << R) - 1u) << 8;
     uint32_t code2[R];     // PAIR: the cells of level <= kBlkTab of every dimension (2 bits each)
-    // The raw coordinates travel global -> shared as asynchronous 8-byte copies, ALL of a thread's R x D in flight at
-    // once (the rows of an ordered batch are a random gather; loaded one by one in front of scale()'s divide they cost
-    // one DRAM latency per coordinate -- 4.6 % of the kernel's time in the round-2 profile). Each thread then
-    // transforms its own column in place; a thread reads only what it copied itself, so no barrier is needed.
+    // The first two tiles are requested before anything else of the batch: they arrive while the points are fetched.
+    if (tid == 0) {
+      blk_issue_tile(g, sm, sm.first[0], 0);
+      if (ntiles > 1) blk_issue_tile(g, sm, sm.first[1], 1);
+    }
+    // The raw coordinates travel global -> shared as asynchronous 8-byte copies, ALL of them in flight at once (the
+    // rows of an ordered batch are a random gather; loaded one by one in front of scale()'s divide they cost one DRAM
+    // latency per coordinate). Row-major points: D lanes fetch one row, so that a warp instruction touches 32 / D rows
+    // (3 rows of 80 bytes for D = 10) instead of 32 different ones, each lane copying into the column of the thread that
+    // owns the point. Each thread then transforms its own column in place.
+    int64_t mm[R];
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       // PAIR: a thread owns R NEIGHBOURS of the cell-key order; otherwise its points are a CTA width apart
       const int64_t j = PAIR ? base + R * (int64_t)tid + k : base + (int64_t)k * NT + tid;
       const int64_t jj = j < M ? j : M - 1;  // tail lanes redo the last point, never store
       if (j >= M) flags &= ~(0x100u << k);
-      const int64_t mm = a.perm ? (int64_t)a.perm[jj] : jj;
-      const double *row = a.X + mm * a.sp;
-      for (int d = 0; d < D; ++d)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_t + (uint32_t)((d * R + k) * NT) * 8u), "l"(row + d * a.sd) : "memory");
+      mm[k] = a.perm ? (int64_t)a.perm[jj] : jj;
+    }
+    if (a.sd == 1) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        for (uint32_t i = 0; i < 32u; i += row_ppi) {
+          const uint32_t src = i + row_sub;  // lane that owns the point this lane helps to fetch
+          const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)mm[k], (int)(src & 31u));
+          const uint32_t hi = __shfl_sync(0xffffffffu, (uint32_t)((uint64_t)mm[k] >> 32), (int)(src & 31u));
+          if (row_sub < row_ppi && src < 32u) {
+            const double *p = a.X + (int64_t)(((uint64_t)hi << 32) | lo) * a.sp + row_d;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_w + src * 8u + (uint32_t)((row_d * R + k) * NT) * 8u), "l"(p) : "memory");
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const double *row = a.X + mm[k] * a.sp;
+        for (int d = 0; d < D; ++d)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(xs_t + (uint32_t)((d * R + k) * NT) * 8u), "l"(row + d * a.sd) : "memory");
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();  // the copies into a thread's column were made by other lanes of its warp
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       bool in = true;
@@ -502,10 +533,6 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
         pin_f64(pt.phC[k][l]);
         pin_f64(pt.phB[k][l]);
       }
-    }
-    if (tid == 0) {
-      blk_issue_tile(g, sm, sm.first[0], 0);
-      if (ntiles > 1) blk_issue_tile(g, sm, sm.first[1], 1);
     }
     double acc[R];
 #pragma unroll

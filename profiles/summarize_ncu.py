@@ -108,7 +108,12 @@ def main():
         src = ncu_csv(rep, "source")
         h = src[1]
         ia, isrc, ismp = h.index("Instructions Executed"), h.index("Source"), h.index("# Samples")
-        body = [(int(r[ismp] or 0), int(r[ia] or 0), r[isrc].strip()) for r in src[2:] if len(r) > ismp]
+        first = src[2:]
+        for n, r in enumerate(first):  # the page lists every profiled launch in turn: keep the first kernel
+            if r and r[0] == "Kernel Name":
+                first = first[:n]
+                break
+        body = [(int(r[ismp] or 0), int(r[ia] or 0), r[isrc].strip()) for r in first if len(r) > ismp and r[0] != "Address"]
         tot_s, tot_i = sum(b[0] for b in body) or 1, sum(b[1] for b in body) or 1
         with open(name + "_hot_sass.txt", "w") as f:
             f.write(f"# {src[0][1] if len(src[0]) > 1 else ''}\n# total warp instructions {tot_i}, stall samples {tot_s}\n")
