@@ -406,7 +406,7 @@ def main():
     asg._capi.check(lib.asg_measure_fp64_peak(C.byref(fma_rate)))
     block = bool(info.get("block")) and os.environ.get("ASG_EVAL_KERNEL", "b")[0] == "b"
     kname = "k_eval_block<2,false,512,PAIR>" if block else f"k_eval_stream<{D},R,false>"
-    prof_names = (["r02x_eval_block_d10_summary.json", "r02_eval_block_d10_summary.json", "r01b_final_eval_block_d10_summary.json"] if block
+    prof_names = (["r02z_eval_block_d10_summary.json", "r02_eval_block_d10_summary.json", "r01b_final_eval_block_d10_summary.json"] if block
                   else ["r01_final_eval_stream_d10_summary.json"])
     k_ms = statistics.median(kern_ms)
     pts_per_launch = M
