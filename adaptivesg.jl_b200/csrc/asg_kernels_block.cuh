@@ -7,7 +7,10 @@
 //   stream for them; one CTA per SM, grid-stride over the points.
 // * Records (32 B, pre-decoded, one per prefix level vector) and the coefficient blocks they reference are streamed
 //   from L2 into shared memory by 1-D TMA bulk copies (cp.async.bulk, SASS UBLKCP) completed on
-//   mbarriers, double buffered.
+//   mbarriers, double buffered. A tile starts with a header record (its extent and the extent of the tile that takes
+//   the buffer next), so the walk reads no table from global memory; the warps are not synchronised per tile: each
+//   counts itself out of a buffer and the last one out requests the refill.
+// * The points of a batch arrive as asynchronous 8-byte copies (cp.async, SASS LDGSTS), D lanes per row.
 // * A record applies ONE data-driven stage (the level of its last non-trivial prefix dimension) to the
 //   prefix product / position saved by its parent record (a small stack in shared memory), then runs
 //   the COMPILED walk of the last three dimensions: the kernel is templated on the suffix budget, all
