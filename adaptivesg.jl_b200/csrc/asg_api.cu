@@ -310,21 +310,7 @@ int device_upload(asg_grid *g, int r, const PackResult &pk) {
     if (pk.blk_ok) {
       if (int rc = R.d_bcoef.reserve(pk.bcoef.size())) return rc;
       // device record stream: a header record in front of every tile (blk_tile_header, asg_block.h)
-      const size_t ntl = pk.btiles.size();
-      std::vector<uint32_t> at(ntl);
-      uint32_t pos = 0;
-      for (size_t t = 0; t < ntl; ++t) {
-        at[t] = pos;
-        pos += 1u + (pk.btiles[t].r1 - pk.btiles[t].r0);
-      }
-      blk_drec.resize(pos);
-      blk_dtiles.resize(ntl);
-      for (size_t t = 0; t < ntl; ++t) {
-        const BlockTile &tl = pk.btiles[t];
-        blk_drec[at[t]] = blk_tile_header(tl, t + 2 < ntl ? &pk.btiles[t + 2] : nullptr, t + 2 < ntl ? at[t + 2] : 0u);
-        std::copy(pk.brec.begin() + tl.r0, pk.brec.begin() + tl.r1, blk_drec.begin() + at[t] + 1);
-        blk_dtiles[t] = BlockTile{at[t], at[t] + 1u + (tl.r1 - tl.r0), tl.c0, tl.c1};
-      }
+      block_device_stream(pk, blk_drec, blk_dtiles);
       if (int rc = R.d_brec.reserve(blk_drec.size())) return rc;
       if (int rc = R.d_btiles.reserve(blk_dtiles.size())) return rc;
       CK(cudaMemcpyAsync(R.d_bcoef.p, pk.bcoef.data(), pk.bcoef.size() * 8, cudaMemcpyHostToDevice, st));

@@ -137,6 +137,7 @@ struct BlockTile {  // records [r0, r1) read coefficient slots inside [c0, c1)
 // a tile's extent -- and the extent of the tile after next, which it has to request -- from the shared-memory copy of
 // the tile itself instead of a table in global memory. `at[t]` is the device index of tile t's header; the device tile
 // table counts the header in [r0, r1).
+constexpr int kBlkTileBufs = 2;  // tile buffers of the walk: tile t + kBlkTileBufs takes the buffer of tile t
 inline BlockRec blk_tile_header(const BlockTile &t, const BlockTile *next2, uint32_t next2_at) {
   BlockRec h{};
   h.cbase = t.c0;        // first coefficient slot of the tile

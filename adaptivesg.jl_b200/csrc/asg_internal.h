@@ -174,6 +174,12 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
                 bool selfcheck, PackResult &out, std::string &err);
 // host model of the BLOCK walk of asg_kernels_block.cu for one unit-cube point (packer self-check, tests)
 double block_walk_host(int D, const PackResult &pk, const double *x01, int rem);
+// device form of the BLOCK record stream: a header record in front of every tile (blk_tile_header, asg_block.h);
+// dtiles[t] = tile t with [r0, r1) in device record numbers, header included
+void block_device_stream(const PackResult &pk, std::vector<BlockRec> &drec, std::vector<BlockTile> &dtiles);
+// follows the stream the way the kernel does (first tiles from the table, every later one from the header of the tile
+// that held its buffer) and compares what it meets with the packed records
+bool block_device_stream_ok(const PackResult &pk, std::string &why);
 
 // device-format persistence (asg_persist.cpp): node arrays + every packed layout as one blob
 void pack_serialize(int D, const double *lb, const double *ub, const std::vector<int64_t> &levels,

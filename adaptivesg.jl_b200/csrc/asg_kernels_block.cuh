@@ -42,6 +42,7 @@ constexpr int kBlkTab = 4;  // levels 2..kBlkTab of dimensions B, C are tabulate
 static_assert(kBlkMaxBudget == 9, "the dispatch lists the suffix budgets 0..9");
 static_assert(kBlkTab == kBlkPairLevel, "the packer flags shared records with the level the tables cover");
 
+static_assert(kBlkTileBufs == 2, "BlkSmem, the phase bits and the buffer index are written for two buffers");
 struct __align__(16) BlkSmem {
   BlockRec rec[2][kBlkTileRecs + 1];  // a tile's header record (blk_tile_header, asg_block.h) + its records
   unsigned long long bar[2];
@@ -586,7 +587,7 @@ __global__ void __maxnreg__(NT == 512 ? 128 : (NT == 256 ? 255 : 168)) k_eval_bl
       __syncwarp();
       if ((tid & 31u) == 0u) {
         __threadfence_block();  // the warp's reads of the buffer are done before it is counted out
-        if (atomicInc(&sm.done[buf], (unsigned)(NT / 32 - 1)) == (unsigned)(NT / 32 - 1) && t + 2 < ntiles) {
+        if (atomicInc(&sm.done[buf], (unsigned)(NT / 32 - 1)) == (unsigned)(NT / 32 - 1) && t + kBlkTileBufs < ntiles) {
           __threadfence_block();
           uint32_t nr0, nrb, nc0, ncc;  // the header also names the tile after next
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];" : "=r"(nr0), "=r"(nrb), "=r"(nc0), "=r"(ncc) : "r"(hbase));

@@ -439,7 +439,74 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     }
   }
   if (!synth.empty()) std::fill(out.bcoef.begin(), out.bcoef.end(), 0.0);
+  {  // the device form of the record stream must lead the walk through exactly these records (cheap: every pack)
+    std::string why;
+    if (!block_device_stream_ok(out, why)) {
+      err = "internal error: BLOCK device record stream: " + why;
+      out.blk_ok = false;
+      return ASG_ESTATE;
+    }
+  }
   return ASG_OK;
+}
+
+void block_device_stream(const PackResult &pk, std::vector<BlockRec> &drec, std::vector<BlockTile> &dtiles) {
+  const size_t ntl = pk.btiles.size();
+  std::vector<uint32_t> at(ntl);
+  uint32_t pos = 0;
+  for (size_t t = 0; t < ntl; ++t) {
+    at[t] = pos;
+    pos += 1u + (pk.btiles[t].r1 - pk.btiles[t].r0);
+  }
+  drec.assign(pos, BlockRec{});
+  dtiles.resize(ntl);
+  for (size_t t = 0; t < ntl; ++t) {
+    const BlockTile &tl = pk.btiles[t];
+    const size_t n2 = t + (size_t)kBlkTileBufs;
+    drec[at[t]] = blk_tile_header(tl, n2 < ntl ? &pk.btiles[n2] : nullptr, n2 < ntl ? at[n2] : 0u);
+    std::copy(pk.brec.begin() + tl.r0, pk.brec.begin() + tl.r1, drec.begin() + at[t] + 1);
+    dtiles[t] = BlockTile{at[t], at[t] + 1u + (tl.r1 - tl.r0), tl.c0, tl.c1};
+  }
+}
+
+bool block_device_stream_ok(const PackResult &pk, std::string &why) {
+  std::vector<BlockRec> drec;
+  std::vector<BlockTile> dtiles;
+  block_device_stream(pk, drec, dtiles);
+  const size_t ntl = pk.btiles.size();
+  struct Req { uint32_t r0, rbytes, c0, cc; };  // what blk_issue_tile is given
+  Req buf[kBlkTileBufs] = {};
+  for (int b = 0; b < kBlkTileBufs && (size_t)b < ntl; ++b)
+    buf[b] = Req{dtiles[(size_t)b].r0, (dtiles[(size_t)b].r1 - dtiles[(size_t)b].r0) * (uint32_t)sizeof(BlockRec), dtiles[(size_t)b].c0,
+                 dtiles[(size_t)b].c1 - dtiles[(size_t)b].c0};
+  size_t next_rec = 0;  // packed records met so far
+  for (size_t t = 0; t < ntl; ++t) {
+    const Req q = buf[t % kBlkTileBufs];
+    const BlockTile &tl = pk.btiles[t];
+    if (q.rbytes % sizeof(BlockRec) || q.rbytes > (uint32_t)((kBlkTileRecs + 1) * sizeof(BlockRec)) ||
+        (size_t)q.r0 + q.rbytes / sizeof(BlockRec) > drec.size() || q.cc > (uint32_t)pk.blk_tile_coefs ||
+        (size_t)q.c0 + q.cc > pk.bcoef.size() || ((q.c0 | q.cc) & 1u)) {  // 16-byte granules for the bulk copies
+      why = "tile " + std::to_string(t) + ": request outside the stream or larger than a buffer";
+      return false;
+    }
+    const BlockRec &h = drec[q.r0];
+    const uint32_t nrec = h.sw;
+    if (h.cbase != tl.c0 || q.c0 != tl.c0 || q.cc != tl.c1 - tl.c0 || nrec != tl.r1 - tl.r0 || nrec + 1u != q.rbytes / sizeof(BlockRec)) {
+      why = "tile " + std::to_string(t) + ": header does not describe the tile";
+      return false;
+    }
+    for (uint32_t k = 0; k < nrec; ++k, ++next_rec)
+      if (next_rec != (size_t)tl.r0 + k || std::memcmp(&drec[q.r0 + 1u + k], &pk.brec[next_rec], sizeof(BlockRec)) != 0) {
+        why = "tile " + std::to_string(t) + ": records out of order";
+        return false;
+      }
+    if (t + (size_t)kBlkTileBufs < ntl) buf[t % kBlkTileBufs] = Req{h.b, h.s_hi, h.lim, h.odd};
+  }
+  if (next_rec != pk.brec.size()) {
+    why = "the tiles do not cover the record stream";
+    return false;
+  }
+  return true;
 }
 
 // The walk of asg_kernels_block.cu, one point, plain loops: records in order, one stage per record from

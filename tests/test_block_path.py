@@ -24,7 +24,8 @@ def _pack_info(asg, levels, indices):
 
 def test_block_layout_regular_grids(asg):
     """asg_pack_info runs the packer's self-check (host model of the kernel's walk against the direct sum
-    over the nodes, with and without a depth mask) for every grid of at most 50 000 nodes."""
+    over the nodes, with and without a depth mask) for every grid of at most 50 000 nodes, and on every pack follows the
+    DEVICE form of the record stream (tile headers, block_device_stream_ok) from tile to tile the way the kernel does."""
     for D, depth, ml, nrec in [(4, 6, 6, 1), (5, 5, 5, 1), (6, 7, (6, 7, 8, 9, 10, 11), None), (10, 5, 5, None),
                                (7, 4, (2, 3, 4, 4, 2, 3, 4), None), (12, 3, 3, None)]:
         G = asg.SparseGridInterpolant(D)
