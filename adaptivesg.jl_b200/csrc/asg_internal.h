@@ -5,7 +5,12 @@
 
 #include <atomic>
 #include <mutex>
+#include <algorithm>
 #include <string>
+#include <thread>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "asg_cuda.h"
@@ -164,6 +169,30 @@ struct PackResult {
 
 // Validate + pack. levels/indices: row-major N x D copies owned by the caller. Returns ASG_OK,
 // ASG_EINVALID_NODE (and err) or ASG_EUNSUPPORTED.
+// ASG_PACK_TIMING=1: phases of the host packer on stderr (diagnostic)
+struct PackTimer {
+  const char *name;
+  std::chrono::steady_clock::time_point t0;
+  bool on;
+  explicit PackTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("ASG_PACK_TIMING") != nullptr) {}
+  ~PackTimer() {
+    if (on) fprintf(stderr, "[asg pack] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+};
+// host threads of the packer's data-parallel passes (ASG_PACK_THREADS overrides; small grids stay serial)
+int pack_threads(int64_t N);
+// fn(t, n0, n1) on nth contiguous ranges of [0, N), one host thread each
+template <class F>
+inline void pack_parallel(int64_t N, int nth, F fn) {
+  if (nth <= 1) { fn(0, (int64_t)0, N); return; }
+  std::vector<std::thread> th;
+  const int64_t per = (N + nth - 1) / nth;
+  for (int t = 0; t < nth; ++t) {
+    const int64_t n0 = std::min<int64_t>(N, (int64_t)t * per), n1 = std::min<int64_t>(N, n0 + per);
+    th.emplace_back([=]() { fn(t, n0, n1); });
+  }
+  for (auto &x : th) x.join();
+}
 int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, const double *coefs,
               PackResult &out, std::string &err);
 

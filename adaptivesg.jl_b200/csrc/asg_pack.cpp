@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "asg_internal.h"
 
@@ -30,8 +31,19 @@ static inline uint32_t hash_slot(uint32_t pos, int lg) {
   return lg == 0 ? 0u : (uint32_t)((pos * 0x9E3779B1u) >> (32 - lg));
 }
 
+int pack_threads(int64_t N) {
+  if (N < (1 << 15)) return 1;
+  static const int v = [] {
+    const char *e = getenv("ASG_PACK_THREADS");
+    int t = e ? atoi(e) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    return std::max(1, std::min(t, 64));
+  }();
+  return v;
+}
+
 int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, const double *coefs,
               PackResult &out, std::string &err) {
+  PackTimer t_all("pack_grid total");
   out = PackResult();
   out.sw.resize((size_t)N * D);
   out.sw_low.assign((size_t)N, 0);
@@ -49,52 +61,94 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
   std::vector<uint32_t> cells;  // N x D cell numbers (BLOCK layout)
   if (canonical) { lv.resize((size_t)N * D); pos.resize((size_t)N); cells.resize((size_t)N * D); }
 
+  // per-node pass (validation, sweep words, level bytes, cells, subspace position): independent per node, so large
+  // grids are scanned by a few host threads; errors and demotions are merged to what the serial scan reports (the
+  // first offending node in input order)
+  struct Scan {
+    int err_code = ASG_OK;
+    std::string err_msg;
+    int64_t err_n = -1;
+    bool canon = true;
+    const char *why = "";
+    int64_t why_n = -1;
+    int max_level = 0;
+    int64_t max_depth = 0;
+  };
+  const bool canon0 = canonical;
+  auto scan = [&](int64_t n0, int64_t n1, Scan &sc) {
+    sc.canon = canon0;
+    auto demote_l = [&](const char *w, int64_t n) {
+      if (sc.canon) { sc.canon = false; sc.why = w; sc.why_n = n; }
+    };
+    for (int64_t n = n0; n < n1; ++n) {
+      int64_t dsum = 0;
+      uint64_t p = 0;
+      int tb = 0;
+      for (int d = 0; d < D; ++d) {
+        const int64_t l = levels[n * D + d], i = indices[n * D + d];
+        // the rule of phi(x, l, i), src/math.jl:345-357: these are the pairs it throws on
+        if (l < 1 || (l == 2 && i != 0 && i != 2)) {
+          sc.err_msg = "invalid level-index pair (" + std::to_string(l) + ", " + std::to_string(i) + ") at node " +
+                       std::to_string(n) + ", dim " + std::to_string(d);
+          sc.err_code = ASG_EINVALID_NODE;
+          sc.err_n = n;
+          return;
+        }
+        if (l > 62) { sc.err_msg = "level > 62 is not supported"; sc.err_code = ASG_EUNSUPPORTED; sc.err_n = n; return; }
+        dsum += l;
+        sc.max_level = std::max<int>(sc.max_level, (int)l);
+        SweepDim &s = out.sw[(size_t)n * D + d];
+        if (l == 1) {
+          s.s = 0.0; s.c = 0.0;
+          out.sw_low[n] |= (1ull << d);
+          if (i != 1) demote_l("level-1 index != 1", n);
+        } else {
+          s.s = std::ldexp(1.0, (int)(l - 1));  // power2(l-1), src/math.jl:59-61
+          s.c = (double)i;                       // Int -> Float64 promotion in x*2^(l-1) - i
+          if (l == 2) out.sw_low[n] |= (1ull << d);
+        }
+        if (sc.canon) {
+          if (l > kMaxLevelFast) { demote_l("level > 32", n); continue; }
+          if (l > 2 && (i < 1 || !(i & 1) || i > ((int64_t)1 << (l - 1)) - 1)) { demote_l("index out of range", n); continue; }
+          const int b = cell_bits((int)l);
+          const uint64_t cell = l == 1 ? 0 : (l == 2 ? (uint64_t)(i >> 1) : (uint64_t)((i - 1) >> 1));
+          if (tb + b > kMaxPosBits) { demote_l("subspace position needs more than 32 bits", n); continue; }
+          // dims 0..D-2: concatenate (dim 0 most significant); the last dim goes on top of them
+          if (d < D - 1 || D == 1) p = (b ? (p << b) : p) | cell;
+          else p |= cell << tb;
+          tb += b;
+          lv[(size_t)n * D + d] = (uint8_t)l;
+          cells[(size_t)n * D + d] = (uint32_t)cell;
+        }
+      }
+      const int64_t depth = dsum - D + 1;
+      if (depth > 0x3fffffff) { sc.err_msg = "depth overflow"; sc.err_code = ASG_EUNSUPPORTED; sc.err_n = n; return; }
+      out.depth[n] = (int32_t)depth;
+      sc.max_depth = std::max(sc.max_depth, depth);
+      if (sc.canon) pos[n] = (uint32_t)p;
+    }
+  };
+  const int nth = pack_threads(N);
+  std::vector<Scan> scans((size_t)nth);
+  {
+    PackTimer t_scan("per-node scan");
+    pack_parallel(N, nth, [&](int t, int64_t n0, int64_t n1) { scan(n0, n1, scans[(size_t)t]); });
+  }
   int max_level = 0;
   int64_t max_depth = 0;
-  for (int64_t n = 0; n < N; ++n) {
-    int64_t dsum = 0;
-    uint64_t p = 0;
-    int tb = 0;
-    for (int d = 0; d < D; ++d) {
-      const int64_t l = levels[n * D + d], i = indices[n * D + d];
-      // the rule of phi(x, l, i), src/math.jl:345-357: these are the pairs it throws on
-      if (l < 1 || (l == 2 && i != 0 && i != 2)) {
-        err = "invalid level-index pair (" + std::to_string(l) + ", " + std::to_string(i) + ") at node " +
-              std::to_string(n) + ", dim " + std::to_string(d);
-        return ASG_EINVALID_NODE;
-      }
-      if (l > 62) { err = "level > 62 is not supported"; return ASG_EUNSUPPORTED; }
-      dsum += l;
-      max_level = std::max<int>(max_level, (int)l);
-      SweepDim &s = out.sw[(size_t)n * D + d];
-      if (l == 1) {
-        s.s = 0.0; s.c = 0.0;
-        out.sw_low[n] |= (1ull << d);
-        if (i != 1) demote("level-1 index != 1");
-      } else {
-        s.s = std::ldexp(1.0, (int)(l - 1));  // power2(l-1), src/math.jl:59-61
-        s.c = (double)i;                       // Int -> Float64 promotion in x*2^(l-1) - i
-        if (l == 2) out.sw_low[n] |= (1ull << d);
-      }
-      if (canonical) {
-        if (l > kMaxLevelFast) { demote("level > 32"); continue; }
-        if (l > 2 && (i < 1 || !(i & 1) || i > ((int64_t)1 << (l - 1)) - 1)) { demote("index out of range"); continue; }
-        const int b = cell_bits((int)l);
-        const uint64_t cell = l == 1 ? 0 : (l == 2 ? (uint64_t)(i >> 1) : (uint64_t)((i - 1) >> 1));
-        if (tb + b > kMaxPosBits) { demote("subspace position needs more than 32 bits"); continue; }
-        // dims 0..D-2: concatenate (dim 0 most significant); the last dim goes on top of them
-        if (d < D - 1 || D == 1) p = (b ? (p << b) : p) | cell;
-        else p |= cell << tb;
-        tb += b;
-        lv[(size_t)n * D + d] = (uint8_t)l;
-        cells[(size_t)n * D + d] = (uint32_t)cell;
-      }
+  {
+    const Scan *first_err = nullptr, *first_dem = nullptr;
+    for (const Scan &sc : scans) {
+      max_level = std::max(max_level, sc.max_level);
+      max_depth = std::max(max_depth, sc.max_depth);
+      if (sc.err_code != ASG_OK && (!first_err || sc.err_n < first_err->err_n)) first_err = &sc;
+      if (canon0 && !sc.canon && (!first_dem || sc.why_n < first_dem->why_n)) first_dem = &sc;
     }
-    const int64_t depth = dsum - D + 1;
-    if (depth > 0x3fffffff) { err = "depth overflow"; return ASG_EUNSUPPORTED; }
-    out.depth[n] = (int32_t)depth;
-    max_depth = std::max(max_depth, depth);
-    if (canonical) pos[n] = (uint32_t)p;
+    if (first_err) {  // the serial scan stops at the first invalid node
+      err = first_err->err_msg;
+      return first_err->err_code;
+    }
+    if (first_dem) demote(first_dem->why);
   }
   out.max_level = max_level;
   out.max_depth = max_depth;
@@ -104,12 +158,40 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
     std::vector<int64_t> perm((size_t)N);
     std::iota(perm.begin(), perm.end(), (int64_t)0);
     const uint8_t *L = lv.data();
-    std::sort(perm.begin(), perm.end(), [&](int64_t a, int64_t b) {
-      const int c = std::memcmp(L + (size_t)a * D, L + (size_t)b * D, (size_t)D);
-      if (c) return c < 0;
-      if (pos[a] != pos[b]) return pos[a] < pos[b];
-      return a < b;
-    });
+    {
+      // order: level vector (bytes, lexicographic), position inside the subspace, node number. The D <= 12 level bytes
+      // are packed big-endian into integers, so the order of the keys is the order memcmp gives; chunks are sorted by a
+      // few threads and merged pairwise.
+      PackTimer t_sort("sort nodes by level vector");
+      static_assert(kMaxDimFast <= 12, "the sort key holds 12 level bytes");
+      struct SortKey {
+        uint64_t hi, lo;  // level bytes 0..7 | level bytes 8..11, position
+        int64_t n;
+        bool operator<(const SortKey &o) const { return hi != o.hi ? hi < o.hi : (lo != o.lo ? lo < o.lo : n < o.n); }
+      };
+      std::vector<SortKey> keys((size_t)N);
+      const int nth = pack_threads(N);
+      const int64_t per = (N + nth - 1) / nth;
+      pack_parallel(N, nth, [&](int, int64_t n0, int64_t n1) {
+        for (int64_t n = n0; n < n1; ++n) {
+          uint64_t hi = 0, lo = 0;
+          for (int d = 0; d < 8; ++d) hi = (hi << 8) | (d < D ? L[(size_t)n * D + d] : 0u);
+          for (int d = 8; d < 12; ++d) lo = (lo << 8) | (d < D ? L[(size_t)n * D + d] : 0u);
+          keys[(size_t)n] = SortKey{hi, (lo << 32) | pos[n], n};
+        }
+        std::sort(keys.begin() + n0, keys.begin() + n1);
+      });
+      for (int64_t width = per; width < N && nth > 1; width *= 2) {  // merge tree over the sorted chunks
+        std::vector<std::thread> th;
+        for (int64_t lo0 = 0; lo0 + width < N; lo0 += 2 * width) {
+          const int64_t mid = lo0 + width, hi0 = std::min<int64_t>(N, lo0 + 2 * width);
+          th.emplace_back([&keys, lo0, mid, hi0]() { std::inplace_merge(keys.begin() + lo0, keys.begin() + mid, keys.begin() + hi0); });
+        }
+        for (auto &x : th) x.join();
+      }
+      for (int64_t k = 0; k < N; ++k) perm[(size_t)k] = keys[(size_t)k].n;
+    }
+    PackTimer t_rest("subspaces, trie, stream layout");
     out.rec.assign((size_t)D, {});
     std::vector<uint64_t> grp_levels;  // per prefix group: levels of dims 0..D-2, 5 bits each
     std::vector<uint8_t> grp_k0, grp_used;
@@ -386,6 +468,7 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
       // install_pack): its BLOCK layout is built but the self-check's comparison of sums would be NaN vs NaN
       bool finite_c = true;
       for (int64_t n = 0; coefs && n < N && finite_c; ++n) finite_c = std::isfinite(coefs[n]);
+      PackTimer t_blk("BLOCK layout (all tile sizes)");
       const int rc = pack_blocks(D, N, lv.data(), cells.data(), perm.data(), coefs, (force_check || N <= 50000) && finite_c, out, err);
       if (rc != ASG_OK) return rc;
     }

@@ -133,6 +133,7 @@ int pack_blocks(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, cons
 
 static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t *cells, const int64_t *perm,
                             const double *coefs, bool selfcheck, int tile_coefs, PackResult &out, std::string &err) {
+  PackTimer t_tile("  BLOCK layout, one tile size");
   out.blk_ok = false;
   out.blk_tile_coefs = tile_coefs;
   out.blk_why.clear();
@@ -266,6 +267,12 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
   if (max_slot >= kBlkMaxSlots) return no("more than 7 non-trivial prefix dimensions on a path");
   if (total > 2ull * (uint64_t)N + 4096ull) return no("padding exceeds the number of nodes");
   out.blk_slots = max_slot + 1;
+  {  // the stack depth is known: a tile size whose walk cannot fit an SM is given up before its storage is laid out
+    const bool last = tile_coefs == kBlkTileCandidates[sizeof(kBlkTileCandidates) / sizeof(int) - 1];
+    if (block_smem_bytes(D, out.blk_slots, tile_coefs, 2, kBlkThreadsWalk) > 227u * 1024u &&
+        !(last && block_smem_bytes(D, out.blk_slots, tile_coefs, 1, kBlkThreadsWalk) <= 227u * 1024u))
+      return no("the walk's shared memory does not fit an SM (tile size)");
+  }
   out.bcoef.assign((size_t)total + 2, 0.0);
   out.bslot_of_node.assign((size_t)N, -1);
   std::vector<double> synth;  // self-check of a coefficient-free pack (asg_pack_info): use synthetic values
@@ -274,43 +281,53 @@ static int pack_blocks_tile(int D, int64_t N, const uint8_t *lv, const uint32_t 
     for (int64_t n = 0; n < N; ++n) synth[(size_t)n] = std::sin(1.0 + 0.37 * (double)n) + 0.25;
     coefs = synth.data();
   }
-  // 5. node slots
+  // 5. node slots (independent per node: a few host threads on large grids)
   {
-    Key cur;
-    const Rec *pi = nullptr;
-    for (int64_t k = 0; k < N; ++k) {
-      const int64_t n = perm[k];
-      const uint8_t *L = lv + (size_t)n * D;
-      const uint32_t *C = cells + (size_t)n * D;
-      if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
-        cur.assign(L, L + K);
-        pi = &recs[cover[cur]];
-      }
-      uint64_t O = 0;
-      for (int d = 0; d < pi->depth; ++d) O = (O << blk_bits(L[d])) | C[d];
-      uint64_t slot;
-      int rr = pi->r;
-      if (!pi->split) {
-        slot = pi->cbase + O * t_size(pi->S, pi->r);
-        for (int j = pi->S; j >= 3; --j) {  // compiled dimensions above the 2-D block, outermost first
-          const int l = L[D - j];
-          slot += t_off(j, l, rr) + (uint64_t)C[D - j] * t_size(j - 1, rr - (l - 1));
-          rr -= l - 1;
+    const int nth = pack_threads(N);
+    std::vector<int> bad((size_t)nth, 0);
+    pack_parallel(N, nth, [&](int th, int64_t k0, int64_t k1) {
+      Key cur;
+      const Rec *pi = nullptr;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int64_t n = perm[k];
+        const uint8_t *L = lv + (size_t)n * D;
+        const uint32_t *C = cells + (size_t)n * D;
+        if (!pi || std::memcmp(cur.data(), L, (size_t)K) != 0) {
+          cur.assign(L, L + K);
+          const auto it = cover.find(cur);  // (find: no insertion from concurrent readers)
+          if (it == cover.end()) { bad[(size_t)th] = 1; return; }
+          const auto ir = recs.find(it->second);
+          if (ir == recs.end()) { bad[(size_t)th] = 1; return; }
+          pi = &ir->second;
         }
-      } else {
-        const int lA = L[K];
-        rr -= lA - 1;
-        slot = pi->cbaseA[lA - 1] + ((O << blk_bits(lA)) | C[K]) * t_size(2, rr);
+        uint64_t O = 0;
+        for (int d = 0; d < pi->depth; ++d) O = (O << blk_bits(L[d])) | C[d];
+        uint64_t slot;
+        int rr = pi->r;
+        if (!pi->split) {
+          slot = pi->cbase + O * t_size(pi->S, pi->r);
+          for (int j = pi->S; j >= 3; --j) {  // compiled dimensions above the 2-D block, outermost first
+            const int l = L[D - j];
+            slot += t_off(j, l, rr) + (uint64_t)C[D - j] * t_size(j - 1, rr - (l - 1));
+            rr -= l - 1;
+          }
+        } else {
+          const int lA = L[K];
+          rr -= lA - 1;
+          slot = pi->cbaseA[lA - 1] + ((O << blk_bits(lA)) | C[K]) * t_size(2, rr);
+        }
+        const int lB = L[K + 1], lC = L[K + 2];
+        slot += (uint64_t)t_off(2, lB, rr) + (uint64_t)C[K + 1] * blk_n1(rr - (lB - 1)) + blk_off1(lC) + C[K + 2];
+        if (slot >= total || out.bslot_of_node[(size_t)n] != -1) { bad[(size_t)th] = 1; return; }  // duplicates were rejected before: packer bug
+        out.bslot_of_node[(size_t)n] = (int64_t)slot;
+        out.bcoef[(size_t)slot] = coefs ? coefs[n] : 0.0;
       }
-      const int lB = L[K + 1], lC = L[K + 2];
-      slot += (uint64_t)t_off(2, lB, rr) + (uint64_t)C[K + 1] * blk_n1(rr - (lB - 1)) + blk_off1(lC) + C[K + 2];
-      if (slot >= total || out.bslot_of_node[(size_t)n] != -1) {  // duplicates were rejected before: packer bug
+    });
+    for (int b : bad)
+      if (b) {
         err = "internal error: block slot out of range or assigned twice";
         return ASG_ESTATE;
       }
-      out.bslot_of_node[(size_t)n] = (int64_t)slot;
-      out.bcoef[(size_t)slot] = coefs ? coefs[n] : 0.0;
-    }
   }
   // 6. records in lexicographic order + the slot span each one reads
   std::vector<uint32_t> lo, hi;

@@ -196,6 +196,45 @@ def test_packer_rejects_and_demotes(asg):
     assert rc == 0 and info["canonical"] == 0 and "ASG_MAX_DIM_FAST" in msg
 
 
+def test_packer_threads_report_like_the_serial_scan(asg):
+    """Large grids are scanned and sorted by several host threads (asg_pack.cpp): errors and demotions must be the ones
+    of the FIRST offending node in input order, whichever thread meets it, and the sort must give the serial order
+    (same subspace / trie counts; the BLOCK layout's packer follows the device record stream on every pack)."""
+    E = asg._capi
+    G = asg.SparseGridInterpolant(8)
+    asg.rsg(G, 7, 7)
+    N = len(G.levels)
+    assert N >= 1 << 15                                   # above the serial threshold
+    rc, info, _ = _pack_info(asg, G.levels, G.indices)
+    assert rc == 0 and info["canonical"] == 1 and info["regular"] == 1 and info["block"] == 1
+    assert info["subspaces"] == 3003 and info["coef_slots"] == N          # C(14, 8) level vectors, every node once
+    rng = np.random.default_rng(3)
+    p = rng.permutation(N)                                # input order must not matter
+    rc, info2, _ = _pack_info(asg, G.levels[p], G.indices[p])
+    assert rc == 0 and {k: info2[k] for k in info if k != "generation"} == {k: info[k] for k in info if k != "generation"}
+    # two invalid pairs, far apart: the first one in input order is reported
+    Lv, Ix = G.levels.copy(), G.indices.copy()
+    k2 = int(np.flatnonzero(Lv[:, 3] == 2)[-1])
+    k1 = int(np.flatnonzero(Lv[:, 5] == 2)[0])
+    assert k1 < k2
+    Ix[k2, 3] = 1
+    Ix[k1, 5] = 1
+    rc, _, msg = _pack_info(asg, Lv, Ix)
+    assert rc == E.ASG_EINVALID_NODE and f"at node {k1}, dim 5" in msg, msg
+    # two demotions of different kinds: the reason of the first node
+    Lv, Ix = G.levels.copy(), G.indices.copy()
+    a = int(np.flatnonzero(Lv[:, 0] == 3)[0])
+    b = int(np.flatnonzero(Lv[:, 1] == 1)[-1])
+    assert a < b
+    Ix[a, 0] = 2                                          # even index at level 3
+    Ix[b, 1] = 3                                          # level-1 index != 1
+    rc, info3, msg = _pack_info(asg, Lv, Ix)
+    assert rc == 0 and info3["canonical"] == 0 and "range" in msg, msg
+    Ix[a, 0] = 1
+    rc, info3, msg = _pack_info(asg, Lv, Ix)
+    assert rc == 0 and info3["canonical"] == 0 and "level-1" in msg, msg
+
+
 def test_math_exports_host_helpers(asg, oracle):
     """The reference exports these next to phi (src/math.jl:9-22); the mirror's versions against the oracle's
     restatement and the docstring known answers (src/math.jl:513-514, 626-627, 997-999)."""
