@@ -43,7 +43,23 @@ struct DevCtx {  // per device: streams and events of this library
   void *stage[kStage] = {};
   cudaEvent_t stage_ev[kStage] = {};
   std::mutex stage_mu;
+  // pinned staging of large PAGEABLE host -> device copies (the feeder of the evaluation pipeline)
+  void *stage_in[kStage] = {};
+  cudaEvent_t stage_in_ev[kStage] = {};
+  std::mutex stage_in_mu;
 };
+constexpr size_t kStagePiece = (size_t)16 << 20;  // bytes per staging buffer
+// ASG_STAGE_HOST=0: leave pageable host buffers to the driver's own staging (A/B knob)
+bool stage_host() {
+  static const bool v = [] { const char *e = getenv("ASG_STAGE_HOST"); return !(e && e[0] == '0'); }();
+  return v;
+}
+bool is_pageable(const void *p) {
+  cudaPointerAttributes at;
+  const bool pinned_or_dev = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type != cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  return !pinned_or_dev;
+}
 
 struct Context {
   std::mutex mu;
@@ -561,6 +577,8 @@ int64_t pipe_super() {
   return v;
 }
 
+int d2h_fast(DevCtx &dc, void *dst, const void *dsrc, size_t bytes, cudaStream_t st);
+
 struct Feeder {  // copy-in side of one super-batch, run by its own host thread
   std::atomic<int64_t> issued{0};  // pieces whose completion event has been recorded
   std::atomic<bool> abort{false};
@@ -604,6 +622,18 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
   cudaStream_t s_in = dc.pipe[0], s_walk = dc.pipe[1], s_out = dc.pipe[2];
   double *dX = R.s_X[0].p, *dOut = R.s_out[0].p, *dF = fvals ? R.s_f[0].p : nullptr;
 
+  // PAGEABLE row-major points (a numpy array, a Julia Matrix): cudaMemcpyAsync would go through the driver's own staging
+  // at a fraction of the PCIe rate. Instead kStage host threads copy 16 MiB chunks into pinned buffers and the feeder
+  // sends them on in order; the piece events are recorded as the chunks pass the piece boundaries.
+  const size_t xbytes = (size_t)cnt * D * 8;
+  std::unique_lock<std::mutex> stage_lk(dc.stage_in_mu, std::defer_lock);
+  bool staged = stage_host() && rowlike && sp == D && xbytes >= 4 * kStagePiece && is_pageable(X) && stage_lk.try_lock();
+  if (staged)
+    for (int k = 0; k < DevCtx::kStage; ++k) {
+      if (!dc.stage_in[k]) CK(cudaHostAlloc(&dc.stage_in[k], kStagePiece, cudaHostAllocDefault));
+      if (!dc.stage_in_ev[k]) CK(cudaEventCreateWithFlags(&dc.stage_in_ev[k], cudaEventDisableTiming));
+    }
+
   Feeder fd;
   std::thread feeder([&]() {
     if (cudaSetDevice(dc.device) != cudaSuccess) { fd.rc = ASG_ECUDA; fd.err = "cudaSetDevice failed in the copy thread"; fd.issued = np; return; }
@@ -612,6 +642,54 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
       fd.rc = e == cudaErrorMemoryAllocation ? ASG_ENOMEM : ASG_ECUDA;
       fd.err = std::string("host -> device copy: ") + cudaGetErrorString(e);
     };
+    if (staged) {
+      constexpr int K = DevCtx::kStage;
+      const int64_t nc = (int64_t)((xbytes + kStagePiece - 1) / kStagePiece);
+      std::atomic<int64_t> sent{0};       // chunks whose H2D copy has been issued (in order)
+      std::atomic<int64_t> filled[K];     // chunks of buffer k that have been copied into it
+      for (int k = 0; k < K; ++k) filled[k] = 0;
+      std::atomic<int> bad{0};
+      std::vector<std::thread> th;
+      for (int k = 0; k < K; ++k)
+        th.emplace_back([&, k]() {
+          cudaSetDevice(dc.device);
+          for (int64_t c = k; c < nc; c += K) {
+            if (c >= K) {  // the buffer's previous chunk must have left for the device
+              while (sent.load(std::memory_order_acquire) <= c - K && !bad.load() && !fd.abort.load()) std::this_thread::yield();
+              if (bad.load() || fd.abort.load()) return;
+              if (cudaEventSynchronize(dc.stage_in_ev[k]) != cudaSuccess) { bad = 1; return; }
+            }
+            const size_t off = (size_t)c * kStagePiece, n = std::min(kStagePiece, xbytes - off);
+            std::memcpy(dc.stage_in[k], (const char *)X + off, n);
+            filled[k].fetch_add(1, std::memory_order_release);
+          }
+        });
+      cudaError_t e = cudaSuccess;
+      int64_t piece = 0;  // next piece whose event is due
+      for (int64_t c = 0; c < nc && e == cudaSuccess && !bad.load() && !fd.abort.load(); ++c) {
+        const int k = (int)(c % K);
+        while (filled[k].load(std::memory_order_acquire) <= c / K && !bad.load() && !fd.abort.load()) std::this_thread::yield();
+        if (bad.load() || fd.abort.load()) break;
+        const size_t off = (size_t)c * kStagePiece, n = std::min(kStagePiece, xbytes - off);
+        e = cudaMemcpyAsync((char *)dX + off, dc.stage_in[k], n, cudaMemcpyHostToDevice, s_in);
+        if (e == cudaSuccess) e = cudaEventRecord(dc.stage_in_ev[k], s_in);
+        if (e == cudaSuccess) sent.store(c + 1, std::memory_order_release);
+        // pieces that are complete on the stream now
+        while (e == cudaSuccess && piece < np && (size_t)std::min(cnt, (piece + 1) * P) * D * 8 <= off + n) {
+          const int64_t p0 = piece * P, pn = std::min(P, cnt - p0);
+          if (fvals) e = cudaMemcpyAsync(dF + p0, fvals + p0, (size_t)pn * 8, cudaMemcpyHostToDevice, s_in);
+          if (e == cudaSuccess) e = cudaEventRecord(R.piece_ev[(size_t)piece], s_in);
+          if (e == cudaSuccess) fd.issued.store(++piece, std::memory_order_release);
+        }
+      }
+      if (e != cudaSuccess || bad.load()) {
+        bad = 1;
+        fail(e != cudaSuccess ? e : cudaErrorUnknown);
+      }
+      for (auto &t : th) t.join();
+      fd.issued = np;
+      return;
+    }
     for (int64_t k = 0; k < np && !fd.abort.load(); ++k) {
       const int64_t p0 = k * P, n = std::min(P, cnt - p0);
       cudaError_t e = cudaSuccess;
@@ -644,6 +722,7 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
 
   int64_t done = 0, prev_p0 = -1, prev_n = 0;
   int wk = 0;
+  const bool out_pageable = stage_host() && is_pageable(out);
   while (done < np) {
     // at least one more piece: wait until its copy has been issued, then until it has arrived
     while (fd.issued.load(std::memory_order_acquire) <= done) std::this_thread::yield();
@@ -667,8 +746,15 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
     a.out = dOut + p0;
     if (int rc = run_eval(g, r, a, s_walk, 0)) return finish(rc);
     e = cudaEventRecord(R.walk_ev[wk], s_walk);
-    // results of the PREVIOUS window go home while this one walks (its walk has finished: we waited for it below)
-    if (e == cudaSuccess && prev_p0 >= 0) e = cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out);
+    // results of the PREVIOUS window go home while this one walks (its walk has finished: we waited for it below);
+    // a pageable destination through the pinned staging of d2h_fast (returns when the copy is done)
+    if (e == cudaSuccess && prev_p0 >= 0) {
+      if (out_pageable) {
+        if (int rc = d2h_fast(dc, out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, s_out)) return finish(rc);
+      } else {
+        e = cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out);
+      }
+    }
     if (e == cudaSuccess) e = cudaEventSynchronize(R.walk_ev[wk]);
     if (e != cudaSuccess) { finish(ASG_ECUDA); return set_err(ASG_ECUDA, std::string("evaluation pipeline: ") + cudaGetErrorString(e)); }
     prev_p0 = p0;
@@ -678,7 +764,13 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
   }
   feeder.join();
   if (fd.rc != ASG_OK) return set_err(fd.rc, fd.err);
-  if (prev_p0 >= 0) CK(cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out));
+  if (prev_p0 >= 0) {
+    if (out_pageable) {
+      if (int rc = d2h_fast(dc, out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, s_out)) return rc;
+    } else {
+      CK(cudaMemcpyAsync(out + prev_p0, dOut + prev_p0, (size_t)prev_n * 8, cudaMemcpyDeviceToHost, s_out));
+    }
+  }
   CK(cudaStreamSynchronize(s_out));
   return ASG_OK;
 }
@@ -731,12 +823,10 @@ int eval_host(asg_grid *g, const double *X, int64_t M, int64_t sp, int64_t sdim,
 // buffers and four host threads move the pieces to their destination in parallel (~25 GB/s). Blocks until done; work
 // queued on `st` before the call is waited for like cudaMemcpy would. Pinned destinations take the direct path.
 int d2h_fast(DevCtx &dc, void *dst, const void *dsrc, size_t bytes, cudaStream_t st) {
-  constexpr size_t kPiece = (size_t)16 << 20;
   if (bytes == 0) return ASG_OK;
-  cudaPointerAttributes at;
-  const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  if (pinned || bytes < 4 * kPiece) {
+  // pieces of 16 MiB for large copies, 2 MiB for medium ones (the result windows of the evaluation pipeline)
+  const size_t kPiece = bytes >= 4 * kStagePiece ? kStagePiece : (size_t)2 << 20;
+  if (!stage_host() || !is_pageable(dst) || bytes < 4 * kPiece) {
     CK(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return ASG_OK;
@@ -744,7 +834,7 @@ int d2h_fast(DevCtx &dc, void *dst, const void *dsrc, size_t bytes, cudaStream_t
   std::lock_guard<std::mutex> lk(dc.stage_mu);
   constexpr int K = DevCtx::kStage;
   for (int k = 0; k < K; ++k) {
-    if (!dc.stage[k]) CK(cudaHostAlloc(&dc.stage[k], kPiece, cudaHostAllocDefault));
+    if (!dc.stage[k]) CK(cudaHostAlloc(&dc.stage[k], kStagePiece, cudaHostAllocDefault));
     if (!dc.stage_ev[k]) CK(cudaEventCreateWithFlags(&dc.stage_ev[k], cudaEventDisableTiming));
   }
   const int64_t np = (int64_t)((bytes + kPiece - 1) / kPiece);
@@ -890,6 +980,10 @@ int32_t asg_shutdown(void) {
       if (dc.stage_ev[k]) cudaEventDestroy(dc.stage_ev[k]);
       dc.stage[k] = nullptr;
       dc.stage_ev[k] = nullptr;
+      if (dc.stage_in[k]) cudaFreeHost(dc.stage_in[k]);
+      if (dc.stage_in_ev[k]) cudaEventDestroy(dc.stage_in_ev[k]);
+      dc.stage_in[k] = nullptr;
+      dc.stage_in_ev[k] = nullptr;
     }
     dc.device = -1;
     dc.stream = nullptr;
