@@ -627,7 +627,8 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
   // sends them on in order; the piece events are recorded as the chunks pass the piece boundaries.
   const size_t xbytes = (size_t)cnt * D * 8;
   std::unique_lock<std::mutex> stage_lk(dc.stage_in_mu, std::defer_lock);
-  bool staged = stage_host() && rowlike && sp == D && xbytes >= 4 * kStagePiece && is_pageable(X) && stage_lk.try_lock();
+  // (column-major points -- Julia's M x D Matrix -- are D contiguous segments per piece, staged the same way)
+  bool staged = stage_host() && ((rowlike && sp == D) || colmajor) && xbytes >= 4 * kStagePiece && is_pageable(X) && stage_lk.try_lock();
   if (staged)
     for (int k = 0; k < DevCtx::kStage; ++k) {
       if (!dc.stage_in[k]) CK(cudaHostAlloc(&dc.stage_in[k], kStagePiece, cudaHostAllocDefault));
@@ -644,9 +645,30 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
     };
     if (staged) {
       constexpr int K = DevCtx::kStage;
-      const int64_t nc = (int64_t)((xbytes + kStagePiece - 1) / kStagePiece);
-      std::atomic<int64_t> sent{0};       // chunks whose H2D copy has been issued (in order)
-      std::atomic<int64_t> filled[K];     // chunks of buffer k that have been copied into it
+      // the copy as a list of contiguous segments of at most one staging buffer each; `pieces` = pipeline pieces that
+      // are complete once the segment is on the stream
+      struct Seg { const char *src; char *dst; size_t n; int64_t pieces; };
+      std::vector<Seg> segs;
+      if (colmajor) {
+        for (int64_t k = 0; k < np; ++k) {
+          const int64_t p0 = k * P, pn = std::min(P, cnt - p0);
+          for (int d = 0; d < D; ++d)
+            for (size_t o = 0; o < (size_t)pn * 8; o += kStagePiece)
+              segs.push_back(Seg{(const char *)(X + p0 + (int64_t)d * sdim) + o, (char *)(dX + (size_t)d * cnt + p0) + o,
+                                 std::min(kStagePiece, (size_t)pn * 8 - o), k});
+          segs.back().pieces = k + 1;
+        }
+      } else {
+        int64_t piece = 0;
+        for (size_t off = 0; off < xbytes; off += kStagePiece) {
+          const size_t n = std::min(kStagePiece, xbytes - off);
+          while (piece < np && (size_t)std::min(cnt, (piece + 1) * P) * D * 8 <= off + n) ++piece;
+          segs.push_back(Seg{(const char *)X + off, (char *)dX + off, n, piece});
+        }
+      }
+      const int64_t nc = (int64_t)segs.size();
+      std::atomic<int64_t> sent{0};       // segments whose H2D copy has been issued (in order)
+      std::atomic<int64_t> filled[K];     // segments of buffer k that have been copied into it
       for (int k = 0; k < K; ++k) filled[k] = 0;
       std::atomic<int> bad{0};
       std::vector<std::thread> th;
@@ -654,13 +676,12 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
         th.emplace_back([&, k]() {
           cudaSetDevice(dc.device);
           for (int64_t c = k; c < nc; c += K) {
-            if (c >= K) {  // the buffer's previous chunk must have left for the device
+            if (c >= K) {  // the buffer's previous segment must have left for the device
               while (sent.load(std::memory_order_acquire) <= c - K && !bad.load() && !fd.abort.load()) std::this_thread::yield();
               if (bad.load() || fd.abort.load()) return;
               if (cudaEventSynchronize(dc.stage_in_ev[k]) != cudaSuccess) { bad = 1; return; }
             }
-            const size_t off = (size_t)c * kStagePiece, n = std::min(kStagePiece, xbytes - off);
-            std::memcpy(dc.stage_in[k], (const char *)X + off, n);
+            std::memcpy(dc.stage_in[k], segs[(size_t)c].src, segs[(size_t)c].n);
             filled[k].fetch_add(1, std::memory_order_release);
           }
         });
@@ -670,12 +691,10 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
         const int k = (int)(c % K);
         while (filled[k].load(std::memory_order_acquire) <= c / K && !bad.load() && !fd.abort.load()) std::this_thread::yield();
         if (bad.load() || fd.abort.load()) break;
-        const size_t off = (size_t)c * kStagePiece, n = std::min(kStagePiece, xbytes - off);
-        e = cudaMemcpyAsync((char *)dX + off, dc.stage_in[k], n, cudaMemcpyHostToDevice, s_in);
+        e = cudaMemcpyAsync(segs[(size_t)c].dst, dc.stage_in[k], segs[(size_t)c].n, cudaMemcpyHostToDevice, s_in);
         if (e == cudaSuccess) e = cudaEventRecord(dc.stage_in_ev[k], s_in);
         if (e == cudaSuccess) sent.store(c + 1, std::memory_order_release);
-        // pieces that are complete on the stream now
-        while (e == cudaSuccess && piece < np && (size_t)std::min(cnt, (piece + 1) * P) * D * 8 <= off + n) {
+        while (e == cudaSuccess && piece < segs[(size_t)c].pieces) {  // pieces that are complete on the stream now
           const int64_t p0 = piece * P, pn = std::min(P, cnt - p0);
           if (fvals) e = cudaMemcpyAsync(dF + p0, fvals + p0, (size_t)pn * 8, cudaMemcpyHostToDevice, s_in);
           if (e == cudaSuccess) e = cudaEventRecord(R.piece_ev[(size_t)piece], s_in);

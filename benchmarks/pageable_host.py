@@ -41,6 +41,10 @@ for name, H, M in (("cfg2", A, 10_000_000), ("cfg3", G, 20_000_000)):
     tp = timed(lambda: H.evaluate(Xp, out=op))
     th = timed(lambda: H.evaluate(Xh.numpy(), out=oh.numpy()))
     same = bool(np.array_equal(op, oh.numpy()))
-    print(json.dumps({"config": name, "points": M, "pageable_ms": tp * 1e3, "pinned_ms": th * 1e3,
-                      "pageable_points_per_s": M / tp, "pinned_points_per_s": M / th, "identical": same,
-                      "stage_host": os.environ.get("ASG_STAGE_HOST", "1")}), flush=True)
+    Xf = np.asfortranarray(Xp)                                # column-major: Julia's M x D Matrix
+    of = np.empty(M)
+    tf = timed(lambda: H.evaluate(Xf, out=of))
+    same = same and bool(np.array_equal(of, op))
+    print(json.dumps({"config": name, "points": M, "pageable_ms": tp * 1e3, "pageable_colmajor_ms": tf * 1e3,
+                      "pinned_ms": th * 1e3, "pageable_points_per_s": M / tp, "pinned_points_per_s": M / th,
+                      "identical": same, "stage_host": os.environ.get("ASG_STAGE_HOST", "1")}), flush=True)
