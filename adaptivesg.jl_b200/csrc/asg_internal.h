@@ -11,6 +11,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <new>
+#include <utility>
 #include <vector>
 
 #include "asg_cuda.h"
@@ -51,6 +53,21 @@ constexpr int kLeafTable = 8;  // last-dimension levels 1..8 are served from per
 struct HashEnt {  // open addressing, linear probing; key = pos + 1 (0 = empty)
   unsigned long long key;
   double coef;
+};
+
+// allocator whose vectors do not zero-fill on resize(n): for the large host arrays of a pack that are written in full by
+// the (threaded) passes right after -- the serial zero fill of 100+ MB was a fifth of the pack of the benchmark grid
+template <class T>
+struct NoInitAlloc {
+  using value_type = T;
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U> &) {}
+  T *allocate(size_t n) { return static_cast<T *>(::operator new(n * sizeof(T))); }
+  void deallocate(T *p, size_t) { ::operator delete(p); }
+  template <class U> void construct(U *p) { ::new ((void *)p) U; }  // default-initialisation: no fill
+  template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+  template <class U> bool operator==(const NoInitAlloc<U> &) const { return true; }
+  template <class U> bool operator!=(const NoInitAlloc<U> &) const { return false; }
 };
 
 struct SweepDim {  // one (node, dimension) of the sweep engine: phi = hat(x*s - c)
@@ -162,7 +179,7 @@ struct PackResult {
   bool blk_pair_ok = false;           // every record without kBrShared has a budget <= kBlkPairMaxR
   bool blk_wide = false;              // some record has a suffix budget above 7
   // sweep engine
-  std::vector<SweepDim> sw;
+  std::vector<SweepDim, NoInitAlloc<SweepDim>> sw;  // written in full by pack_grid's per-node pass
   std::vector<uint64_t> sw_low;
   std::vector<int32_t> depth;
 };

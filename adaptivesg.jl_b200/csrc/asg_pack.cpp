@@ -58,7 +58,7 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
 
   std::vector<uint8_t> lv;   // N x D level bytes (canonical path only)
   std::vector<uint32_t> pos; // position inside the subspace
-  std::vector<uint32_t> cells;  // N x D cell numbers (BLOCK layout)
+  std::vector<uint32_t, NoInitAlloc<uint32_t>> cells;  // N x D cell numbers (BLOCK layout); written by the per-node pass
   if (canonical) { lv.resize((size_t)N * D); pos.resize((size_t)N); cells.resize((size_t)N * D); }
 
   // per-node pass (validation, sweep words, level bytes, cells, subspace position): independent per node, so large
@@ -169,7 +169,7 @@ int pack_grid(int D, int64_t N, const int64_t *levels, const int64_t *indices, c
         int64_t n;
         bool operator<(const SortKey &o) const { return hi != o.hi ? hi < o.hi : (lo != o.lo ? lo < o.lo : n < o.n); }
       };
-      std::vector<SortKey> keys((size_t)N);
+      std::vector<SortKey, NoInitAlloc<SortKey>> keys((size_t)N);
       const int nth = pack_threads(N);
       const int64_t per = (N + nth - 1) / nth;
       pack_parallel(N, nth, [&](int, int64_t n0, int64_t n1) {

@@ -48,7 +48,7 @@ struct Writer {
     const unsigned char *p = reinterpret_cast<const unsigned char *>(&v);
     out.insert(out.end(), p, p + sizeof(T));
   }
-  template <class T> void vec(const std::vector<T> &v) {
+  template <class T, class A> void vec(const std::vector<T, A> &v) {
     pod<uint64_t>((uint64_t)v.size());
     const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
     out.insert(out.end(), p, p + v.size() * sizeof(T));
@@ -67,7 +67,7 @@ struct Reader {
     std::memcpy(&v, p, sizeof(T));
     p += sizeof(T);
   }
-  template <class T> void vec(std::vector<T> &v) {
+  template <class T, class A> void vec(std::vector<T, A> &v) {
     uint64_t n = 0;
     pod(n);
     if (!ok || n > (uint64_t)(end - p) / sizeof(T)) { ok = false; return; }
