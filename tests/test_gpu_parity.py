@@ -907,3 +907,32 @@ def test_fuzz_engines_against_oracle(asg, oracle):
             assert_close(G.evaluate(X, max_depth=L), wantm, sc, f"grid {t} D={D} depth={depth} {mode} {p} depth<={L}")
         done += 1
     assert done >= 40
+
+
+def test_pageable_staging_boundaries(asg, oracle):
+    """Pageable host buffers go through the library's pinned staging from 64 MiB of points / 8 MiB of results on
+    (asg_api.cu, eval_super / d2h_fast): sizes just below and above both limits, row- and column-major, evaluate and
+    surplus, against the same points evaluated in small calls (which take the direct path) and against the oracle."""
+    G = asg.SparseGridInterpolant(4)
+    asg.train(G, lambda X: np.sum(np.sin(2 * np.pi * X), axis=1), 7, 6, vectorized=True)
+    OG = oracle.OracleGrid(4)
+    OG.levels, OG.indices, OG.depths, OG.coefs, OG.fvals = G.levels, G.indices, G.depths, G.coefs, G.fvals
+    rng = np.random.default_rng(11)
+    Mmax = 3_000_001
+    X = rng.random((Mmax, 4))
+    X[::1013, 2] = 1.0
+    X[::7919, 0] = -0.5
+    f = rng.standard_normal(Mmax)
+    ref = np.concatenate([G.evaluate(X[i:i + 200_000]) for i in range(0, Mmax, 200_000)])
+    sel = rng.choice(Mmax, size=500, replace=False)
+    want, sc = OG.evaluate(X[sel], return_abssum=True)
+    assert_close(ref[sel], want, sc, "small calls vs oracle")
+    # 64 MiB of D = 4 points are 2 097 152 points; 8 MiB of results 1 048 576 points
+    for M in (1_048_575, 1_048_577, 2_097_151, 2_097_153, Mmax):
+        Xm = np.ascontiguousarray(X[:M])
+        y = G.evaluate(Xm)
+        assert np.array_equal(y, ref[:M]), f"row-major, M = {M}"
+        yf = G.evaluate(np.asfortranarray(Xm))
+        assert np.array_equal(yf, ref[:M]), f"column-major, M = {M}"
+        a = G.surplus(Xm, f[:M], max_depth=5)
+        assert np.array_equal(a, f[:M] - G.evaluate(Xm, max_depth=5)), f"surplus, M = {M}"
