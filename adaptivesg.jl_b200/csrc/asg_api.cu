@@ -369,6 +369,7 @@ int install_pack(asg_grid *g, PackResult &pk) {
     if (!std::isfinite(c)) { g->finite = false; break; }
   // every device of the context gets the same packed layouts (packed once on the host)
   for (int r = ctx.ndev - 1; r >= 0; --r) {
+    PackTimer t("device upload (one replica)");
     rc = device_upload(g, r, pk);
     if (rc != ASG_OK) return rc;
   }
@@ -413,16 +414,37 @@ int install_pack(asg_grid *g, PackResult &pk) {
 int copy_nodes(asg_grid *g, int64_t at, int64_t n, const int64_t *levels, const int64_t *indices, int64_t sn,
                int64_t sd, const double *coefs) {
   const int D = g->D;
+  if (sn == D && sd == 1 && n > 0) {
+    // row-major, contiguous: appended in one pass each (no zero fill first), the two large arrays side by side
+    g->levels.resize((size_t)at * D);
+    g->indices.resize((size_t)at * D);
+    g->coefs.resize((size_t)at);
+    auto app = [&](std::vector<int64_t> &v, const int64_t *p) { v.insert(v.end(), p, p + (size_t)n * D); };
+    if (n * D >= (1 << 20)) {
+      std::thread t([&]() { app(g->levels, levels); });
+      app(g->indices, indices);
+      t.join();
+    } else {
+      app(g->levels, levels);
+      app(g->indices, indices);
+    }
+    if (coefs) g->coefs.insert(g->coefs.end(), coefs, coefs + n);
+    else g->coefs.resize((size_t)(at + n), 0.0);
+    g->N = at + n;
+    return ASG_OK;
+  }
   g->levels.resize((size_t)(at + n) * D);
   g->indices.resize((size_t)(at + n) * D);
   g->coefs.resize((size_t)(at + n));
-  for (int64_t k = 0; k < n; ++k) {
-    for (int d = 0; d < D; ++d) {
-      g->levels[(size_t)(at + k) * D + d] = levels[k * sn + d * sd];
-      g->indices[(size_t)(at + k) * D + d] = indices[k * sn + d * sd];
+  pack_parallel(n, pack_threads(n), [&](int, int64_t k0, int64_t k1) {
+    for (int64_t k = k0; k < k1; ++k) {
+      for (int d = 0; d < D; ++d) {
+        g->levels[(size_t)(at + k) * D + d] = levels[k * sn + d * sd];
+        g->indices[(size_t)(at + k) * D + d] = indices[k * sn + d * sd];
+      }
+      g->coefs[(size_t)(at + k)] = coefs ? coefs[k] : 0.0;
     }
-    g->coefs[(size_t)(at + k)] = coefs ? coefs[k] : 0.0;
-  }
+  });
   g->N = at + n;
   return ASG_OK;
 }
@@ -1076,7 +1098,10 @@ int32_t asg_grid_upload(asg_grid *g, int64_t N, const int64_t *levels, const int
   std::lock_guard<std::recursive_mutex> lk(g->mu);
   g->uploaded = false;
   g->levels.clear(); g->indices.clear(); g->coefs.clear();
-  copy_nodes(g, 0, N, levels, indices, sn, sd, coefs);
+  {
+    PackTimer t("copy of the caller's node arrays");
+    copy_nodes(g, 0, N, levels, indices, sn, sd, coefs);
+  }
   return repack(g);
 }
 
