@@ -698,11 +698,12 @@ int eval_super(asg_grid *g, int r, const double *X, int64_t cnt, int64_t sp, int
         th.emplace_back([&, k]() {
           cudaSetDevice(dc.device);
           for (int64_t c = k; c < nc; c += K) {
-            if (c >= K) {  // the buffer's previous segment must have left for the device
+            if (c >= K) {  // the buffer's previous segment must have been sent on ...
               while (sent.load(std::memory_order_acquire) <= c - K && !bad.load() && !fd.abort.load()) std::this_thread::yield();
               if (bad.load() || fd.abort.load()) return;
-              if (cudaEventSynchronize(dc.stage_in_ev[k]) != cudaSuccess) { bad = 1; return; }
             }
+            // ... and have left the buffer (for the first segments: whatever an earlier, aborted call left in flight)
+            if (cudaEventSynchronize(dc.stage_in_ev[k]) != cudaSuccess) { bad = 1; return; }
             std::memcpy(dc.stage_in[k], segs[(size_t)c].src, segs[(size_t)c].n);
             filled[k].fetch_add(1, std::memory_order_release);
           }
